@@ -1,0 +1,110 @@
+/* said_b200 -- C ABI of the B200-native SAiD inference hot path (libsaid_sm100.so).
+ *
+ * Drop-in boundary: these are the entry points a host binds (ctypes in said_b200/_lib.py; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add) to replace the PyTorch-eager
+ * implementation of `SAID.inference()` (reference said/model/diffusion.py:308-472) and the modules it
+ * calls.  Plain pointers and sizes only; no C++ or torch types cross the boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; said_last_error() describes the failure
+ *     (thread-local string, valid until the next call on that thread);
+ *   - "dev" pointers are device pointers on the engine's device, borrowed for the duration of the call;
+ *     "host" pointers are ordinary host memory;
+ *   - all tensors are contiguous float32, row-major, channel-last: (clip, frame, channel);
+ *   - work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed as void*) and is
+ *     NOT synchronised before returning, except where a function says so;
+ *   - one engine per (process, device); an engine is not thread-safe; engines are independent.
+ */
+#ifndef SAID_B200_H
+#define SAID_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SAID_API __attribute__((visibility("default")))
+#else
+#define SAID_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct said_engine said_engine;
+
+/* Library / device */
+SAID_API const char* said_last_error(void);
+SAID_API int said_version(void);                                   /* ABI version, currently 1 */
+SAID_API int said_create(int device, said_engine** out);           /* fails unless the device is sm_100 */
+SAID_API void said_destroy(said_engine* e);
+
+/* Weights.  Replaces nn.Module.load_state_dict + .to(device) for the kernels' purposes
+ * (reference script/inference.py:152-159).  `name` is the reference state-dict key
+ * ("denoiser.model.input_blocks.0.0.weight", "audio_encoder.encoder.layers.3.attention.q_proj.bias",
+ * "null_cond_emb", "audio_proj_layer.weight", ...; both weight-norm spellings of the positional conv
+ * are accepted).  The data is copied.  "time_freqs" (96 floats: exp(-ln(1e4) k/96), reference
+ * said/model/ldm/util.py:75-78) must also be supplied by the host so that it is bit-identical to the
+ * value the reference computes with torch.  said_commit_weights() validates the set, infers the
+ * configuration from the shapes, repacks into the kernels' layouts and uploads. */
+SAID_API int said_set_tensor(said_engine* e, const char* name, const float* host_data, const int64_t* shape, int ndim);
+SAID_API int said_commit_weights(said_engine* e);
+/* 1 if said_commit_weights has succeeded since the last said_set_tensor */
+SAID_API int said_weights_ready(const said_engine* e);
+/* configuration inferred at commit: in_channels, context dim seen by the denoiser, encoder hidden size */
+SAID_API int said_get_config(const said_engine* e, int* in_channels, int* ctx_dim, int* enc_hidden);
+
+/* Audio encoder: SAID.get_audio_embedding (reference said/model/diffusion.py:209-230 ->
+ * said/model/wav2vec2.py:14-82): processed waveform (B, T_a) -> features (B, T, ctx_dim). */
+SAID_API int said_encode_audio(said_engine* e, const float* wave_dev, int B, int T_a, int T, float* emb_out_dev, void* stream);
+
+/* Hoist of everything the step loop needs from the audio features: cross-attention keys/values of all
+ * four transformer blocks (reference said/model/ldm/attention.py:90-91 evaluates them on every step)
+ * and, when with_uncond != 0, the constant value vector of the null-condition branch
+ * (reference diffusion.py:397-400).  emb_dev: (B, T, ctx_dim). */
+SAID_API int said_prepare_context(said_engine* e, const float* emb_dev, int B, int T, int with_uncond, void* stream);
+
+/* The denoising loop (reference diffusion.py:409-470). */
+typedef struct said_denoise_args {
+    int B, T, n_steps;              /* clips, frames, loop iterations actually run (after strength) */
+    const float* timesteps_host;    /* (n_steps) timestep of each iteration, as float */
+    const float* step_table_host;   /* (n_steps, 8): sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), dir coef, sigma,
+                                       clip range (<0: no clipping), blend sqrt(a_next), blend sqrt(1-a_next) */
+    int prediction_type;            /* 0 epsilon, 1 sample, 2 v_prediction */
+    int do_cfg;                     /* guidance_scale > 1: two denoiser branches per clip */
+    float guidance_scale, guidance_rescale;
+    float latent_scale;
+    const float* init_src_dev;      /* (B,T,C): the randn draw (generation) or init_samples (editing) */
+    float init_scale;               /* latent_scale * init_noise_sigma (diffusion.py:370) */
+    const float* edit_noise_dev;    /* (B,T,C) or NULL: noise added to init_samples (diffusion.py:376-385) */
+    float edit_sqrt_a, edit_sqrt_b; /* add_noise coefficients at the starting timestep */
+    const float* mask_dev;          /* (B,T,C) or NULL: 1 = keep init_samples (diffusion.py:446-456) */
+    const float* eta_noise_dev;     /* (n_steps,B,T,C) or NULL: variance noise for eta > 0 */
+    float* intermediates_dev;       /* (n_steps,B,T,C) or NULL: latents/latent_scale before each step */
+    float* result_dev;              /* (B,T,C): clamp(latents/latent_scale, 0, 1) */
+    float* latents_out_dev;         /* (B,T,C) or NULL: final latents before the clamp */
+    int use_graph;                  /* replay one captured CUDA graph per step */
+} said_denoise_args;
+SAID_API int said_denoise(said_engine* e, const said_denoise_args* args, void* stream);
+
+/* One denoiser forward: SAID.forward / UNet1DConditionModel.forward (reference
+ * said/model/diffusion.py:127-155, said/model/unet_1d_condition.py:51-77).
+ * x_dev (Bp,T,C), timesteps_host (Bp) as float, ctx_dev (Bp,T,ctx_dim) -> out_dev (Bp,T,C).
+ * taps_dev (optional, 10 x (Bp,T,192)): outputs of the ten UNet blocks in execution order (parity tests).
+ * Synchronises the stream before returning. */
+SAID_API int said_denoiser_forward(said_engine* e, const float* x_dev, const float* timesteps_host, const float* ctx_dev,
+                          int Bp, int T, float* out_dev, float* taps_dev, void* stream);
+
+/* Unit entry points used by the parity tests (each is one kernel of the path). */
+SAID_API int said_op_ddim_step(said_engine* e, const float* pred_dev, float* latents_dev, int B, int n, int do_cfg,
+                      float guidance_scale, float guidance_rescale, int prediction_type, const float* row8_host,
+                      const float* eta_noise_dev, void* stream);
+SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, int heads, int head_dim,
+                           float* out_dev, void* stream);
+
+/* Number of kernels this engine has launched (graph replays counted node by node). */
+SAID_API long long said_launch_count(const said_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAID_B200_H */

@@ -1,0 +1,279 @@
+"""ctypes binding of ``libsaid_sm100.so`` (C ABI declared in ``include/said_b200.h``).
+
+This is the only place Python touches the native library.  There is no fallback: if the shared
+library is missing or the device is not sm_100, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsaid_sm100.so")
+
+# every symbol include/said_b200.h declares (tests check the .so exports exactly these)
+EXPORTED_SYMBOLS = (
+    "said_last_error",
+    "said_version",
+    "said_create",
+    "said_destroy",
+    "said_set_tensor",
+    "said_commit_weights",
+    "said_weights_ready",
+    "said_get_config",
+    "said_encode_audio",
+    "said_prepare_context",
+    "said_denoise",
+    "said_denoiser_forward",
+    "said_op_ddim_step",
+    "said_op_self_attention",
+    "said_launch_count",
+)
+
+
+class DenoiseArgs(ctypes.Structure):
+    """``said_denoise_args`` (include/said_b200.h)."""
+
+    _fields_ = [
+        ("B", ctypes.c_int),
+        ("T", ctypes.c_int),
+        ("n_steps", ctypes.c_int),
+        ("timesteps_host", ctypes.c_void_p),
+        ("step_table_host", ctypes.c_void_p),
+        ("prediction_type", ctypes.c_int),
+        ("do_cfg", ctypes.c_int),
+        ("guidance_scale", ctypes.c_float),
+        ("guidance_rescale", ctypes.c_float),
+        ("latent_scale", ctypes.c_float),
+        ("init_src_dev", ctypes.c_void_p),
+        ("init_scale", ctypes.c_float),
+        ("edit_noise_dev", ctypes.c_void_p),
+        ("edit_sqrt_a", ctypes.c_float),
+        ("edit_sqrt_b", ctypes.c_float),
+        ("mask_dev", ctypes.c_void_p),
+        ("eta_noise_dev", ctypes.c_void_p),
+        ("intermediates_dev", ctypes.c_void_p),
+        ("result_dev", ctypes.c_void_p),
+        ("latents_out_dev", ctypes.c_void_p),
+        ("use_graph", ctypes.c_int),
+    ]
+
+
+class SaidLibraryError(RuntimeError):
+    pass
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the native library or raise -- never falls back to anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SaidLibraryError(
+            f"{LIB_PATH} is not built. Build it with `make -C said_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`); said_b200 has no non-CUDA path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.said_last_error.restype = ctypes.c_char_p
+    lib.said_last_error.argtypes = []
+    lib.said_version.restype = ci
+    lib.said_create.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.said_destroy.argtypes = [vp]
+    lib.said_destroy.restype = None
+    lib.said_set_tensor.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
+    lib.said_commit_weights.argtypes = [vp]
+    lib.said_weights_ready.argtypes = [vp]
+    lib.said_get_config.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.said_encode_audio.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.said_prepare_context.argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.said_denoise.argtypes = [vp, ctypes.POINTER(DenoiseArgs), vp]
+    lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp]
+    lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, vp]
+    lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
+    lib.said_launch_count.argtypes = [vp]
+    lib.said_launch_count.restype = ctypes.c_longlong
+    _lib = lib
+    return lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_dev(t: torch.Tensor, device: torch.device, name: str) -> torch.Tensor:
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, the engine runs on {device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+class Engine:
+    """One native engine on one CUDA device."""
+
+    def __init__(self, device: torch.device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise SaidLibraryError(f"said_b200 runs on CUDA sm_100a devices only (got device '{device}')")
+        self.lib = load_library()
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        h = ctypes.c_void_p()
+        self._h = None
+        self._call(self.lib.said_create(self.device.index, ctypes.byref(h)))
+        self._h = h
+        self._keep: list = []
+
+    def _call(self, rc: int) -> None:
+        if rc != 0:
+            raise SaidLibraryError(self.lib.said_last_error().decode("utf-8", "replace"))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.said_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ weights
+    def set_tensor(self, name: str, value: torch.Tensor) -> None:
+        a = np.ascontiguousarray(value.detach().to("cpu", torch.float32).numpy())
+        shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+        self._call(self.lib.said_set_tensor(self._h, name.encode(), a.ctypes.data, shape, a.ndim))
+
+    def load_weights(self, tensors: Dict[str, torch.Tensor]) -> None:
+        for k, v in tensors.items():
+            self.set_tensor(k, v)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_commit_weights(self._h))
+
+    def config(self):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._call(self.lib.said_get_config(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"in_channels": a.value, "ctx_dim": b.value, "enc_hidden": c.value}
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.said_launch_count(self._h))
+
+    # ------------------------------------------------------------------ phases
+    def encode_audio(self, wave: torch.Tensor, num_frames: int) -> torch.Tensor:
+        wave = _check_dev(wave, self.device, "waveform")
+        B, T_a = wave.shape
+        out = torch.empty((B, num_frames, self.config()["ctx_dim"]), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_encode_audio(self._h, wave.data_ptr(), B, T_a, num_frames, out.data_ptr(), self._stream()))
+        return out
+
+    def prepare_context(self, emb: torch.Tensor, with_uncond: bool) -> None:
+        emb = _check_dev(emb, self.device, "audio embedding")
+        B, T, _ = emb.shape
+        self._keep = [emb]
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_prepare_context(self._h, emb.data_ptr(), B, T, int(with_uncond), self._stream()))
+
+    def denoise(
+        self,
+        init_src: torch.Tensor,
+        timesteps: Sequence[int],
+        step_table: np.ndarray,
+        prediction_type: int,
+        do_cfg: bool,
+        guidance_scale: float,
+        guidance_rescale: float,
+        latent_scale: float,
+        init_scale: float,
+        edit_noise: Optional[torch.Tensor] = None,
+        edit_coefs=(1.0, 0.0),
+        mask: Optional[torch.Tensor] = None,
+        eta_noise: Optional[torch.Tensor] = None,
+        intermediates: Optional[torch.Tensor] = None,
+        latents_out: Optional[torch.Tensor] = None,
+        use_graph: bool = True,
+    ) -> torch.Tensor:
+        init_src = _check_dev(init_src, self.device, "initial latents")
+        B, T, C = init_src.shape
+        n_steps = len(timesteps)
+        ts = np.ascontiguousarray(np.asarray(timesteps, dtype=np.float32))
+        tab = np.ascontiguousarray(step_table, dtype=np.float32).reshape(n_steps, 8)
+        result = torch.empty((B, T, C), dtype=torch.float32, device=self.device)
+        opt = {}
+        for name, t in (("edit_noise", edit_noise), ("mask", mask), ("eta_noise", eta_noise)):
+            opt[name] = None if t is None else _check_dev(t, self.device, name)
+        for name, t in (("intermediates", intermediates), ("latents_out", latents_out)):
+            if t is not None and (t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous float32 tensor on {self.device}")
+        a = DenoiseArgs(
+            B=B, T=T, n_steps=n_steps,
+            timesteps_host=ts.ctypes.data if n_steps else None,
+            step_table_host=tab.ctypes.data if n_steps else None,
+            prediction_type=int(prediction_type), do_cfg=int(bool(do_cfg)),
+            guidance_scale=float(guidance_scale), guidance_rescale=float(guidance_rescale),
+            latent_scale=float(latent_scale),
+            init_src_dev=init_src.data_ptr(), init_scale=float(init_scale),
+            edit_noise_dev=_ptr(opt["edit_noise"]), edit_sqrt_a=float(edit_coefs[0]), edit_sqrt_b=float(edit_coefs[1]),
+            mask_dev=_ptr(opt["mask"]), eta_noise_dev=_ptr(opt["eta_noise"]),
+            intermediates_dev=_ptr(intermediates), result_dev=result.data_ptr(),
+            latents_out_dev=_ptr(latents_out), use_graph=int(bool(use_graph)),
+        )
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_denoise(self._h, ctypes.byref(a), self._stream()))
+        # the kernels read these asynchronously; keep them alive until the caller synchronises / next call
+        self._keep = [init_src, opt, intermediates, latents_out, result] + self._keep[:1]
+        return result
+
+    def denoiser_forward(self, x: torch.Tensor, timesteps: torch.Tensor, ctx: torch.Tensor, taps: bool = False):
+        x = _check_dev(x, self.device, "noisy samples")
+        ctx = _check_dev(ctx, self.device, "audio embedding")
+        Bp, T, C = x.shape
+        if ctx.shape[0] != Bp or ctx.shape[1] != T:
+            raise ValueError(
+                f"audio embedding must be (batch={Bp}, frames={T}, dim); got {tuple(ctx.shape)} "
+                "(the aligned cross-attention kernel needs one feature frame per coefficient frame)"
+            )
+        ts = np.ascontiguousarray(timesteps.detach().to("cpu").reshape(-1).numpy().astype(np.float32))
+        if ts.shape[0] == 1 and Bp > 1:
+            ts = np.repeat(ts, Bp)
+        if ts.shape[0] != Bp:
+            raise ValueError(f"timesteps must have 1 or {Bp} entries, got {ts.shape[0]}")
+        out = torch.empty_like(x)
+        tap_buf = torch.empty((10, Bp, T, 192), dtype=torch.float32, device=self.device) if taps else None
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_denoiser_forward(self._h, x.data_ptr(), ts.ctypes.data, ctx.data_ptr(), Bp, T,
+                                                      out.data_ptr(), _ptr(tap_buf), self._stream()))
+        return (out, tap_buf) if taps else out
+
+    # ------------------------------------------------------------------ unit ops (tests)
+    def op_ddim_step(self, pred, latents, do_cfg, guidance_scale, guidance_rescale, prediction_type, row8, eta_noise=None):
+        pred = _check_dev(pred, self.device, "pred")
+        latents = _check_dev(latents, self.device, "latents").clone()
+        B = latents.shape[0]
+        n = latents[0].numel()
+        row = np.ascontiguousarray(row8, dtype=np.float32)
+        en = None if eta_noise is None else _check_dev(eta_noise, self.device, "eta_noise")
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_op_ddim_step(self._h, pred.data_ptr(), latents.data_ptr(), B, n, int(do_cfg),
+                                                  float(guidance_scale), float(guidance_rescale), int(prediction_type),
+                                                  row.ctypes.data, _ptr(en), self._stream()))
+            torch.cuda.synchronize(self.device)
+        return latents
+
+    def op_self_attention(self, qkv: torch.Tensor, heads: int, head_dim: int) -> torch.Tensor:
+        qkv = _check_dev(qkv, self.device, "qkv")
+        B, T, W = qkv.shape
+        assert W == 3 * heads * head_dim
+        out = torch.empty((B, T, heads * head_dim), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_op_self_attention(self._h, qkv.data_ptr(), B, T, heads, head_dim, out.data_ptr(), self._stream()))
+        return out

@@ -1,0 +1,1142 @@
+// libsaid_sm100.so -- engine and C ABI of the B200-native SAiD inference hot path.
+//
+// Host-side "program" for the three device phases of SAID.inference() (reference
+// said/model/diffusion.py:308-472):
+//   encode_audio     Wav2Vec2 feature encoder + transformer        (said/model/wav2vec2.py:14-82)
+//   prepare_context  cross-attention K/V of all 4 blocks, hoisted   (said/model/ldm/attention.py:90-91)
+//   denoise          N x [UNet1D forward (both CFG branches) + CFG combine + scheduler step + blend]
+// Every arithmetic op is a hand-written kernel from the .cuh files next to this one; this file only
+// sequences launches, owns workspaces and packs weights.  No cuBLAS / cuDNN / torch.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/said_b200.h"
+#include "attention.cuh"
+#include "diffusion_kernels.cuh"
+#include "encoder_kernels.cuh"
+#include "gemm_simt.cuh"
+#include "norm_kernels.cuh"
+
+using namespace said;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) {
+    g_err = m;
+    return 1;
+}
+#define CK(x)                                                                                              \
+    do {                                                                                                   \
+        cudaError_t _e = (x);                                                                              \
+        if (_e != cudaSuccess) return fail(std::string(__FILE__) + ":" + std::to_string(__LINE__) + " " +  \
+                                           #x + ": " + cudaGetErrorString(_e));                            \
+    } while (0)
+#define CKI(x)                      \
+    do {                            \
+        int _r = (x);               \
+        if (_r != 0) return _r;     \
+    } while (0)
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+    int64_t numel() const { return (int64_t)data.size(); }
+};
+
+struct DevBuf {
+    float* p = nullptr;
+    size_t cap = 0;   // floats
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(float));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+constexpr int C = 192;        // model_channels (unet_1d_condition.py:40)
+constexpr int HEADS = 6;
+constexpr int HD = 32;
+constexpr int FF = 768;       // GEGLU inner width (attention.py:36-38)
+constexpr int TE = 768;       // time_embed_dim
+
+struct ResBlockW {
+    int cin = C;
+    bool skip = false;
+    int k2 = 3 * C;            // contraction of the second conv (+ cin when the 1x1 skip is fused in)
+    float *gn1_g, *gn1_b, *w1, *b1, *gn2_g, *gn2_b, *w2, *b2;
+};
+struct TransformerW {
+    float *gn_g, *gn_b, *ln1_g, *ln1_b, *wqkv, *wo1, *bo1, *ln2_g, *ln2_b, *wq2, *wo2, *bo2;
+    float *ln3_g, *ln3_b, *wff1, *bff1, *wff2, *bff2, *wproj, *bproj;
+};
+struct EncLayerW {
+    float *wqkv, *bqkv, *wo, *bo, *ln1_g, *ln1_b, *wff1, *bff1, *wff2, *bff2, *ln2_g, *ln2_b;
+};
+
+}  // namespace
+
+struct said_engine {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    long long launches = 0;
+
+    std::map<std::string, HostTensor> raw;
+    bool ready = false;
+    std::vector<float*> arena;   // device allocations holding packed weights
+
+    // ---- configuration (inferred at commit) ----
+    int in_ch = 32, ctx_dim = 768;
+    int enc_hidden = 768, enc_layers = 12, enc_heads = 12, enc_ffn = 3072, enc_conv_dim = 512;
+    int n_conv = 7, conv_k[8] = {10, 3, 3, 3, 3, 2, 2, 0}, conv_s[8] = {5, 2, 2, 2, 2, 2, 2, 0};
+    int pos_k = 128, pos_g = 16;
+    int proj_dim = 0;            // audio_proj_layer output width (0: absent)
+
+    // ---- packed denoiser weights ----
+    TimeEmbedWeights te{};
+    float *w_in = nullptr, *b_in = nullptr;
+    ResBlockW rb[5];
+    TransformerW tr[4];
+    float *out_gn_g = nullptr, *out_gn_b = nullptr, *w_out = nullptr, *b_out = nullptr;
+    float *w_kv = nullptr;       // (ctx_dim, 4*384): per block [K(192) | V(192)]
+    float *null_emb = nullptr;   // (ctx_dim)
+    float *w_aproj = nullptr, *b_aproj = nullptr;
+
+    // ---- packed encoder weights ----
+    float *c0_w = nullptr, *c0_g = nullptr, *c0_b = nullptr;
+    float *conv_w[8] = {nullptr};
+    float *fp_ln_g = nullptr, *fp_ln_b = nullptr, *fp_w = nullptr, *fp_b = nullptr;
+    float *pos_w = nullptr, *pos_b = nullptr, *enc_ln_g = nullptr, *enc_ln_b = nullptr;
+    std::vector<EncLayerW> enc;
+
+    // ---- workspaces ----
+    DevBuf act[7], qkv, ao, q2, ffb, eps, ss, ss_st, emb_tab, tvals, step_tab, kv, vnull, lat, init_lat, vnull_tmp;
+    DevBuf e_a, e_b, e_c, e_d, e_qkv, e_ff, e_xp, e_emb;
+    double* c0_partial = nullptr;
+    size_t c0_partial_cap = 0;
+    int* step_ctr = nullptr;
+    int ctx_B = 0, ctx_T = 0, ctx_uncond = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+
+    ~said_engine() {
+        cudaSetDevice(device);
+        cudaDeviceSynchronize();
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        for (float* p : arena) cudaFree(p);
+        if (c0_partial) cudaFree(c0_partial);
+        if (step_ctr) cudaFree(step_ctr);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    // ------------------------------------------------------------------ weights
+    const HostTensor* find(const std::string& name) const {
+        auto it = raw.find(name);
+        return it == raw.end() ? nullptr : &it->second;
+    }
+    int need(const std::string& name, std::initializer_list<int64_t> shape, const HostTensor** out) {
+        const HostTensor* t = find(name);
+        if (!t) return fail("missing tensor '" + name + "'");
+        std::vector<int64_t> want(shape);
+        if (t->shape != want) {
+            std::string s = "tensor '" + name + "' has shape (";
+            for (auto d : t->shape) s += std::to_string(d) + ",";
+            s += ") expected (";
+            for (auto d : want) s += std::to_string(d) + ",";
+            return fail(s + ")");
+        }
+        *out = t;
+        return 0;
+    }
+    int upload(const std::vector<float>& h, float** dptr) {
+        float* d = nullptr;
+        CK(cudaMalloc((void**)&d, std::max<size_t>(h.size(), 4) * sizeof(float)));
+        arena.push_back(d);
+        CK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        *dptr = d;
+        return 0;
+    }
+    int upload_raw(const std::string& name, std::initializer_list<int64_t> shape, float** dptr) {
+        const HostTensor* t;
+        CKI(need(name, shape, &t));
+        return upload(t->data, dptr);
+    }
+    int commit();
+    int commit_denoiser();
+    int commit_encoder();
+
+    // ------------------------------------------------------------------ programs
+    int encode_audio(const float* wave, int B, int T_a, int T, float* emb_out, cudaStream_t st);
+    int prepare_context(const float* emb, int B, int T, int with_uncond, cudaStream_t st);
+    int ensure_denoiser_ws(int Bp, int T);
+    int forward(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T, const float* emb_table,
+                const int* step_ptr, float* eps_out, float* taps);
+    int denoise(const said_denoise_args& a, cudaStream_t user);
+};
+
+// =====================================================================================================
+// Weight packing (host side, one-off)
+// =====================================================================================================
+namespace {
+
+// Linear / Conv1d weight (Co, Ci, KT) -> K-major "Wt": dst[(row_off + tap*Ci + ci) * ldd + col_off + co]
+void pack_w(const HostTensor& w, int Co, int Ci, int KT, std::vector<float>& dst, int ldd, int row_off, int col_off) {
+    const float* s = w.data.data();
+    for (int co = 0; co < Co; ++co)
+        for (int ci = 0; ci < Ci; ++ci)
+            for (int tap = 0; tap < KT; ++tap)
+                dst[(size_t)(row_off + tap * Ci + ci) * ldd + col_off + co] = s[((size_t)co * Ci + ci) * KT + tap];
+}
+
+}  // namespace
+
+int said_engine::commit_denoiser() {
+    const std::string P = "denoiser.model.";
+    const HostTensor* t;
+    // ---- shapes -> configuration
+    const HostTensor* win = find(P + "input_blocks.0.0.weight");
+    if (!win || win->shape.size() != 3 || win->shape[0] != C || win->shape[2] != 3)
+        return fail("denoiser.model.input_blocks.0.0.weight missing or not (192, in_channels, 3)");
+    in_ch = (int)win->shape[1];
+    if (in_ch % 4 != 0 || (3 * in_ch) % GEMM_BK != 0) return fail("in_channels must make 3*in_channels a multiple of 16");
+    const HostTensor* wk = find(P + "input_blocks.1.1.transformer_blocks.0.attn2.to_k.weight");
+    if (!wk || wk->shape.size() != 2 || wk->shape[0] != C) return fail("attn2.to_k.weight missing or malformed");
+    ctx_dim = (int)wk->shape[1];
+    if (ctx_dim % GEMM_BK != 0) return fail("context dim must be a multiple of 16");
+
+    // ---- time embedding
+    CKI(upload_raw("time_freqs", {C / 2}, (float**)&te.freqs));
+    CKI(upload_raw(P + "time_embed.0.weight", {TE, C}, (float**)&te.w1));
+    CKI(upload_raw(P + "time_embed.0.bias", {TE}, (float**)&te.b1));
+    CKI(upload_raw(P + "time_embed.2.weight", {TE, TE}, (float**)&te.w2));
+    CKI(upload_raw(P + "time_embed.2.bias", {TE}, (float**)&te.b2));
+
+    // ---- input conv
+    {
+        std::vector<float> w((size_t)3 * in_ch * C);
+        pack_w(*win, C, in_ch, 3, w, C, 0, 0);
+        CKI(upload(w, &w_in));
+        CKI(upload_raw(P + "input_blocks.0.0.bias", {C}, &b_in));
+    }
+    // ---- ResBlocks in execution order (openaimodel.py:697-704)
+    const char* rb_paths[5] = {"input_blocks.1.0", "middle_block.0", "middle_block.2", "output_blocks.0.0", "output_blocks.1.0"};
+    const int rb_cin[5] = {C, C, C, 2 * C, 2 * C};
+    for (int i = 0; i < 5; ++i) {
+        ResBlockW& r = rb[i];
+        const std::string p = P + rb_paths[i] + ".";
+        r.cin = rb_cin[i];
+        r.skip = r.cin != C;
+        CKI(upload_raw(p + "in_layers.0.weight", {r.cin}, &r.gn1_g));
+        CKI(upload_raw(p + "in_layers.0.bias", {r.cin}, &r.gn1_b));
+        CKI(need(p + "in_layers.2.weight", {C, r.cin, 3}, &t));
+        std::vector<float> w1((size_t)3 * r.cin * C);
+        pack_w(*t, C, r.cin, 3, w1, C, 0, 0);
+        CKI(upload(w1, &r.w1));
+        CKI(upload_raw(p + "in_layers.2.bias", {C}, &r.b1));
+        CKI(upload_raw(p + "emb_layers.1.weight", {C, TE}, (float**)&te.wr[i]));
+        CKI(upload_raw(p + "emb_layers.1.bias", {C}, (float**)&te.br[i]));
+        CKI(upload_raw(p + "out_layers.0.weight", {C}, &r.gn2_g));
+        CKI(upload_raw(p + "out_layers.0.bias", {C}, &r.gn2_b));
+        CKI(need(p + "out_layers.3.weight", {C, C, 3}, &t));
+        r.k2 = 3 * C + (r.skip ? r.cin : 0);
+        std::vector<float> w2((size_t)r.k2 * C);
+        pack_w(*t, C, C, 3, w2, C, 0, 0);
+        CKI(need(p + "out_layers.3.bias", {C}, &t));
+        std::vector<float> b2 = t->data;
+        if (r.skip) {   // 1x1 skip_connection fused as extra contraction rows; biases add
+            CKI(need(p + "skip_connection.weight", {C, r.cin, 1}, &t));
+            pack_w(*t, C, r.cin, 1, w2, C, 3 * C, 0);
+            CKI(need(p + "skip_connection.bias", {C}, &t));
+            for (int j = 0; j < C; ++j) b2[j] += t->data[j];
+        }
+        CKI(upload(w2, &r.w2));
+        CKI(upload(b2, &r.b2));
+    }
+    // ---- SpatialTransformers in execution order
+    const char* tr_paths[4] = {"input_blocks.1.1", "middle_block.1", "output_blocks.0.1", "output_blocks.1.1"};
+    std::vector<float> wkv((size_t)ctx_dim * 4 * 2 * C);
+    for (int i = 0; i < 4; ++i) {
+        TransformerW& s = tr[i];
+        const std::string p = P + tr_paths[i] + ".";
+        const std::string b = p + "transformer_blocks.0.";
+        CKI(upload_raw(p + "norm.weight", {C}, &s.gn_g));
+        CKI(upload_raw(p + "norm.bias", {C}, &s.gn_b));
+        CKI(upload_raw(b + "norm1.weight", {C}, &s.ln1_g));
+        CKI(upload_raw(b + "norm1.bias", {C}, &s.ln1_b));
+        CKI(upload_raw(b + "norm2.weight", {C}, &s.ln2_g));
+        CKI(upload_raw(b + "norm2.bias", {C}, &s.ln2_b));
+        CKI(upload_raw(b + "norm3.weight", {C}, &s.ln3_g));
+        CKI(upload_raw(b + "norm3.bias", {C}, &s.ln3_b));
+        std::vector<float> qkvw((size_t)C * 3 * C);
+        const char* nm[3] = {"attn1.to_q.weight", "attn1.to_k.weight", "attn1.to_v.weight"};
+        for (int j = 0; j < 3; ++j) {
+            CKI(need(b + nm[j], {C, C}, &t));
+            pack_w(*t, C, C, 1, qkvw, 3 * C, 0, j * C);
+        }
+        CKI(upload(qkvw, &s.wqkv));
+        std::vector<float> w((size_t)C * C);
+        CKI(need(b + "attn1.to_out.0.weight", {C, C}, &t));
+        pack_w(*t, C, C, 1, w, C, 0, 0);
+        CKI(upload(w, &s.wo1));
+        CKI(upload_raw(b + "attn1.to_out.0.bias", {C}, &s.bo1));
+        CKI(need(b + "attn2.to_q.weight", {C, C}, &t));
+        pack_w(*t, C, C, 1, w, C, 0, 0);
+        CKI(upload(w, &s.wq2));
+        CKI(need(b + "attn2.to_out.0.weight", {C, C}, &t));
+        pack_w(*t, C, C, 1, w, C, 0, 0);
+        CKI(upload(w, &s.wo2));
+        CKI(upload_raw(b + "attn2.to_out.0.bias", {C}, &s.bo2));
+        CKI(need(b + "attn2.to_k.weight", {C, ctx_dim}, &t));
+        pack_w(*t, C, ctx_dim, 1, wkv, 8 * C, 0, i * 2 * C);
+        CKI(need(b + "attn2.to_v.weight", {C, ctx_dim}, &t));
+        pack_w(*t, C, ctx_dim, 1, wkv, 8 * C, 0, i * 2 * C + C);
+        // GEGLU projection: interleave (value_j, gate_j) columns (attention.py:31-32: value = first half)
+        CKI(need(b + "ff.net.0.proj.weight", {2 * FF, C}, &t));
+        std::vector<float> wff1((size_t)C * 2 * FF), bff1((size_t)2 * FF);
+        for (int o = 0; o < 2 * FF; ++o) {
+            const int col = o < FF ? 2 * o : 2 * (o - FF) + 1;
+            for (int k = 0; k < C; ++k) wff1[(size_t)k * 2 * FF + col] = t->data[(size_t)o * C + k];
+        }
+        CKI(upload(wff1, &s.wff1));
+        CKI(need(b + "ff.net.0.proj.bias", {2 * FF}, &t));
+        for (int o = 0; o < 2 * FF; ++o) bff1[o < FF ? 2 * o : 2 * (o - FF) + 1] = t->data[o];
+        CKI(upload(bff1, &s.bff1));
+        CKI(need(b + "ff.net.2.weight", {C, FF}, &t));
+        std::vector<float> wff2((size_t)FF * C);
+        pack_w(*t, C, FF, 1, wff2, C, 0, 0);
+        CKI(upload(wff2, &s.wff2));
+        CKI(upload_raw(b + "ff.net.2.bias", {C}, &s.bff2));
+        CKI(need(p + "proj_out.weight", {C, C, 1}, &t));
+        pack_w(*t, C, C, 1, w, C, 0, 0);
+        CKI(upload(w, &s.wproj));
+        CKI(upload_raw(p + "proj_out.bias", {C}, &s.bproj));
+    }
+    CKI(upload(wkv, &w_kv));
+    // ---- output head
+    CKI(upload_raw(P + "out.0.weight", {C}, &out_gn_g));
+    CKI(upload_raw(P + "out.0.bias", {C}, &out_gn_b));
+    CKI(need(P + "out.2.weight", {in_ch, C, 3}, &t));
+    std::vector<float> wo((size_t)3 * C * in_ch);
+    pack_w(*t, in_ch, C, 3, wo, in_ch, 0, 0);
+    CKI(upload(wo, &w_out));
+    CKI(upload_raw(P + "out.2.bias", {in_ch}, &b_out));
+    // ---- null condition, optional audio projection
+    CKI(need("null_cond_emb", {1, 1, ctx_dim}, &t));
+    CKI(upload(t->data, &null_emb));
+    proj_dim = 0;
+    if (const HostTensor* pw = find("audio_proj_layer.weight")) {
+        if (pw->shape.size() != 2) return fail("audio_proj_layer.weight malformed");
+        proj_dim = (int)pw->shape[0];
+        const int kin = (int)pw->shape[1];
+        if (proj_dim != ctx_dim) return fail("audio_proj_layer output width != denoiser context dim");
+        std::vector<float> w((size_t)kin * proj_dim);
+        pack_w(*pw, proj_dim, kin, 1, w, proj_dim, 0, 0);
+        CKI(upload(w, &w_aproj));
+        CKI(upload_raw("audio_proj_layer.bias", {proj_dim}, &b_aproj));
+    }
+    return 0;
+}
+
+int said_engine::commit_encoder() {
+    const std::string P = "audio_encoder.";
+    const HostTensor* t;
+    // ---- feature encoder (TF modeling_wav2vec2.py:254-323, 382-419)
+    n_conv = 0;
+    while (find(P + "feature_extractor.conv_layers." + std::to_string(n_conv) + ".conv.weight")) ++n_conv;
+    if (n_conv != 7) return fail("audio encoder: expected 7 conv feature layers (wav2vec2-base family), found " + std::to_string(n_conv));
+    const int ks[7] = {10, 3, 3, 3, 3, 2, 2};
+    CKI(need(P + "feature_extractor.conv_layers.0.conv.weight", {C0_CH, 1, C0_K}, &t));
+    enc_conv_dim = C0_CH;
+    {
+        std::vector<float> w((size_t)C0_K * C0_CH);
+        for (int c = 0; c < C0_CH; ++c)
+            for (int k = 0; k < C0_K; ++k) w[(size_t)k * C0_CH + c] = t->data[(size_t)c * C0_K + k];
+        CKI(upload(w, &c0_w));
+    }
+    if (find(P + "feature_extractor.conv_layers.0.conv.bias")) return fail("audio encoder: conv_bias=True is not supported");
+    if (find(P + "feature_extractor.conv_layers.1.layer_norm.weight"))
+        return fail("audio encoder: feat_extract_norm='layer' is not supported (wav2vec2-base family only)");
+    CKI(upload_raw(P + "feature_extractor.conv_layers.0.layer_norm.weight", {C0_CH}, &c0_g));
+    CKI(upload_raw(P + "feature_extractor.conv_layers.0.layer_norm.bias", {C0_CH}, &c0_b));
+    for (int i = 1; i < 7; ++i) {
+        conv_k[i] = ks[i];
+        CKI(need(P + "feature_extractor.conv_layers." + std::to_string(i) + ".conv.weight", {C0_CH, C0_CH, ks[i]}, &t));
+        std::vector<float> w((size_t)ks[i] * C0_CH * C0_CH);
+        pack_w(*t, C0_CH, C0_CH, ks[i], w, C0_CH, 0, 0);
+        CKI(upload(w, &conv_w[i]));
+    }
+    // ---- feature projection
+    const HostTensor* pw = find(P + "feature_projection.projection.weight");
+    if (!pw || pw->shape.size() != 2 || pw->shape[1] != C0_CH) return fail("feature_projection.projection.weight missing or malformed");
+    enc_hidden = (int)pw->shape[0];
+    const int H = enc_hidden;
+    if (H % 64 != 0 || H > 1024) return fail("audio encoder: hidden size must be a multiple of 64 and <= 1024");
+    enc_heads = H / 64;
+    CKI(upload_raw(P + "feature_projection.layer_norm.weight", {C0_CH}, &fp_ln_g));
+    CKI(upload_raw(P + "feature_projection.layer_norm.bias", {C0_CH}, &fp_ln_b));
+    {
+        std::vector<float> w((size_t)C0_CH * H);
+        pack_w(*pw, H, C0_CH, 1, w, H, 0, 0);
+        CKI(upload(w, &fp_w));
+        CKI(upload_raw(P + "feature_projection.projection.bias", {H}, &fp_b));
+    }
+    // ---- positional conv: fold weight norm (w = v * g / ||v||, norm over (out, in) per tap), regroup
+    {
+        const std::string pc = P + "encoder.pos_conv_embed.conv.";
+        const HostTensor* g = find(pc + "weight_g");
+        const HostTensor* v = find(pc + "weight_v");
+        if (!g) g = find(pc + "parametrizations.weight.original0");
+        if (!v) v = find(pc + "parametrizations.weight.original1");
+        if (!g || !v || v->shape.size() != 3 || v->shape[0] != H) return fail("pos_conv_embed weight_g / weight_v missing or malformed");
+        const int cg = (int)v->shape[1];
+        pos_k = (int)v->shape[2];
+        if (H % cg != 0) return fail("pos_conv_embed: hidden not divisible by group width");
+        pos_g = H / cg;
+        if (g->numel() != pos_k) return fail("pos_conv_embed weight_g must have one entry per kernel tap");
+        if (pos_k % 2 != 0) return fail("pos_conv_embed: odd kernel sizes are not supported");
+        if (cg % 4 != 0 || (pos_k * cg) % GEMM_BK != 0) return fail("pos_conv_embed: unsupported group width");
+        std::vector<double> nrm(pos_k, 0.0);
+        for (int co = 0; co < H; ++co)
+            for (int ci = 0; ci < cg; ++ci)
+                for (int k = 0; k < pos_k; ++k) {
+                    const double x = v->data[((size_t)co * cg + ci) * pos_k + k];
+                    nrm[k] += x * x;
+                }
+        std::vector<float> w((size_t)pos_g * pos_k * cg * cg);
+        for (int gi = 0; gi < pos_g; ++gi)
+            for (int co = 0; co < cg; ++co)
+                for (int ci = 0; ci < cg; ++ci)
+                    for (int k = 0; k < pos_k; ++k) {
+                        const float fac = g->data[k] / (float)std::sqrt(nrm[k]);
+                        w[((size_t)gi * pos_k * cg + (size_t)k * cg + ci) * cg + co] =
+                            v->data[((size_t)(gi * cg + co) * cg + ci) * pos_k + k] * fac;
+                    }
+        CKI(upload(w, &pos_w));
+        CKI(upload_raw(pc + "bias", {H}, &pos_b));
+    }
+    CKI(upload_raw(P + "encoder.layer_norm.weight", {H}, &enc_ln_g));
+    CKI(upload_raw(P + "encoder.layer_norm.bias", {H}, &enc_ln_b));
+    // ---- transformer layers (post-LN; TF modeling_wav2vec2.py:576-609)
+    enc_layers = 0;
+    while (find(P + "encoder.layers." + std::to_string(enc_layers) + ".final_layer_norm.weight")) ++enc_layers;
+    if (enc_layers == 0) return fail("audio encoder: no transformer layers found");
+    const HostTensor* f1 = find(P + "encoder.layers.0.feed_forward.intermediate_dense.weight");
+    if (!f1 || f1->shape.size() != 2) return fail("intermediate_dense.weight missing");
+    enc_ffn = (int)f1->shape[0];
+    if (enc_ffn % GEMM_BK != 0) return fail("audio encoder: ffn width must be a multiple of 16");
+    enc.assign(enc_layers, EncLayerW{});
+    for (int l = 0; l < enc_layers; ++l) {
+        EncLayerW& L = enc[l];
+        const std::string p = P + "encoder.layers." + std::to_string(l) + ".";
+        std::vector<float> wqkv((size_t)H * 3 * H), bqkv((size_t)3 * H);
+        const char* nm[3] = {"q_proj", "k_proj", "v_proj"};
+        for (int j = 0; j < 3; ++j) {
+            CKI(need(p + "attention." + nm[j] + ".weight", {H, H}, &t));
+            pack_w(*t, H, H, 1, wqkv, 3 * H, 0, j * H);
+            CKI(need(p + "attention." + nm[j] + ".bias", {H}, &t));
+            std::copy(t->data.begin(), t->data.end(), bqkv.begin() + (size_t)j * H);
+        }
+        CKI(upload(wqkv, &L.wqkv));
+        CKI(upload(bqkv, &L.bqkv));
+        std::vector<float> w((size_t)H * H);
+        CKI(need(p + "attention.out_proj.weight", {H, H}, &t));
+        pack_w(*t, H, H, 1, w, H, 0, 0);
+        CKI(upload(w, &L.wo));
+        CKI(upload_raw(p + "attention.out_proj.bias", {H}, &L.bo));
+        CKI(upload_raw(p + "layer_norm.weight", {H}, &L.ln1_g));
+        CKI(upload_raw(p + "layer_norm.bias", {H}, &L.ln1_b));
+        CKI(need(p + "feed_forward.intermediate_dense.weight", {enc_ffn, H}, &t));
+        std::vector<float> w1((size_t)H * enc_ffn);
+        pack_w(*t, enc_ffn, H, 1, w1, enc_ffn, 0, 0);
+        CKI(upload(w1, &L.wff1));
+        CKI(upload_raw(p + "feed_forward.intermediate_dense.bias", {enc_ffn}, &L.bff1));
+        CKI(need(p + "feed_forward.output_dense.weight", {H, enc_ffn}, &t));
+        std::vector<float> w2((size_t)enc_ffn * H);
+        pack_w(*t, H, enc_ffn, 1, w2, H, 0, 0);
+        CKI(upload(w2, &L.wff2));
+        CKI(upload_raw(p + "feed_forward.output_dense.bias", {H}, &L.bff2));
+        CKI(upload_raw(p + "final_layer_norm.weight", {H}, &L.ln2_g));
+        CKI(upload_raw(p + "final_layer_norm.bias", {H}, &L.ln2_b));
+    }
+    return 0;
+}
+
+int said_engine::commit() {
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceSynchronize());
+    for (float* p : arena) cudaFree(p);
+    arena.clear();
+    ready = false;
+    ctx_B = ctx_T = 0;
+    CKI(commit_denoiser());
+    CKI(commit_encoder());
+    const int enc_out = proj_dim > 0 ? proj_dim : enc_hidden;
+    if (enc_out != ctx_dim)
+        return fail("audio feature width " + std::to_string(enc_out) + " != denoiser context dim " + std::to_string(ctx_dim));
+    ready = true;
+    return 0;
+}
+
+// =====================================================================================================
+// Launch helpers
+// =====================================================================================================
+namespace {
+
+EpiStd mk_epi(float* out, long long ldo, int N) {
+    EpiStd e;
+    memset(&e, 0, sizeof(e));
+    e.out = out;
+    e.ldo = ldo;
+    e.N = N;
+    e.T = 1;
+    e.zdiv = 1;
+    return e;
+}
+ALoadPlain mk_plain(const float* A, long long lda, int M) {
+    ALoadPlain a;
+    a.A = A;
+    a.lda = lda;
+    a.zstride = 0;
+    a.zdiv = 1;
+    a.zstride2 = 0;
+    a.M = M;
+    return a;
+}
+
+}  // namespace
+
+#define LAUNCH_CHECK()                         \
+    do {                                       \
+        ++launches;                            \
+        CK(cudaGetLastError());                \
+    } while (0)
+
+// =====================================================================================================
+// Audio encoder
+// =====================================================================================================
+int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* emb_out, cudaStream_t st) {
+    if (!ready) return fail("weights not committed");
+    if (B <= 0 || T <= 0) return fail("encode_audio: empty batch");
+    int L[8];
+    L[0] = (T_a - conv_k[0]) / conv_s[0] + 1;
+    if (T_a < conv_k[0]) return fail("encode_audio: waveform shorter than the first conv kernel");
+    for (int i = 1; i < n_conv; ++i) {
+        L[i] = (L[i - 1] - conv_k[i]) / conv_s[i] + 1;
+        if (L[i - 1] < conv_k[i] || L[i] < 1) return fail("encode_audio: waveform too short for the conv stack");
+    }
+    const int H = enc_hidden, CD = enc_conv_dim;
+    const int Lf = L[n_conv - 1];
+    // ---- conv0 + per-channel norm + GELU
+    const int nchunk = 32;
+    const int fpc = (L[0] + nchunk - 1) / nchunk;
+    const size_t need_partial = (size_t)B * nchunk * 2 * CD;
+    if (need_partial > c0_partial_cap) {
+        if (c0_partial) cudaFree(c0_partial);
+        c0_partial = nullptr;
+        c0_partial_cap = 0;
+        CK(cudaMalloc((void**)&c0_partial, need_partial * sizeof(double)));
+        c0_partial_cap = need_partial;
+    }
+    CK(e_a.ensure((size_t)B * L[0] * CD));
+    CK(e_b.ensure((size_t)B * L[1] * CD));
+    conv0_stats_kernel<<<dim3(nchunk, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, fpc, c0_partial);
+    LAUNCH_CHECK();
+    conv0_apply_kernel<<<dim3((L[0] + C0_TILE - 1) / C0_TILE, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, c0_partial, nchunk,
+                                                                                   c0_g, c0_b, 1e-5f, e_a.p);
+    LAUNCH_CHECK();
+    // ---- conv1..6 (stride 2, GELU): overlapping-row GEMMs, one batch entry per clip
+    float* src = e_a.p;
+    float* dst = e_b.p;
+    for (int i = 1; i < n_conv; ++i) {
+        ALoadPlain al = mk_plain(src, (long long)conv_s[i] * CD, L[i]);
+        al.zstride = (long long)L[i - 1] * CD;
+        EpiStd ep = mk_epi(dst, CD, CD);
+        ep.act = 1;
+        ep.zs0 = (long long)L[i] * CD;
+        CK(launch_gemm(st, L[i], CD, conv_k[i] * CD, al, conv_w[i], CD, ep, B));
+        ++launches;
+        std::swap(src, dst);
+    }
+    // src now holds (B, Lf, CD)
+    const int M = B * T;
+    CK(e_c.ensure((size_t)M * std::max(CD, H)));
+    CK(e_d.ensure((size_t)M * H));
+    CK(e_qkv.ensure((size_t)M * 3 * H));
+    CK(e_ff.ensure((size_t)M * enc_ffn));
+    CK(e_xp.ensure((size_t)B * pos_g * (T + pos_k) * (H / pos_g)));
+    // ---- interpolate to T frames + LayerNorm(512)  -> e_c (M, CD)
+    interp_layernorm_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(src, B, Lf, T, CD, 1e-5f, fp_ln_g, fp_ln_b, e_c.p);
+    LAUNCH_CHECK();
+    // ---- projection 512 -> H  -> e_d
+    {
+        EpiStd ep = mk_epi(e_d.p, H, H);
+        ep.bias = fp_b;
+        CK(launch_gemm(st, M, H, CD, mk_plain(e_c.p, CD, M), fp_w, H, ep));
+        ++launches;
+    }
+    // ---- positional conv embedding: x + gelu(conv(x)) then LayerNorm   (TF :690-693)
+    {
+        const int cg = H / pos_g, Tp = T + pos_k;
+        const long long tot = (long long)B * pos_g * Tp * cg;
+        posconv_regroup_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(e_d.p, B, T, H, pos_g, pos_k, e_xp.p);
+        LAUNCH_CHECK();
+        ALoadPlain al = mk_plain(e_xp.p, cg, T);
+        al.zdiv = pos_g;
+        al.zstride = (long long)pos_g * Tp * cg;
+        al.zstride2 = (long long)Tp * cg;
+        EpiStd ep = mk_epi(e_c.p, H, cg);
+        ep.bias = pos_b;
+        ep.act = 1;
+        ep.res = e_d.p;
+        ep.ldr = H;
+        ep.zdiv = pos_g;
+        ep.zs0 = (long long)T * H;
+        ep.zs1 = cg;
+        ep.bias_zs = cg;
+        CK(launch_gemm(st, T, cg, pos_k * cg, al, pos_w, cg, ep, B * pos_g, pos_g, (long long)pos_k * cg * cg));
+        ++launches;
+        layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(e_c.p, nullptr, M, H, 1e-5f, enc_ln_g, enc_ln_b, e_d.p);
+        LAUNCH_CHECK();
+    }
+    // ---- transformer layers; x lives in e_d
+    CK(cudaFuncSetAttribute(self_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)attention_smem_bytes<64>()));
+    const bool last_direct = proj_dim == 0;
+    for (int l = 0; l < enc_layers; ++l) {
+        const EncLayerW& W = enc[l];
+        {
+            EpiStd ep = mk_epi(e_qkv.p, 3 * H, 3 * H);
+            ep.bias = W.bqkv;
+            CK(launch_gemm(st, M, 3 * H, H, mk_plain(e_d.p, H, M), W.wqkv, 3 * H, ep));
+            ++launches;
+        }
+        self_attention_kernel<64><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, enc_heads, B), ATT_THREADS,
+                                    attention_smem_bytes<64>(), st>>>(e_qkv.p, 3 * H, 0, H, 2 * H, T, 0.125f, e_c.p, H);
+        LAUNCH_CHECK();
+        {
+            EpiStd ep = mk_epi(e_qkv.p, H, H);   // attention output projection + residual -> e_qkv (as M x H)
+            ep.bias = W.bo;
+            ep.res = e_d.p;
+            ep.ldr = H;
+            CK(launch_gemm(st, M, H, H, mk_plain(e_c.p, H, M), W.wo, H, ep));
+            ++launches;
+        }
+        layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(e_qkv.p, nullptr, M, H, 1e-5f, W.ln1_g, W.ln1_b, e_d.p);
+        LAUNCH_CHECK();
+        {
+            EpiStd ep = mk_epi(e_ff.p, enc_ffn, enc_ffn);
+            ep.bias = W.bff1;
+            ep.act = 1;
+            CK(launch_gemm(st, M, enc_ffn, H, mk_plain(e_d.p, H, M), W.wff1, enc_ffn, ep));
+            ++launches;
+        }
+        {
+            EpiStd ep = mk_epi(e_c.p, H, H);
+            ep.bias = W.bff2;
+            ep.res = e_d.p;
+            ep.ldr = H;
+            CK(launch_gemm(st, M, H, enc_ffn, mk_plain(e_ff.p, enc_ffn, M), W.wff2, H, ep));
+            ++launches;
+        }
+        float* dst_ln = (l == enc_layers - 1 && last_direct) ? emb_out : e_d.p;
+        layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(e_c.p, nullptr, M, H, 1e-5f, W.ln2_g, W.ln2_b, dst_ln);
+        LAUNCH_CHECK();
+    }
+    if (!last_direct) {   // audio_proj_layer (diffusion.py:228-229)
+        EpiStd ep = mk_epi(emb_out, proj_dim, proj_dim);
+        ep.bias = b_aproj;
+        CK(launch_gemm(st, M, proj_dim, H, mk_plain(e_d.p, H, M), w_aproj, proj_dim, ep));
+        ++launches;
+    }
+    return 0;
+}
+
+// =====================================================================================================
+// Context hoist
+// =====================================================================================================
+int said_engine::prepare_context(const float* emb, int B, int T, int with_uncond, cudaStream_t st) {
+    if (!ready) return fail("weights not committed");
+    if (B <= 0 || T <= 0) return fail("prepare_context: empty batch");
+    const int M = B * T, N = 8 * C;
+    CK(kv.ensure((size_t)M * N));
+    CK(vnull.ensure((size_t)4 * C));
+    CK(vnull_tmp.ensure((size_t)N));
+    {
+        EpiStd ep = mk_epi(kv.p, N, N);
+        CK(launch_gemm(st, M, N, ctx_dim, mk_plain(emb, ctx_dim, M), w_kv, N, ep));
+        ++launches;
+    }
+    if (with_uncond) {
+        EpiStd ep = mk_epi(vnull_tmp.p, N, N);
+        CK(launch_gemm(st, 1, N, ctx_dim, mk_plain(null_emb, ctx_dim, 1), w_kv, N, ep));
+        ++launches;
+        for (int l = 0; l < 4; ++l)
+            CK(cudaMemcpyAsync(vnull.p + l * C, vnull_tmp.p + l * 2 * C + C, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    ctx_B = B;
+    ctx_T = T;
+    ctx_uncond = with_uncond ? 1 : 0;
+    return 0;
+}
+
+// =====================================================================================================
+// Denoiser forward
+// =====================================================================================================
+int said_engine::ensure_denoiser_ws(int Bp, int T) {
+    const size_t M = (size_t)Bp * T;
+    for (auto& a : act) CK(a.ensure(M * C));
+    CK(qkv.ensure(M * 3 * C));
+    CK(ao.ensure(M * C));
+    CK(q2.ensure(M * C));
+    CK(ffb.ensure(M * FF));
+    CK(eps.ensure(M * in_ch));
+    CK(ss.ensure((size_t)Bp * 2 * C * 2));
+    CK(ss_st.ensure((size_t)Bp * C * 2));
+    if (!step_ctr) CK(cudaMalloc((void**)&step_ctr, sizeof(int)));
+    CK(cudaFuncSetAttribute(self_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)attention_smem_bytes<32>()));
+    return 0;
+}
+
+// x: (src_batch, T, in_ch) latents; sample b of the Bp denoiser samples reads clip b % src_batch.
+// Samples [0, n_uncond) are the null-condition branch.  emb_table: (rows, 5, 192), row = *step_ptr
+// or the sample index when step_ptr is null.
+int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T,
+                         const float* emb_table, const int* step_ptr, float* eps_out, float* taps) {
+    const int M = Bp * T;
+    const int Mc = (Bp - n_uncond) * T;
+    float* h0 = act[0].p; float* h1 = act[1].p; float* A = act[2].p; float* Bb = act[3].p;
+    float* t1 = act[4].p; float* x1 = act[5].p; float* x2 = act[6].p;
+    float* sc = ss.p; float* sh = ss.p + (size_t)Bp * 2 * C;
+    float* sc_st = ss_st.p; float* sh_st = ss_st.p + (size_t)Bp * C;
+    const float att_scale = 1.0f / sqrtf((float)HD);
+    int tap_idx = 0;
+    auto tap = [&](const float* p) -> int {
+        if (taps) {
+            CK(cudaMemcpyAsync(taps + (size_t)tap_idx * M * C, p, (size_t)M * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            ++tap_idx;
+        }
+        return 0;
+    };
+    auto gn = [&](const float* src, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh, int ld, int off) -> int {
+        gn_stats_kernel<<<Bp, GN_THREADS, 0, st>>>(src, T, cpg, eps_, g, b, osc, osh, ld, off);
+        LAUNCH_CHECK();
+        return 0;
+    };
+    // ResBlock (openaimodel.py:207-227): in (a [, skip]) -> out
+    auto resblock = [&](int i, const float* a, const float* skip, float* out) -> int {
+        const ResBlockW& W = rb[i];
+        const int cin = W.cin;
+        if (skip) {
+            CKI(gn(a, 12, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0));
+            CKI(gn(skip, 12, 1e-5f, W.gn1_g + C, W.gn1_b + C, sc, sh, cin, C));
+        } else {
+            CKI(gn(a, 6, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0));
+        }
+        {
+            ALoadConv3 al{a, skip, C, skip ? C : 0, cin, T, M, Bp, sc, sh, 3 * cin};
+            EpiStd ep = mk_epi(t1, C, C);
+            ep.bias = W.b1;
+            ep.emb = emb_table + (size_t)i * C;
+            ep.emb_ld = 5 * C;
+            ep.step_ptr = step_ptr;
+            ep.T = T;
+            CK(launch_gemm(st, M, C, 3 * cin, al, W.w1, C, ep));
+            ++launches;
+        }
+        CKI(gn(t1, 6, 1e-5f, W.gn2_g, W.gn2_b, sc, sh, C, 0));
+        if (skip) {
+            // second conv over t1 with the 1x1 skip over the raw concat fused as extra contraction rows.
+            // One loader cannot address three tensors, so the skip part runs as a second GEMM that
+            // accumulates through the residual input.
+            ALoadConv3 al{t1, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
+            EpiStd ep = mk_epi(x1, C, C);
+            ep.bias = W.b2;
+            CK(launch_gemm(st, M, C, 3 * C, al, W.w2, C, ep));
+            ++launches;
+            ALoadConv3 al2{a, skip, C, C, cin, T, M, Bp, nullptr, nullptr, 0};   // K3 = 0: raw centre tap only
+            EpiStd ep2 = mk_epi(out, C, C);
+            ep2.res = x1;
+            ep2.ldr = C;
+            CK(launch_gemm(st, M, C, cin, al2, W.w2 + (size_t)3 * C * C, C, ep2));
+            ++launches;
+        } else {
+            ALoadConv3 al{t1, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
+            EpiStd ep = mk_epi(out, C, C);
+            ep.bias = W.b2;
+            ep.res = a;
+            ep.ldr = C;
+            CK(launch_gemm(st, M, C, 3 * C, al, W.w2, C, ep));
+            ++launches;
+        }
+        return 0;
+    };
+    // SpatialTransformer + BasicTransformerBlock (attention.py:223-234, 167-193): h -> out
+    auto transformer = [&](int i, const float* h, float* out) -> int {
+        const TransformerW& W = tr[i];
+        CKI(gn(h, 6, 1e-6f, W.gn_g, W.gn_b, sc_st, sh_st, C, 0));
+        {   // q,k,v = LN1(GN(h)) W   (no bias)
+            ALoadLN al{h, M, T, sc_st, sh_st, W.ln1_g, W.ln1_b, 1e-5f};
+            EpiStd ep = mk_epi(qkv.p, 3 * C, 3 * C);
+            CK(launch_gemm(st, M, 3 * C, C, al, W.wqkv, 3 * C, ep));
+            ++launches;
+        }
+        self_attention_kernel<32><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, Bp), ATT_THREADS,
+                                    attention_smem_bytes<32>(), st>>>(qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
+        LAUNCH_CHECK();
+        {   // x1 = to_out(attn) + GN(h)
+            EpiStd ep = mk_epi(x1, C, C);
+            ep.bias = W.bo1;
+            ep.res = h;
+            ep.ldr = C;
+            ep.res_scale = sc_st;
+            ep.res_shift = sh_st;
+            ep.res_aff_ld = C;
+            ep.T = T;
+            CK(launch_gemm(st, M, C, C, mk_plain(ao.p, C, M), W.wo1, C, ep));
+            ++launches;
+        }
+        if (Mc > 0) {   // cross-attention queries, conditional samples only
+            ALoadLN al{x1 + (size_t)n_uncond * T * C, Mc, T, nullptr, nullptr, W.ln2_g, W.ln2_b, 1e-5f};
+            EpiStd ep = mk_epi(q2.p, C, C);
+            CK(launch_gemm(st, Mc, C, C, al, W.wq2, C, ep));
+            ++launches;
+        }
+        {
+            const long long tot = (long long)M * HEADS;
+            cross_attention3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q2.p, kv.p, 8 * C, i * 2 * C, vnull.p + i * C,
+                                                                                  n_uncond, Bp, T, att_scale, ao.p);
+            LAUNCH_CHECK();
+        }
+        {   // x2 = to_out(attn2) + x1
+            EpiStd ep = mk_epi(x2, C, C);
+            ep.bias = W.bo2;
+            ep.res = x1;
+            ep.ldr = C;
+            CK(launch_gemm(st, M, C, C, mk_plain(ao.p, C, M), W.wo2, C, ep));
+            ++launches;
+        }
+        {   // GEGLU
+            ALoadLN al{x2, M, T, nullptr, nullptr, W.ln3_g, W.ln3_b, 1e-5f};
+            EpiGeglu ep{ffb.p, FF, 2 * FF, W.bff1};
+            CK(launch_gemm(st, M, 2 * FF, C, al, W.wff1, 2 * FF, ep));
+            ++launches;
+        }
+        {   // x3 = ff2 + x2  -> x1
+            EpiStd ep = mk_epi(x1, C, C);
+            ep.bias = W.bff2;
+            ep.res = x2;
+            ep.ldr = C;
+            CK(launch_gemm(st, M, C, FF, mk_plain(ffb.p, FF, M), W.wff2, C, ep));
+            ++launches;
+        }
+        {   // out = proj_out(x3) + h
+            EpiStd ep = mk_epi(out, C, C);
+            ep.bias = W.bproj;
+            ep.res = h;
+            ep.ldr = C;
+            CK(launch_gemm(st, M, C, C, mk_plain(x1, C, M), W.wproj, C, ep));
+            ++launches;
+        }
+        return 0;
+    };
+
+    {   // input conv (openaimodel.py:473-479)
+        ALoadConv3 al{x, nullptr, in_ch, 0, in_ch, T, M, src_batch, nullptr, nullptr, 3 * in_ch};
+        EpiStd ep = mk_epi(h0, C, C);
+        ep.bias = b_in;
+        CK(launch_gemm(st, M, C, 3 * in_ch, al, w_in, C, ep));
+        ++launches;
+    }
+    CKI(tap(h0));
+    CKI(resblock(0, h0, nullptr, A));      CKI(tap(A));
+    CKI(transformer(0, A, h1));            CKI(tap(h1));
+    CKI(resblock(1, h1, nullptr, Bb));     CKI(tap(Bb));
+    CKI(transformer(1, Bb, A));            CKI(tap(A));
+    CKI(resblock(2, A, nullptr, Bb));      CKI(tap(Bb));
+    CKI(resblock(3, Bb, h1, A));           CKI(tap(A));
+    CKI(transformer(2, A, Bb));            CKI(tap(Bb));
+    CKI(resblock(4, Bb, h0, A));           CKI(tap(A));
+    CKI(transformer(3, A, Bb));            CKI(tap(Bb));
+    {   // out: GN + SiLU + conv3 -> in_ch   (openaimodel.py:665-669)
+        CKI(gn(Bb, 6, 1e-5f, out_gn_g, out_gn_b, sc, sh, C, 0));
+        ALoadConv3 al{Bb, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
+        EpiStd ep = mk_epi(eps_out, in_ch, in_ch);
+        ep.bias = b_out;
+        CK(launch_gemm(st, M, in_ch, 3 * C, al, w_out, in_ch, ep));
+        ++launches;
+    }
+    return 0;
+}
+
+// =====================================================================================================
+// Denoising loop
+// =====================================================================================================
+int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
+    if (!ready) return fail("weights not committed");
+    if (a.B <= 0 || a.T <= 0 || a.n_steps < 0) return fail("denoise: bad sizes");
+    if (ctx_B != a.B || ctx_T != a.T || ctx_uncond != (a.do_cfg ? 1 : 0))
+        return fail("denoise: said_prepare_context was not called for this (B, T, cfg)");
+    const int B = a.B, T = a.T, Bp = a.do_cfg ? 2 * B : B;
+    const long long n = (long long)T * in_ch, tot = (long long)B * n;
+    CKI(ensure_denoiser_ws(Bp, T));
+    CK(lat.ensure((size_t)tot));
+    CK(init_lat.ensure((size_t)tot));
+    cudaStream_t st = own_stream;
+    CK(cudaEventRecord(ev_in, user));
+    CK(cudaStreamWaitEvent(st, ev_in, 0));
+
+    prepare_latents_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a.init_src_dev, a.init_scale, a.edit_noise_dev, a.edit_sqrt_a,
+                                                                         a.edit_sqrt_b, lat.p, init_lat.p, tot);
+    LAUNCH_CHECK();
+    if (a.n_steps == 0) {
+        finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(lat.p, a.latent_scale, a.result_dev, tot);
+        LAUNCH_CHECK();
+    } else {
+        CK(tvals.ensure((size_t)a.n_steps));
+        CK(step_tab.ensure((size_t)a.n_steps * 8));
+        CK(emb_tab.ensure((size_t)a.n_steps * 5 * C));
+        CK(cudaMemcpyAsync(tvals.p, a.timesteps_host, a.n_steps * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(step_tab.p, a.step_table_host, (size_t)a.n_steps * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+        time_embed_table_kernel<<<a.n_steps, 256, 0, st>>>(tvals.p, te, emb_tab.p, nullptr);
+        LAUNCH_CHECK();
+        set_int_kernel<<<1, 1, 0, st>>>(step_ctr, 0);
+        LAUNCH_CHECK();
+
+        StepParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.pred = eps.p;
+        sp.latents = lat.p;
+        sp.B = B;
+        sp.n = (int)n;
+        sp.do_cfg = a.do_cfg;
+        sp.gscale = a.guidance_scale;
+        sp.grescale = a.guidance_rescale;
+        sp.one_minus_grescale = (float)(1.0 - (double)a.guidance_rescale);
+        sp.pred_type = a.prediction_type;
+        sp.table = step_tab.p;
+        sp.step_ptr = step_ctr;
+        sp.n_steps = a.n_steps;
+        sp.eta_noise = a.eta_noise_dev;
+        sp.init_latents = init_lat.p;
+        sp.edit_noise = a.edit_noise_dev;
+        sp.mask = a.mask_dev;
+        sp.intermediates = a.intermediates_dev;
+        sp.latent_scale = a.latent_scale;
+        sp.result = a.result_dev;
+        if (sp.mask && !sp.edit_noise) return fail("denoise: mask given without edit noise");
+
+        auto one_step = [&]() -> int {
+            CKI(forward(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
+            ddim_step_kernel<<<B, 256, 0, st>>>(sp);
+            LAUNCH_CHECK();
+            add_int_kernel<<<1, 1, 0, st>>>(step_ctr, 1);
+            LAUNCH_CHECK();
+            return 0;
+        };
+        if (a.use_graph && a.n_steps > 1) {
+            if (graph_exec) {
+                CK(cudaStreamSynchronize(st));
+                cudaGraphExecDestroy(graph_exec);
+                graph_exec = nullptr;
+            }
+            const long long before = launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = one_step();
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != 0) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            CK(ce);
+            const long long per_step = launches - before;
+            CK(cudaGraphInstantiate(&graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            for (int s = 0; s < a.n_steps; ++s) CK(cudaGraphLaunch(graph_exec, st));
+            launches = before + per_step * a.n_steps;
+        } else {
+            for (int s = 0; s < a.n_steps; ++s) CKI(one_step());
+        }
+    }
+    if (a.latents_out_dev)
+        CK(cudaMemcpyAsync(a.latents_out_dev, lat.p, (size_t)tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(ev_out, st));
+    CK(cudaStreamWaitEvent(user, ev_out, 0));
+    return 0;
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* said_last_error(void) { return g_err.c_str(); }
+int said_version(void) { return 1; }
+
+int said_create(int device, said_engine** out) {
+    if (!out) return fail("said_create: null out pointer");
+    *out = nullptr;
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail("said_create: no such CUDA device " + std::to_string(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(std::string("said_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                    std::to_string(prop.minor) + "; this library is built for sm_100a (B200) only");
+    CK(cudaSetDevice(device));
+    std::unique_ptr<said_engine> e(new said_engine());
+    e->device = device;
+    e->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+    *out = e.release();
+    return 0;
+}
+
+void said_destroy(said_engine* e) { delete e; }
+
+int said_set_tensor(said_engine* e, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+    if (!e || !name || !host_data || ndim < 0 || ndim > 8) return fail("said_set_tensor: bad arguments");
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] < 0) return fail("said_set_tensor: negative dimension");
+        t.shape.push_back(shape[i]);
+        n *= shape[i];
+    }
+    t.data.assign(host_data, host_data + n);
+    e->raw[name] = std::move(t);
+    e->ready = false;
+    return 0;
+}
+
+int said_commit_weights(said_engine* e) {
+    if (!e) return fail("null engine");
+    return e->commit();
+}
+
+int said_weights_ready(const said_engine* e) { return e && e->ready ? 1 : 0; }
+
+int said_get_config(const said_engine* e, int* in_channels, int* ctx_dim, int* enc_hidden) {
+    if (!e || !e->ready) return fail("weights not committed");
+    if (in_channels) *in_channels = e->in_ch;
+    if (ctx_dim) *ctx_dim = e->ctx_dim;
+    if (enc_hidden) *enc_hidden = e->enc_hidden;
+    return 0;
+}
+
+int said_encode_audio(said_engine* e, const float* wave_dev, int B, int T_a, int T, float* emb_out_dev, void* stream) {
+    if (!e) return fail("null engine");
+    CK(cudaSetDevice(e->device));
+    return e->encode_audio(wave_dev, B, T_a, T, emb_out_dev, (cudaStream_t)stream);
+}
+
+int said_prepare_context(said_engine* e, const float* emb_dev, int B, int T, int with_uncond, void* stream) {
+    if (!e) return fail("null engine");
+    CK(cudaSetDevice(e->device));
+    return e->prepare_context(emb_dev, B, T, with_uncond, (cudaStream_t)stream);
+}
+
+int said_denoise(said_engine* e, const said_denoise_args* args, void* stream) {
+    if (!e || !args) return fail("null engine / args");
+    CK(cudaSetDevice(e->device));
+    return e->denoise(*args, (cudaStream_t)stream);
+}
+
+int said_denoiser_forward(said_engine* e, const float* x_dev, const float* timesteps_host, const float* ctx_dev, int Bp,
+                          int T, float* out_dev, float* taps_dev, void* stream) {
+    if (!e) return fail("null engine");
+    if (!e->ready) return fail("weights not committed");
+    if (Bp <= 0 || T <= 0) return fail("denoiser_forward: empty batch");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CKI(e->prepare_context(ctx_dev, Bp, T, 0, st));
+    CKI(e->ensure_denoiser_ws(Bp, T));
+    CK(e->tvals.ensure((size_t)Bp));
+    CK(e->emb_tab.ensure((size_t)Bp * 5 * C));
+    CK(cudaMemcpyAsync(e->tvals.p, timesteps_host, Bp * sizeof(float), cudaMemcpyHostToDevice, st));
+    time_embed_table_kernel<<<Bp, 256, 0, st>>>(e->tvals.p, e->te, e->emb_tab.p, nullptr);
+    ++e->launches;
+    CK(cudaGetLastError());
+    CKI(e->forward(st, x_dev, Bp, Bp, 0, T, e->emb_tab.p, nullptr, out_dev, taps_dev));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int said_op_ddim_step(said_engine* e, const float* pred_dev, float* latents_dev, int B, int n, int do_cfg,
+                      float guidance_scale, float guidance_rescale, int prediction_type, const float* row8_host,
+                      const float* eta_noise_dev, void* stream) {
+    if (!e) return fail("null engine");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(e->step_tab.ensure(8));
+    if (!e->step_ctr) CK(cudaMalloc((void**)&e->step_ctr, sizeof(int)));
+    CK(cudaMemcpyAsync(e->step_tab.p, row8_host, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+    set_int_kernel<<<1, 1, 0, st>>>(e->step_ctr, 0);
+    StepParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.pred = pred_dev;
+    sp.latents = latents_dev;
+    sp.B = B;
+    sp.n = n;
+    sp.do_cfg = do_cfg;
+    sp.gscale = guidance_scale;
+    sp.grescale = guidance_rescale;
+    sp.one_minus_grescale = (float)(1.0 - (double)guidance_rescale);
+    sp.pred_type = prediction_type;
+    sp.table = e->step_tab.p;
+    sp.step_ptr = e->step_ctr;
+    sp.n_steps = 2;   // never "last": no result write
+    sp.eta_noise = eta_noise_dev;
+    sp.latent_scale = 1.0f;
+    ddim_step_kernel<<<B, 256, 0, st>>>(sp);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, int heads, int head_dim, float* out_dev,
+                           void* stream) {
+    if (!e) return fail("null engine");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Cw = heads * head_dim;
+    const float scale = 1.0f / sqrtf((float)head_dim);
+    const dim3 grid((T + ATT_QTILE - 1) / ATT_QTILE, heads, B);
+    if (head_dim == 32) {
+        CK(cudaFuncSetAttribute(self_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attention_smem_bytes<32>()));
+        self_attention_kernel<32><<<grid, ATT_THREADS, attention_smem_bytes<32>(), st>>>(qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, scale, out_dev, Cw);
+    } else if (head_dim == 64) {
+        CK(cudaFuncSetAttribute(self_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attention_smem_bytes<64>()));
+        self_attention_kernel<64><<<grid, ATT_THREADS, attention_smem_bytes<64>(), st>>>(qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, scale, out_dev, Cw);
+    } else {
+        return fail("self_attention: head_dim must be 32 or 64");
+    }
+    ++e->launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+long long said_launch_count(const said_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

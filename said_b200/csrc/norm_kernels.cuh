@@ -1,0 +1,173 @@
+// Normalisation statistics and row-wise normalisation kernels.
+#pragma once
+#include "common.cuh"
+
+namespace said {
+
+// GroupNorm statistics -> per-(sample, channel) scale/shift so that  gn(x)[c] = x[c]*scale + shift.
+// (GroupNorm32, ldm/util.py:111-122: 32 groups, biased variance over channels-in-group x T, fp32;
+//  attention.py:63-66 Normalize: same with eps 1e-6.)  One CTA per sample; x is (B', T, C) channel-last,
+// C == 192; `cpg` channels per group (6 for a 192-channel tensor, 12 for one half of a 384-channel
+// concat).  Sums are accumulated in fp64 so E[x^2]-mean^2 has no cancellation problem.
+// scale/shift are written at [b * out_ld + out_off + c].
+constexpr int GN_THREADS = 768;   // 4 row phases x 192 channels
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const float* __restrict__ x, int T, int cpg, float eps, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
+                int out_ld, int out_off) {
+    constexpr int C = 192;
+    __shared__ double s_sum[4][C];
+    __shared__ double s_sq[4][C];
+    __shared__ float s_mean[32], s_rstd[32];
+    const int b = blockIdx.x;
+    const int c = threadIdx.x % C, ph = threadIdx.x / C;
+    const float* xb = x + (long long)b * T * C;
+    double s = 0.0, q = 0.0;
+    int t = ph;
+    for (; t + 12 < T; t += 16) {   // 4 independent loads in flight
+        const float v0 = __ldg(xb + (long long)t * C + c), v1 = __ldg(xb + (long long)(t + 4) * C + c);
+        const float v2 = __ldg(xb + (long long)(t + 8) * C + c), v3 = __ldg(xb + (long long)(t + 12) * C + c);
+        s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+        q += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
+    }
+    for (; t < T; t += 4) {
+        const float v = __ldg(xb + (long long)t * C + c);
+        s += v;
+        q += (double)v * v;
+    }
+    s_sum[ph][c] = s;
+    s_sq[ph][c] = q;
+    __syncthreads();
+    const int ng = C / cpg;
+    if ((int)threadIdx.x < ng) {
+        double gs = 0.0, gq = 0.0;
+        for (int j = 0; j < cpg; ++j) {
+            const int cc = threadIdx.x * cpg + j;
+            gs += (s_sum[0][cc] + s_sum[1][cc]) + (s_sum[2][cc] + s_sum[3][cc]);
+            gq += (s_sq[0][cc] + s_sq[1][cc]) + (s_sq[2][cc] + s_sq[3][cc]);
+        }
+        const double n = (double)cpg * T;
+        const double mean = gs / n;
+        double var = gq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        const int g = c / cpg;
+        const float sc = s_rstd[g] * __ldg(gamma + c);
+        const float sh = __ldg(beta + c) - s_mean[g] * sc;
+        scale[(long long)b * out_ld + out_off + c] = sc;
+        shift[(long long)b * out_ld + out_off + c] = sh;
+    }
+}
+
+// Row-wise LayerNorm (+ optional residual add before it):  y = LN(x [+ r]) * gamma + beta.
+// One warp per row; C % 128 == 0 not required, C % 4 == 0 and C <= 1024.
+// Used by the Wav2Vec2 post-LN encoder layers (TF modeling_wav2vec2.py:592-609).
+template <int MAXV>   // float4 per lane, C <= 128*MAXV
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ r, int M, int C, float eps,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    const float* xr = x + (long long)warp * C;
+    const float* rr = r ? r + (long long)warp * C : nullptr;
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int k = (j * 32 + lane) * 4;
+        float4 a = zero4();
+        if (k < C) {
+            a = ldg4(xr + k);
+            if (rr) { const float4 d = ldg4(rr + k); a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w; }
+        }
+        v[j] = a;
+        s += (a.x + a.y) + (a.z + a.w);
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int k = (j * 32 + lane) * 4;
+        if (k < C) {
+            const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int k = (j * 32 + lane) * 4;
+        if (k < C) {
+            const float4 g = ldg4(gamma + k), bb = ldg4(beta + k);
+            float4 o;
+            o.x = (v[j].x - mean) * rstd * g.x + bb.x;
+            o.y = (v[j].y - mean) * rstd * g.y + bb.y;
+            o.z = (v[j].z - mean) * rstd * g.z + bb.z;
+            o.w = (v[j].w - mean) * rstd * g.w + bb.w;
+            st4(y + (long long)warp * C + k, o);
+        }
+    }
+}
+
+// Linear interpolation over frames (align_corners=True; said/model/wav2vec2.py:41-44, ATen
+// upsample_linear1d: src = j * (L-1)/(T-1), lambda1 = src - floor(src)) fused with the feature
+// projection's LayerNorm(512) (TF modeling_wav2vec2.py:429-434).  x: (B, L, C) -> y: (B, T, C).
+// One warp per output row; T < 0 disables interpolation semantics (never used: T is always given).
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+interp_layernorm_kernel(const float* __restrict__ x, int B, int L, int T, int C, float eps,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B * T) return;
+    const int b = warp / T, j = warp - b * T;
+    const float rscale = (T > 1) ? (float)(L - 1) / (float)(T - 1) : 0.f;
+    const float src = rscale * (float)j;
+    const int i0 = (int)src;
+    const int i1 = i0 + ((i0 < L - 1) ? 1 : 0);
+    const float l1 = src - (float)i0, l0 = 1.0f - l1;
+    const float* x0 = x + ((long long)b * L + i0) * C;
+    const float* x1 = x + ((long long)b * L + i1) * C;
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < MAXV; ++jj) {
+        const int k = (jj * 32 + lane) * 4;
+        float4 a = zero4();
+        if (k < C) {
+            const float4 p = ldg4(x0 + k), q = ldg4(x1 + k);
+            a.x = l0 * p.x + l1 * q.x; a.y = l0 * p.y + l1 * q.y; a.z = l0 * p.z + l1 * q.z; a.w = l0 * p.w + l1 * q.w;
+        }
+        v[jj] = a;
+        s += (a.x + a.y) + (a.z + a.w);
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < MAXV; ++jj) {
+        const int k = (jj * 32 + lane) * 4;
+        if (k < C) {
+            const float a = v[jj].x - mean, bb = v[jj].y - mean, c = v[jj].z - mean, d = v[jj].w - mean;
+            q += (a * a + bb * bb) + (c * c + d * d);
+        }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+    for (int jj = 0; jj < MAXV; ++jj) {
+        const int k = (jj * 32 + lane) * 4;
+        if (k < C) {
+            const float4 g = ldg4(gamma + k), bb = ldg4(beta + k);
+            float4 o;
+            o.x = (v[jj].x - mean) * rstd * g.x + bb.x;
+            o.y = (v[jj].y - mean) * rstd * g.y + bb.y;
+            o.z = (v[jj].z - mean) * rstd * g.z + bb.z;
+            o.w = (v[jj].w - mean) * rstd * g.w + bb.w;
+            st4(y + (long long)warp * C + k, o);
+        }
+    }
+}
+
+}  // namespace said

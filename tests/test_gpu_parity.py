@@ -1,0 +1,256 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the golden vectors produced by the
+UNMODIFIED reference (tests/golden/make_golden.py) and against the CPU oracle.
+
+Tolerances are absolute, on tensors whose entries are O(1); each is stated next to the reference's own
+fp32-vs-fp64 floor for the same quantity (tests/golden/floors.json).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def maxdiff(a, b):
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    return float((a - b).abs().max())
+
+
+def floors(golden_dir):
+    with open(os.path.join(golden_dir, "floors.json")) as f:
+        return json.load(f)["floors"]
+
+
+# ------------------------------------------------------------------------------------------------ scheduler
+def test_ddim_step_bit_exact(golden_dir, gpu_model):
+    """Fused step kernel == restated DDIMScheduler.step, bit for bit, all prediction types, eta 0 / 0.5."""
+    from said_b200 import scheduler as S
+
+    kat = load(golden_dir, "scheduler_kat.npz")
+    eng = gpu_model()._engine(torch.device(DEV))
+    x = torch.from_numpy(kat["step_x"]).to(DEV)
+    e = torch.from_numpy(kat["step_e"]).to(DEV)
+    z = torch.from_numpy(kat["step_z"]).to(DEV)
+    for code, pt in enumerate(("epsilon", "sample", "v_prediction")):
+        sch = S.DDIMScheduler(1000, beta_schedule="squaredcos_cap_v2", prediction_type=pt)
+        sch.set_timesteps(50)
+        for t in (980, 500, 0):
+            for eta in (0.0, 0.5):
+                row = S.ddim_step_table(sch, [t], eta)[0]
+                out = eng.op_ddim_step(e, x, False, 1.0, 0.0, code, row, eta_noise=z if eta > 0 else None)
+                want = kat[f"step_{pt}_{t}_{eta}"]
+                assert np.array_equal(out.cpu().numpy(), want), (pt, t, eta, maxdiff(out, want))
+
+
+def test_cfg_rescale_step_matches_oracle(gpu_model):
+    from oracle import said_oracle as O
+    from said_b200 import scheduler as S
+
+    eng = gpu_model()._engine(torch.device(DEV))
+    g = torch.Generator().manual_seed(5)
+    B, T, C = 3, 60, 32
+    pred = torch.randn(2 * B, T, C, generator=g)
+    x = torch.randn(B, T, C, generator=g)
+    sch = S.DDIMScheduler(1000, beta_schedule="squaredcos_cap_v2")
+    sch.set_timesteps(50)
+    row = S.ddim_step_table(sch, [500], 0.0)[0]
+    u, c = pred.chunk(2)
+    cfg = c + 2.0 * (c - u)
+    cfg_r = O.rescale_noise_cfg(cfg, c, 0.7)
+    for resc, ref_pred in ((0.0, cfg), (0.7, cfg_r)):
+        want = O.ddim_step(ref_pred, 500, x, O.ddim_alphas_cumprod(), 50, "epsilon", 0.0)
+        out = eng.op_ddim_step(pred.to(DEV), x.to(DEV), True, 2.0, resc, 0, row)
+        tol = 0.0 if resc == 0.0 else 2e-6   # std reduction order differs from torch.std by an ulp or two
+        assert maxdiff(out, want) <= tol, (resc, maxdiff(out, want))
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("heads,hd,T,B", [(6, 32, 300, 2), (6, 32, 61, 1), (12, 64, 300, 1), (12, 64, 130, 2), (6, 32, 469, 1)])
+def test_self_attention_vs_torch(gpu_model, heads, hd, T, B):
+    eng = gpu_model()._engine(torch.device(DEV))
+    g = torch.Generator().manual_seed(heads * 1000 + T)
+    qkv = torch.randn(B, T, 3 * heads * hd, generator=g).to(DEV)
+    out = eng.op_self_attention(qkv, heads, hd)
+    q, k, v = qkv.double().chunk(3, dim=-1)
+    sh = lambda t: t.reshape(B, T, heads, hd).transpose(1, 2)  # noqa: E731
+    ref = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) * hd**-0.5, dim=-1) @ sh(v)
+    ref = ref.transpose(1, 2).reshape(B, T, heads * hd)
+    assert maxdiff(out, ref) < 3e-6   # fp32 kernel vs fp64 math on O(1) values
+
+
+# ------------------------------------------------------------------------------------------------ denoiser
+TAP_ORDER = ["input_blocks.0", "input_blocks.1.0", "input_blocks.1.1", "middle_block.0", "middle_block.1",
+             "middle_block.2", "output_blocks.0.0", "output_blocks.0.1", "output_blocks.1.0", "output_blocks.1.1"]
+
+
+def test_denoiser_forward_golden(golden_dir, gpu_model):
+    """One UNet forward vs the reference's own module output and per-block activations.
+    Reference fp32-vs-fp64 floor: 2.4e-6; tolerance 2e-5."""
+    gd = load(golden_dir, "denoiser_forward.npz")
+    eng = gpu_model()._engine(torch.device(DEV))
+    x = torch.from_numpy(gd["x"]).to(DEV)
+    ctx = torch.from_numpy(gd["ctx"]).to(DEV)
+    t = torch.from_numpy(gd["t"])
+    out, taps = eng.denoiser_forward(x, t, ctx, taps=True)
+    errs = {}
+    for i, name in enumerate(TAP_ORDER):
+        key = "act_" + name
+        if key in gd.files:
+            errs[name] = maxdiff(taps[i].transpose(1, 2), gd[key])   # golden activations are (B, C, T)
+    errs["out_vs_ref32"] = maxdiff(out, gd["y"])
+    errs["out_vs_ref64"] = maxdiff(out, gd["y64"])
+    print(errs)
+    assert all(v < 2e-5 for v in errs.values()), errs
+
+
+def test_model_forward_api(golden_dir, gpu_model):
+    gd = load(golden_dir, "denoiser_forward.npz")
+    m = gpu_model()
+    with torch.no_grad():
+        y = m(torch.from_numpy(gd["x"]).to(DEV), torch.from_numpy(gd["t"]).to(DEV), torch.from_numpy(gd["ctx"]).to(DEV))
+    assert maxdiff(y, gd["y"]) < 2e-5
+    # scalar timestep broadcast (diffusion.py:149-152)
+    y1 = m(torch.from_numpy(gd["x"]).to(DEV), torch.tensor(500), torch.from_numpy(gd["ctx"]).to(DEV))
+    assert maxdiff(y1[1], gd["y"][1]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ audio encoder
+def test_audio_encoder_golden(golden_dir, gpu_model):
+    """Wav2Vec2 path vs the reference (transformers) output. Reference fp32-vs-fp64 floor 3.4e-6; tolerance 5e-5."""
+    gd = load(golden_dir, "audio_encoder_1s.npz")
+    m = gpu_model()
+    emb = m.get_audio_embedding(torch.from_numpy(gd["wave"]).to(DEV), 60)
+    e32, e64 = maxdiff(emb, gd["emb"]), maxdiff(emb, gd["emb64"])
+    print("encoder", e32, e64)
+    assert e32 < 5e-5 and e64 < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ chains
+def run(m, wave, noise, init=None, mask=None, steps=10, strength=1.0, gs=2.0, gr=0.0, eta=0.0, eta_noise=None,
+        inter=False, T=None):
+    wave = torch.as_tensor(wave).to(DEV)
+    T = T or int(wave.shape[1] / 16000 * 60)
+    cv = lambda a: None if a is None else torch.as_tensor(a).to(DEV)  # noqa: E731
+    with torch.no_grad():
+        return m._run(wave, cv(noise), cv(init), cv(mask), steps, strength, gs, gr, eta, T, inter, False, cv(eta_noise),
+                      return_latents=True)
+
+
+def test_config1_chain_golden(golden_dir, gpu_model):
+    """BASELINE config 1: 1 s clip, 10 DDIM steps, epsilon prediction, CFG 2.0, end to end (encoder + loop).
+    Reference fp32-vs-fp64 floor on the result: 4.8e-5; tolerance 5e-4 on result and every intermediate."""
+    gd = load(golden_dir, "config1_1s_10steps_eps.npz")
+    out = run(gpu_model("epsilon"), gd["wave"], gd["noise"], inter=True)
+    e_res = maxdiff(out.result, gd["result"])
+    e_int = max(maxdiff(a, b) for a, b in zip(out.intermediates, gd["intermediates"]))
+    print("config1", e_res, e_int, maxdiff(out.result, gd["result64"]))
+    assert len(out.intermediates) == 10
+    assert e_res < 5e-4 and e_int < 5e-4
+
+
+def test_nocfg_and_eta_rescale_golden(golden_dir, gpu_model):
+    w = load(golden_dir, "config1_1s_10steps_eps.npz")["wave"]
+    m = gpu_model("epsilon")
+    g1 = load(golden_dir, "nocfg_1s_10steps.npz")
+    out = run(m, w, g1["noise"], gs=1.0)
+    assert maxdiff(out.result, g1["result"]) < 5e-4
+    g2 = load(golden_dir, "eta_rescale_1s_10steps.npz")
+    out = run(m, w, g2["noise"], gr=0.7, eta=0.5, eta_noise=g2["eta_noise"], inter=True)
+    e = max(maxdiff(out.result, g2["result"]), max(maxdiff(a, b) for a, b in zip(out.intermediates, g2["intermediates"])))
+    print("eta+rescale", e)
+    assert e < 1e-3
+
+
+def test_editing_golden(golden_dir, gpu_model):
+    """Editing mode (init_samples + mask), 50 DDIM steps; kept region must equal clamp(init) exactly."""
+    w = load(golden_dir, "config1_1s_10steps_eps.npz")["wave"]
+    gd = load(golden_dir, "editing_1s_50steps.npz")
+    m = gpu_model("epsilon")
+    init = torch.from_numpy(gd["init"])
+    for tag, strength in (("between_s1.0", 1.0), ("shape_s0.6", 0.6)):
+        mask = torch.from_numpy(gd[f"mask_{tag}"])
+        out = run(m, w, gd[f"noise_{tag}"], init=init, mask=mask, steps=50, strength=strength)
+        res = out.result.cpu()
+        kept = mask.bool()
+        assert torch.equal(res[kept], init.clamp(0, 1)[kept])
+        e = maxdiff(res, gd[f"result_{tag}"])
+        print("editing", tag, e)
+        assert e < 5e-3   # 50 epsilon-prediction steps with untrained weights amplify rounding (oracle-vs-ref: 1.3e-4)
+
+
+@pytest.mark.parametrize("pt", ["v_prediction", "sample"])
+def test_chain_1000_steps_golden(golden_dir, gpu_model, pt):
+    """BASELINE config 2 shape: 5 s clip, 1000 DDIM steps, free-running, against the reference's result.
+    Reference fp32-vs-fp64 floors: v_prediction 1.9e-5, sample 2.4e-5; tolerance 3e-4."""
+    from said_b200.synth import normalise_waveform, synthetic_waveform
+
+    gd = load(golden_dir, f"chain_5s_1000steps_{pt}.npz")
+    wave = torch.from_numpy(normalise_waveform(synthetic_waveform(0, 5.0)))[None]
+    out = run(gpu_model(pt), wave, gd["noise"], steps=1000)
+    e32, e64 = maxdiff(out.result, gd["result"]), maxdiff(out.result, gd["result64"])
+    epre = maxdiff(out.latents, gd["preclamp64"])
+    print(pt, e32, e64, epre)
+    assert e32 < 3e-4 and e64 < 3e-4 and epre < 3e-4
+
+
+# ------------------------------------------------------------------------------------------------ invariants
+def test_invariants(gpu_model):
+    from said_b200.synth import synthetic_batch
+
+    m = gpu_model("epsilon")
+    wave = synthetic_batch(4, 1.0)
+    g = torch.Generator().manual_seed(3)
+    noise = torch.randn(4, 60, 32, generator=g)
+    full = run(m, wave, noise, steps=10).result
+    assert float(full.min()) >= 0.0 and float(full.max()) <= 1.0
+    # clips are independent: any sub-batch / permutation reproduces the same rows bit for bit
+    perm = torch.tensor([2, 0, 3, 1])
+    p = run(m, wave[perm], noise[perm], steps=10).result
+    assert torch.equal(p, full[perm])
+    halves = torch.cat([run(m, wave[:2], noise[:2], steps=10).result, run(m, wave[2:], noise[2:], steps=10).result])
+    assert torch.equal(halves, full)
+    # CUDA-graph replay and plain launches are the same program
+    m.use_cuda_graph = False
+    try:
+        plain = run(m, wave, noise, steps=10).result
+    finally:
+        m.use_cuda_graph = True
+    assert torch.equal(plain, full)
+    # strength < 1 runs int(N * strength) iterations; guidance <= 1 runs one branch
+    out = run(m, wave, noise, steps=10, strength=0.5, inter=True)
+    assert len(out.intermediates) == 5
+    # empty loop: result = clamp(init)
+    out = run(m, wave, noise, steps=10, strength=0.0)
+    assert torch.equal(out.result.cpu(), noise.clamp(0, 1))
+
+
+def test_public_inference_seeded(gpu_model):
+    """inference() consumes the CUDA generator like the reference: one randn(B,T,C) draw (diffusion.py:364)."""
+    from said_b200.synth import synthetic_batch
+
+    m = gpu_model("epsilon")
+    wave = synthetic_batch(2, 1.0).to(DEV)
+    torch.manual_seed(0)
+    a = m.inference(wave, num_inference_steps=10, guidance_scale=2.0).result
+    torch.manual_seed(0)
+    noise = torch.randn(2, 60, 32, device=DEV)
+    b = run(m, wave, noise, steps=10).result
+    assert torch.equal(a, b)
+    assert a.shape == (2, 60, 32) and a.device.type == "cuda"
+
+
+def test_cpu_tensor_fails_loudly(gpu_model):
+    from said_b200.synth import synthetic_batch
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gpu_model("epsilon").inference(synthetic_batch(1, 1.0), num_inference_steps=2)
