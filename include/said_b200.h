@@ -104,6 +104,15 @@ SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B,
 /* Number of kernels this engine has launched (graph replays counted node by node). */
 SAID_API long long said_launch_count(const said_engine* e);
 
+/* Per-kernel-family timing for bench.py's roofline: between begin and end every launch is followed by a
+ * CUDA event on its stream (run said_denoise with use_graph = 0 in between).  said_profile_end
+ * synchronises the device and returns, per family, the summed device time (ms) and the launch count.
+ * Families: 0 conv-loader GEMM, 1 LayerNorm-loader GEMM, 2 plain GEMM, 3 self-attention,
+ * 4 aligned cross-attention, 5 GroupNorm statistics, 6 CFG + scheduler step, 7 other. */
+#define SAID_PROFILE_FAMILIES 8
+SAID_API int said_profile_begin(said_engine* e);
+SAID_API int said_profile_end(said_engine* e, double* ms_out, long long* count_out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "said_op_ddim_step",
     "said_op_self_attention",
     "said_launch_count",
+    "said_profile_begin",
+    "said_profile_end",
 )
 
 
@@ -100,6 +102,8 @@ def load_library() -> ctypes.CDLL:
     lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
     lib.said_launch_count.argtypes = [vp]
     lib.said_launch_count.restype = ctypes.c_longlong
+    lib.said_profile_begin.argtypes = [vp]
+    lib.said_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ci]
     _lib = lib
     return lib
 
@@ -166,6 +170,19 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(self.lib.said_launch_count(self._h))
+
+    PROFILE_FAMILIES = ("gemm_conv3", "gemm_layernorm", "gemm_plain", "self_attention", "cross_attention3",
+                        "gn_stats", "cfg_ddim_step", "other")
+
+    def profile_begin(self) -> None:
+        self._call(self.lib.said_profile_begin(self._h))
+
+    def profile_end(self) -> Dict[str, Dict[str, float]]:
+        n = len(self.PROFILE_FAMILIES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_longlong * n)()
+        self._call(self.lib.said_profile_end(self._h, ms, cnt, n))
+        return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_FAMILIES)}
 
     # ------------------------------------------------------------------ phases
     def encode_audio(self, wave: torch.Tensor, num_frames: int) -> torch.Tensor:

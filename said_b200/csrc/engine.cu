@@ -97,6 +97,32 @@ struct said_engine {
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     long long launches = 0;
 
+    // ---- optional per-kernel-family timing (bench.py roofline): one event after every launch
+    enum Tag { TAG_GEMM_CONV = 0, TAG_GEMM_LN, TAG_GEMM_PLAIN, TAG_ATTN, TAG_XATTN, TAG_GN, TAG_STEP, TAG_OTHER, TAG_COUNT };
+    bool prof_on = false;
+    int cur_tag = TAG_OTHER;
+    std::vector<std::pair<int, cudaEvent_t>> prof_ev;
+    int after_launch(cudaStream_t st) {
+        ++launches;
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) return fail(std::string("kernel launch failed: ") + cudaGetErrorString(le));
+        if (prof_on) {
+            cudaEvent_t ev;
+            if (cudaEventCreate(&ev) != cudaSuccess || cudaEventRecord(ev, st) != cudaSuccess) return fail("profiling event failed");
+            prof_ev.emplace_back(cur_tag, ev);
+        }
+        cur_tag = TAG_OTHER;
+        return 0;
+    }
+    template <class AL, class EP>
+    int gemm(cudaStream_t st, int M, int N, int K, const AL& al, const float* Wt, int ldw, const EP& ep, int batch = 1,
+             int wz_mod = 1, long long w_zstride = 0) {
+        cur_tag = AL::kTag;
+        cudaError_t e = launch_gemm(st, M, N, K, al, Wt, ldw, ep, batch, wz_mod, w_zstride);
+        if (e != cudaSuccess) return fail(std::string("gemm launch failed: ") + cudaGetErrorString(e));
+        return after_launch(st);
+    }
+
     std::map<std::string, HostTensor> raw;
     bool ready = false;
     std::vector<float*> arena;   // device allocations holding packed weights
@@ -522,11 +548,7 @@ ALoadPlain mk_plain(const float* A, long long lda, int M) {
 
 }  // namespace
 
-#define LAUNCH_CHECK()                         \
-    do {                                       \
-        ++launches;                            \
-        CK(cudaGetLastError());                \
-    } while (0)
+#define LAUNCH_CHECK() CKI(after_launch(st))
 
 // =====================================================================================================
 // Audio encoder
@@ -570,8 +592,7 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         EpiStd ep = mk_epi(dst, CD, CD);
         ep.act = 1;
         ep.zs0 = (long long)L[i] * CD;
-        CK(launch_gemm(st, L[i], CD, conv_k[i] * CD, al, conv_w[i], CD, ep, B));
-        ++launches;
+        CKI(gemm(st, L[i], CD, conv_k[i] * CD, al, conv_w[i], CD, ep, B));
         std::swap(src, dst);
     }
     // src now holds (B, Lf, CD)
@@ -588,8 +609,7 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
     {
         EpiStd ep = mk_epi(e_d.p, H, H);
         ep.bias = fp_b;
-        CK(launch_gemm(st, M, H, CD, mk_plain(e_c.p, CD, M), fp_w, H, ep));
-        ++launches;
+        CKI(gemm(st, M, H, CD, mk_plain(e_c.p, CD, M), fp_w, H, ep));
     }
     // ---- positional conv embedding: x + gelu(conv(x)) then LayerNorm   (TF :690-693)
     {
@@ -610,8 +630,7 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         ep.zs0 = (long long)T * H;
         ep.zs1 = cg;
         ep.bias_zs = cg;
-        CK(launch_gemm(st, T, cg, pos_k * cg, al, pos_w, cg, ep, B * pos_g, pos_g, (long long)pos_k * cg * cg));
-        ++launches;
+        CKI(gemm(st, T, cg, pos_k * cg, al, pos_w, cg, ep, B * pos_g, pos_g, (long long)pos_k * cg * cg));
         layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(e_c.p, nullptr, M, H, 1e-5f, enc_ln_g, enc_ln_b, e_d.p);
         LAUNCH_CHECK();
     }
@@ -624,8 +643,7 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         {
             EpiStd ep = mk_epi(e_qkv.p, 3 * H, 3 * H);
             ep.bias = W.bqkv;
-            CK(launch_gemm(st, M, 3 * H, H, mk_plain(e_d.p, H, M), W.wqkv, 3 * H, ep));
-            ++launches;
+            CKI(gemm(st, M, 3 * H, H, mk_plain(e_d.p, H, M), W.wqkv, 3 * H, ep));
         }
         self_attention_kernel<64><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, enc_heads, B), ATT_THREADS,
                                     attention_smem_bytes<64>(), st>>>(e_qkv.p, 3 * H, 0, H, 2 * H, T, 0.125f, e_c.p, H);
@@ -635,8 +653,7 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
             ep.bias = W.bo;
             ep.res = e_d.p;
             ep.ldr = H;
-            CK(launch_gemm(st, M, H, H, mk_plain(e_c.p, H, M), W.wo, H, ep));
-            ++launches;
+            CKI(gemm(st, M, H, H, mk_plain(e_c.p, H, M), W.wo, H, ep));
         }
         layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(e_qkv.p, nullptr, M, H, 1e-5f, W.ln1_g, W.ln1_b, e_d.p);
         LAUNCH_CHECK();
@@ -644,16 +661,14 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
             EpiStd ep = mk_epi(e_ff.p, enc_ffn, enc_ffn);
             ep.bias = W.bff1;
             ep.act = 1;
-            CK(launch_gemm(st, M, enc_ffn, H, mk_plain(e_d.p, H, M), W.wff1, enc_ffn, ep));
-            ++launches;
+            CKI(gemm(st, M, enc_ffn, H, mk_plain(e_d.p, H, M), W.wff1, enc_ffn, ep));
         }
         {
             EpiStd ep = mk_epi(e_c.p, H, H);
             ep.bias = W.bff2;
             ep.res = e_d.p;
             ep.ldr = H;
-            CK(launch_gemm(st, M, H, enc_ffn, mk_plain(e_ff.p, enc_ffn, M), W.wff2, H, ep));
-            ++launches;
+            CKI(gemm(st, M, H, enc_ffn, mk_plain(e_ff.p, enc_ffn, M), W.wff2, H, ep));
         }
         float* dst_ln = (l == enc_layers - 1 && last_direct) ? emb_out : e_d.p;
         layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(e_c.p, nullptr, M, H, 1e-5f, W.ln2_g, W.ln2_b, dst_ln);
@@ -662,8 +677,7 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
     if (!last_direct) {   // audio_proj_layer (diffusion.py:228-229)
         EpiStd ep = mk_epi(emb_out, proj_dim, proj_dim);
         ep.bias = b_aproj;
-        CK(launch_gemm(st, M, proj_dim, H, mk_plain(e_d.p, H, M), w_aproj, proj_dim, ep));
-        ++launches;
+        CKI(gemm(st, M, proj_dim, H, mk_plain(e_d.p, H, M), w_aproj, proj_dim, ep));
     }
     return 0;
 }
@@ -680,13 +694,11 @@ int said_engine::prepare_context(const float* emb, int B, int T, int with_uncond
     CK(vnull_tmp.ensure((size_t)N));
     {
         EpiStd ep = mk_epi(kv.p, N, N);
-        CK(launch_gemm(st, M, N, ctx_dim, mk_plain(emb, ctx_dim, M), w_kv, N, ep));
-        ++launches;
+        CKI(gemm(st, M, N, ctx_dim, mk_plain(emb, ctx_dim, M), w_kv, N, ep));
     }
     if (with_uncond) {
         EpiStd ep = mk_epi(vnull_tmp.p, N, N);
-        CK(launch_gemm(st, 1, N, ctx_dim, mk_plain(null_emb, ctx_dim, 1), w_kv, N, ep));
-        ++launches;
+        CKI(gemm(st, 1, N, ctx_dim, mk_plain(null_emb, ctx_dim, 1), w_kv, N, ep));
         for (int l = 0; l < 4; ++l)
             CK(cudaMemcpyAsync(vnull.p + l * C, vnull_tmp.p + l * 2 * C + C, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
@@ -736,6 +748,7 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         return 0;
     };
     auto gn = [&](const float* src, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh, int ld, int off) -> int {
+        cur_tag = TAG_GN;
         gn_stats_kernel<<<Bp, GN_THREADS, 0, st>>>(src, T, cpg, eps_, g, b, osc, osh, ld, off);
         LAUNCH_CHECK();
         return 0;
@@ -758,8 +771,7 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ep.emb_ld = 5 * C;
             ep.step_ptr = step_ptr;
             ep.T = T;
-            CK(launch_gemm(st, M, C, 3 * cin, al, W.w1, C, ep));
-            ++launches;
+            CKI(gemm(st, M, C, 3 * cin, al, W.w1, C, ep));
         }
         CKI(gn(t1, 6, 1e-5f, W.gn2_g, W.gn2_b, sc, sh, C, 0));
         if (skip) {
@@ -769,22 +781,19 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ALoadConv3 al{t1, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
             EpiStd ep = mk_epi(x1, C, C);
             ep.bias = W.b2;
-            CK(launch_gemm(st, M, C, 3 * C, al, W.w2, C, ep));
-            ++launches;
+            CKI(gemm(st, M, C, 3 * C, al, W.w2, C, ep));
             ALoadConv3 al2{a, skip, C, C, cin, T, M, Bp, nullptr, nullptr, 0};   // K3 = 0: raw centre tap only
             EpiStd ep2 = mk_epi(out, C, C);
             ep2.res = x1;
             ep2.ldr = C;
-            CK(launch_gemm(st, M, C, cin, al2, W.w2 + (size_t)3 * C * C, C, ep2));
-            ++launches;
+            CKI(gemm(st, M, C, cin, al2, W.w2 + (size_t)3 * C * C, C, ep2));
         } else {
             ALoadConv3 al{t1, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
             EpiStd ep = mk_epi(out, C, C);
             ep.bias = W.b2;
             ep.res = a;
             ep.ldr = C;
-            CK(launch_gemm(st, M, C, 3 * C, al, W.w2, C, ep));
-            ++launches;
+            CKI(gemm(st, M, C, 3 * C, al, W.w2, C, ep));
         }
         return 0;
     };
@@ -795,9 +804,9 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         {   // q,k,v = LN1(GN(h)) W   (no bias)
             ALoadLN al{h, M, T, sc_st, sh_st, W.ln1_g, W.ln1_b, 1e-5f};
             EpiStd ep = mk_epi(qkv.p, 3 * C, 3 * C);
-            CK(launch_gemm(st, M, 3 * C, C, al, W.wqkv, 3 * C, ep));
-            ++launches;
+            CKI(gemm(st, M, 3 * C, C, al, W.wqkv, 3 * C, ep));
         }
+        cur_tag = TAG_ATTN;
         self_attention_kernel<32><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, Bp), ATT_THREADS,
                                     attention_smem_bytes<32>(), st>>>(qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
         LAUNCH_CHECK();
@@ -810,17 +819,16 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ep.res_shift = sh_st;
             ep.res_aff_ld = C;
             ep.T = T;
-            CK(launch_gemm(st, M, C, C, mk_plain(ao.p, C, M), W.wo1, C, ep));
-            ++launches;
+            CKI(gemm(st, M, C, C, mk_plain(ao.p, C, M), W.wo1, C, ep));
         }
         if (Mc > 0) {   // cross-attention queries, conditional samples only
             ALoadLN al{x1 + (size_t)n_uncond * T * C, Mc, T, nullptr, nullptr, W.ln2_g, W.ln2_b, 1e-5f};
             EpiStd ep = mk_epi(q2.p, C, C);
-            CK(launch_gemm(st, Mc, C, C, al, W.wq2, C, ep));
-            ++launches;
+            CKI(gemm(st, Mc, C, C, al, W.wq2, C, ep));
         }
         {
             const long long tot = (long long)M * HEADS;
+            cur_tag = TAG_XATTN;
             cross_attention3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q2.p, kv.p, 8 * C, i * 2 * C, vnull.p + i * C,
                                                                                   n_uncond, Bp, T, att_scale, ao.p);
             LAUNCH_CHECK();
@@ -830,30 +838,26 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ep.bias = W.bo2;
             ep.res = x1;
             ep.ldr = C;
-            CK(launch_gemm(st, M, C, C, mk_plain(ao.p, C, M), W.wo2, C, ep));
-            ++launches;
+            CKI(gemm(st, M, C, C, mk_plain(ao.p, C, M), W.wo2, C, ep));
         }
         {   // GEGLU
             ALoadLN al{x2, M, T, nullptr, nullptr, W.ln3_g, W.ln3_b, 1e-5f};
             EpiGeglu ep{ffb.p, FF, 2 * FF, W.bff1};
-            CK(launch_gemm(st, M, 2 * FF, C, al, W.wff1, 2 * FF, ep));
-            ++launches;
+            CKI(gemm(st, M, 2 * FF, C, al, W.wff1, 2 * FF, ep));
         }
         {   // x3 = ff2 + x2  -> x1
             EpiStd ep = mk_epi(x1, C, C);
             ep.bias = W.bff2;
             ep.res = x2;
             ep.ldr = C;
-            CK(launch_gemm(st, M, C, FF, mk_plain(ffb.p, FF, M), W.wff2, C, ep));
-            ++launches;
+            CKI(gemm(st, M, C, FF, mk_plain(ffb.p, FF, M), W.wff2, C, ep));
         }
         {   // out = proj_out(x3) + h
             EpiStd ep = mk_epi(out, C, C);
             ep.bias = W.bproj;
             ep.res = h;
             ep.ldr = C;
-            CK(launch_gemm(st, M, C, C, mk_plain(x1, C, M), W.wproj, C, ep));
-            ++launches;
+            CKI(gemm(st, M, C, C, mk_plain(x1, C, M), W.wproj, C, ep));
         }
         return 0;
     };
@@ -862,8 +866,7 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         ALoadConv3 al{x, nullptr, in_ch, 0, in_ch, T, M, src_batch, nullptr, nullptr, 3 * in_ch};
         EpiStd ep = mk_epi(h0, C, C);
         ep.bias = b_in;
-        CK(launch_gemm(st, M, C, 3 * in_ch, al, w_in, C, ep));
-        ++launches;
+        CKI(gemm(st, M, C, 3 * in_ch, al, w_in, C, ep));
     }
     CKI(tap(h0));
     CKI(resblock(0, h0, nullptr, A));      CKI(tap(A));
@@ -880,8 +883,7 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         ALoadConv3 al{Bb, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
         EpiStd ep = mk_epi(eps_out, in_ch, in_ch);
         ep.bias = b_out;
-        CK(launch_gemm(st, M, in_ch, 3 * C, al, w_out, in_ch, ep));
-        ++launches;
+        CKI(gemm(st, M, in_ch, 3 * C, al, w_out, in_ch, ep));
     }
     return 0;
 }
@@ -945,6 +947,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
 
         auto one_step = [&]() -> int {
             CKI(forward(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
+            cur_tag = TAG_STEP;
             ddim_step_kernel<<<B, 256, 0, st>>>(sp);
             LAUNCH_CHECK();
             add_int_kernel<<<1, 1, 0, st>>>(step_ctr, 1);
@@ -1138,5 +1141,32 @@ int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, i
 }
 
 long long said_launch_count(const said_engine* e) { return e ? e->launches : 0; }
+
+int said_profile_begin(said_engine* e) {
+    if (!e) return fail("null engine");
+    for (auto& pe : e->prof_ev) cudaEventDestroy(pe.second);
+    e->prof_ev.clear();
+    e->prof_on = true;
+    return 0;
+}
+
+int said_profile_end(said_engine* e, double* ms_out, long long* count_out, int n) {
+    if (!e) return fail("null engine");
+    e->prof_on = false;
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < n; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+    // time attributed to a launch = interval between the previous launch's end event and its own end
+    // event (kernels of one stream run back to back, so this is the kernel's duration plus launch gap)
+    for (size_t i = 1; i < e->prof_ev.size(); ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e->prof_ev[i - 1].second, e->prof_ev[i].second));
+        const int tag = e->prof_ev[i].first;
+        if (tag >= 0 && tag < n) { ms_out[tag] += ms; count_out[tag] += 1; }
+    }
+    for (auto& pe : e->prof_ev) cudaEventDestroy(pe.second);
+    e->prof_ev.clear();
+    return 0;
+}
 
 }  // extern "C"

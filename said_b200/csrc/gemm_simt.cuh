@@ -34,6 +34,7 @@ struct GemmDims {
 // Plain strided matrix; rows may overlap (lda < K) which is how strided Conv1d over a channel-last
 // signal becomes a GEMM: row j = frames [s*j, s*j + k) = one contiguous run of k*C floats.
 struct ALoadPlain {
+    static constexpr int kTag = 2;
     const float* A;
     long long lda;
     long long zstride;      // floats between A batches (blockIdx.z / zdiv)
@@ -50,6 +51,7 @@ struct ALoadPlain {
 // per-sample per-channel affine (the SpatialTransformer GroupNorm, attention.py:228, folded in so
 // its output is never materialised).  y = ((x*ps+pb) - mean) * rstd * gamma + beta.
 struct ALoadLN {
+    static constexpr int kTag = 1;
     const float* X;         // (M, 192) rows
     int M, T;
     const float* pre_scale; // (B', 192) or null
@@ -118,6 +120,7 @@ struct ALoadLN {
 // k = tap*Cin + c for k < 3*Cin; k >= 3*Cin addresses the raw centre tap (the ResBlock's 1x1
 // skip_connection, openaimodel.py:187-194, fused as extra K).  Zero padding applies after GN+SiLU.
 struct ALoadConv3 {
+    static constexpr int kTag = 0;
     const float* src0;
     const float* src1;      // null when there is no concat
     int C0, C1, Cin;        // Cin = C0 + C1
