@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=100, help="loop iterations per CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-b1", action="store_true")
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
+                    help="contraction precision of the denoiser GEMMs (see include/said_b200.h said_set_precision)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -226,6 +228,7 @@ def main():
     model = SAID_UNet1D(prediction_type="epsilon")
     model.load_state_dict(sd)
     model.to(dev).eval()
+    model.precision = args.precision
     eng = model._engine(dev)
 
     B = args.batch
@@ -301,7 +304,8 @@ def main():
     gemm_flops_per_step = 2 * B * fl["gemm"]
     achieved_tflops = (gemm_flops_per_step * prof_steps) / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {
-        "kernel": "gemm_simt_kernel (all loader/epilogue instantiations; every Linear/Conv1d of the UNet)",
+        "kernel": ("gemm_tc_kernel (tcgen05, " + args.precision + ")" if args.precision != "fp32" else "gemm_simt_kernel (fp32 FFMA)")
+                  + ": all loader/epilogue instantiations = every Linear/Conv1d of the UNet",
         "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
@@ -309,15 +313,16 @@ def main():
         "avg_launch_ms": gemm_ms / max(1, gemm_launches),
         "share_of_step": gemm_ms / loop_ms if loop_ms > 0 else None,
         "family_ms_share": {k: (v["ms"] / loop_ms if loop_ms > 0 else None) for k, v in prof.items()},
-        "note": "fp32 FFMA contraction engine (IEEE fp32 parity mode); measured with one CUDA event per launch over "
-                f"{prof_steps} un-graphed loop iterations at the bench batch",
+        "note": f"precision mode {args.precision}; algorithmic FLOPs (one multiply-add per weight per row; the extra passes of "
+                f"the 3xTF32 split are not counted); measured with one CUDA event per launch over {prof_steps} un-graphed loop "
+                "iterations at the bench batch",
     }
 
     line = {
         "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "denoise_clip_steps_per_s": value * NUM_STEPS,
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split, fp32 accumulate)", "tf32": "tf32"}[args.precision],
+        "data": "synthetic", "denoise_clip_steps_per_s": value * NUM_STEPS,
         "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(wave_host.numel() * 4) * world,

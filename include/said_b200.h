@@ -104,6 +104,13 @@ SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B,
 /* Number of kernels this engine has launched (graph replays counted node by node). */
 SAID_API long long said_launch_count(const said_engine* e);
 
+/* Contraction precision of the denoiser's Linear / Conv1d layers:
+ *   0  IEEE fp32 FFMA (CUDA cores);
+ *   1  tcgen05 tensor cores, 3xTF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulate): fp32-level accuracy [default];
+ *   2  tcgen05 tensor cores, single TF32 pass (what the reference gets from cuDNN for its convs on a GPU).
+ * GEMMs with fewer than tc_min_rows rows (<= 0: keep the current threshold) stay on the FFMA kernel. */
+SAID_API int said_set_precision(said_engine* e, int mode, int tc_min_rows);
+
 /* Per-kernel-family timing for bench.py's roofline: between begin and end every launch is followed by a
  * CUDA event on its stream (run said_denoise with use_graph = 0 in between).  said_profile_end
  * synchronises the device and returns, per family, the summed device time (ms) and the launch count.

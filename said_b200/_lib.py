@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "said_op_ddim_step",
     "said_op_self_attention",
     "said_launch_count",
+    "said_set_precision",
     "said_profile_begin",
     "said_profile_end",
 )
@@ -102,6 +103,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
     lib.said_launch_count.argtypes = [vp]
     lib.said_launch_count.restype = ctypes.c_longlong
+    lib.said_set_precision.argtypes = [vp, ci, ci]
     lib.said_profile_begin.argtypes = [vp]
     lib.said_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ci]
     _lib = lib
@@ -173,6 +175,13 @@ class Engine:
 
     PROFILE_FAMILIES = ("gemm_conv3", "gemm_layernorm", "gemm_plain", "self_attention", "cross_attention3",
                         "gn_stats", "cfg_ddim_step", "other")
+
+    PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+
+    def set_precision(self, mode: str, tc_min_rows: int = 0) -> None:
+        if mode not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(self.PRECISIONS)}")
+        self._call(self.lib.said_set_precision(self._h, self.PRECISIONS[mode], int(tc_min_rows)))
 
     def profile_begin(self) -> None:
         self._call(self.lib.said_profile_begin(self._h))

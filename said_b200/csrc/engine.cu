@@ -22,6 +22,7 @@
 #include "diffusion_kernels.cuh"
 #include "encoder_kernels.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "norm_kernels.cuh"
 
 using namespace said;
@@ -114,10 +115,47 @@ struct said_engine {
         cur_tag = TAG_OTHER;
         return 0;
     }
+    // ---- tensor-core path: per GEMM weight, a pre-split / pre-swizzled tile image (gemm_tc.cuh)
+    struct TcW { float* img; int K, N, bn; };
+    std::map<const float*, TcW> tcmap;   // keyed by the SIMT "Wt" device pointer of the same weight
+    int precision = 1;                   // 0: fp32 FFMA, 1: 3xTF32 tcgen05 (fp32-level), 2: 1xTF32 tcgen05
+    int register_tc(const float* key, const float* host_wt, int K, int N, int ldw) {
+        const int bn = (N % 192 == 0) ? 192 : (N == 32 ? 32 : 0);
+        if (bn == 0 || K % tc::BK != 0) return 0;
+        std::vector<float> img;
+        tc::pack_weights_tc(host_wt, K, N, ldw, bn, 3, img);
+        float* d = nullptr;
+        CKI(upload(img, &d));
+        tcmap[key] = TcW{d, K, N, bn};
+        return 0;
+    }
+    static ALoadLN8 to_tc_loader(const ALoadLN& a) { return ALoadLN8{a.X, a.M, a.T, a.pre_scale, a.pre_shift, a.gamma, a.beta, a.eps}; }
+    static const ALoadPlain& to_tc_loader(const ALoadPlain& a) { return a; }
+    static const ALoadConv3& to_tc_loader(const ALoadConv3& a) { return a; }
+    template <class AL, class EP>
+    int gemm_tc_dispatch(cudaStream_t st, int M, int N, int K, const AL& al, const TcW& w, const EP& ep) {
+        const int stride = 2 * w.bn * 32;   // image holds hi + lo tiles
+        cudaError_t e = cudaErrorInvalidValue;
+        if (w.bn == 192) {
+            e = precision == 1 ? tc::launch_gemm_tc<192, 3>(st, M, N, K, al, w.img, stride, ep)
+                               : tc::launch_gemm_tc<192, 1>(st, M, N, K, al, w.img, stride, ep);
+        } else if (w.bn == 32) {
+            e = precision == 1 ? tc::launch_gemm_tc<32, 3>(st, M, N, K, al, w.img, stride, ep)
+                               : tc::launch_gemm_tc<32, 1>(st, M, N, K, al, w.img, stride, ep);
+        }
+        if (e != cudaSuccess) return fail(std::string("tcgen05 gemm launch failed: ") + cudaGetErrorString(e));
+        return after_launch(st);
+    }
+    int tc_min_rows = 2048;              // below this many rows the small-tile FFMA kernel spreads better over the SMs
     template <class AL, class EP>
     int gemm(cudaStream_t st, int M, int N, int K, const AL& al, const float* Wt, int ldw, const EP& ep, int batch = 1,
              int wz_mod = 1, long long w_zstride = 0) {
         cur_tag = AL::kTag;
+        if (precision != 0 && batch == 1 && M >= tc_min_rows) {
+            auto it = tcmap.find(Wt);
+            if (it != tcmap.end() && it->second.K == K && it->second.N == N)
+                return gemm_tc_dispatch(st, M, N, K, to_tc_loader(al), it->second, ep);
+        }
         cudaError_t e = launch_gemm(st, M, N, K, al, Wt, ldw, ep, batch, wz_mod, w_zstride);
         if (e != cudaSuccess) return fail(std::string("gemm launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
@@ -259,6 +297,7 @@ int said_engine::commit_denoiser() {
         std::vector<float> w((size_t)3 * in_ch * C);
         pack_w(*win, C, in_ch, 3, w, C, 0, 0);
         CKI(upload(w, &w_in));
+        CKI(register_tc(w_in, w.data(), 3 * in_ch, C, C));
         CKI(upload_raw(P + "input_blocks.0.0.bias", {C}, &b_in));
     }
     // ---- ResBlocks in execution order (openaimodel.py:697-704)
@@ -275,6 +314,7 @@ int said_engine::commit_denoiser() {
         std::vector<float> w1((size_t)3 * r.cin * C);
         pack_w(*t, C, r.cin, 3, w1, C, 0, 0);
         CKI(upload(w1, &r.w1));
+        CKI(register_tc(r.w1, w1.data(), 3 * r.cin, C, C));
         CKI(upload_raw(p + "in_layers.2.bias", {C}, &r.b1));
         CKI(upload_raw(p + "emb_layers.1.weight", {C, TE}, (float**)&te.wr[i]));
         CKI(upload_raw(p + "emb_layers.1.bias", {C}, (float**)&te.br[i]));
@@ -293,6 +333,8 @@ int said_engine::commit_denoiser() {
             for (int j = 0; j < C; ++j) b2[j] += t->data[j];
         }
         CKI(upload(w2, &r.w2));
+        CKI(register_tc(r.w2, w2.data(), 3 * C, C, C));
+        if (r.skip) CKI(register_tc(r.w2 + (size_t)3 * C * C, w2.data() + (size_t)3 * C * C, r.cin, C, C));
         CKI(upload(b2, &r.b2));
     }
     // ---- SpatialTransformers in execution order
@@ -317,17 +359,21 @@ int said_engine::commit_denoiser() {
             pack_w(*t, C, C, 1, qkvw, 3 * C, 0, j * C);
         }
         CKI(upload(qkvw, &s.wqkv));
+        CKI(register_tc(s.wqkv, qkvw.data(), C, 3 * C, 3 * C));
         std::vector<float> w((size_t)C * C);
         CKI(need(b + "attn1.to_out.0.weight", {C, C}, &t));
         pack_w(*t, C, C, 1, w, C, 0, 0);
         CKI(upload(w, &s.wo1));
+        CKI(register_tc(s.wo1, w.data(), C, C, C));
         CKI(upload_raw(b + "attn1.to_out.0.bias", {C}, &s.bo1));
         CKI(need(b + "attn2.to_q.weight", {C, C}, &t));
         pack_w(*t, C, C, 1, w, C, 0, 0);
         CKI(upload(w, &s.wq2));
+        CKI(register_tc(s.wq2, w.data(), C, C, C));
         CKI(need(b + "attn2.to_out.0.weight", {C, C}, &t));
         pack_w(*t, C, C, 1, w, C, 0, 0);
         CKI(upload(w, &s.wo2));
+        CKI(register_tc(s.wo2, w.data(), C, C, C));
         CKI(upload_raw(b + "attn2.to_out.0.bias", {C}, &s.bo2));
         CKI(need(b + "attn2.to_k.weight", {C, ctx_dim}, &t));
         pack_w(*t, C, ctx_dim, 1, wkv, 8 * C, 0, i * 2 * C);
@@ -341,6 +387,7 @@ int said_engine::commit_denoiser() {
             for (int k = 0; k < C; ++k) wff1[(size_t)k * 2 * FF + col] = t->data[(size_t)o * C + k];
         }
         CKI(upload(wff1, &s.wff1));
+        CKI(register_tc(s.wff1, wff1.data(), C, 2 * FF, 2 * FF));
         CKI(need(b + "ff.net.0.proj.bias", {2 * FF}, &t));
         for (int o = 0; o < 2 * FF; ++o) bff1[o < FF ? 2 * o : 2 * (o - FF) + 1] = t->data[o];
         CKI(upload(bff1, &s.bff1));
@@ -348,13 +395,16 @@ int said_engine::commit_denoiser() {
         std::vector<float> wff2((size_t)FF * C);
         pack_w(*t, C, FF, 1, wff2, C, 0, 0);
         CKI(upload(wff2, &s.wff2));
+        CKI(register_tc(s.wff2, wff2.data(), FF, C, C));
         CKI(upload_raw(b + "ff.net.2.bias", {C}, &s.bff2));
         CKI(need(p + "proj_out.weight", {C, C, 1}, &t));
         pack_w(*t, C, C, 1, w, C, 0, 0);
         CKI(upload(w, &s.wproj));
+        CKI(register_tc(s.wproj, w.data(), C, C, C));
         CKI(upload_raw(p + "proj_out.bias", {C}, &s.bproj));
     }
     CKI(upload(wkv, &w_kv));
+    CKI(register_tc(w_kv, wkv.data(), ctx_dim, 8 * C, 8 * C));
     // ---- output head
     CKI(upload_raw(P + "out.0.weight", {C}, &out_gn_g));
     CKI(upload_raw(P + "out.0.bias", {C}, &out_gn_b));
@@ -362,6 +412,7 @@ int said_engine::commit_denoiser() {
     std::vector<float> wo((size_t)3 * C * in_ch);
     pack_w(*t, in_ch, C, 3, wo, in_ch, 0, 0);
     CKI(upload(wo, &w_out));
+    CKI(register_tc(w_out, wo.data(), 3 * C, in_ch, in_ch));
     CKI(upload_raw(P + "out.2.bias", {in_ch}, &b_out));
     // ---- null condition, optional audio projection
     CKI(need("null_cond_emb", {1, 1, ctx_dim}, &t));
@@ -509,6 +560,7 @@ int said_engine::commit() {
     CK(cudaDeviceSynchronize());
     for (float* p : arena) cudaFree(p);
     arena.clear();
+    tcmap.clear();
     ready = false;
     ctx_B = ctx_T = 0;
     CKI(commit_denoiser());
@@ -1141,6 +1193,14 @@ int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, i
 }
 
 long long said_launch_count(const said_engine* e) { return e ? e->launches : 0; }
+
+int said_set_precision(said_engine* e, int mode, int tc_min_rows) {
+    if (!e) return fail("null engine");
+    if (mode < 0 || mode > 2) return fail("said_set_precision: mode must be 0 (fp32 FFMA), 1 (3xTF32 tcgen05) or 2 (TF32 tcgen05)");
+    e->precision = mode;
+    if (tc_min_rows > 0) e->tc_min_rows = tc_min_rows;
+    return 0;
+}
 
 int said_profile_begin(said_engine* e) {
     if (!e) return fail("null engine");

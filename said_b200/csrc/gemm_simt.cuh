@@ -50,7 +50,11 @@ struct ALoadPlain {
 // LayerNorm over the full row (row length == K == 192) applied on load, optionally preceded by a
 // per-sample per-channel affine (the SpatialTransformer GroupNorm, attention.py:228, folded in so
 // its output is never materialised).  y = ((x*ps+pb) - mean) * rstd * gamma + beta.
-struct ALoadLN {
+// LPR consecutive lanes share a row (4 in the SIMT kernel, 8 in the tcgen05 kernel) and compute its
+// statistics together: lane kq holds the float4s kq, kq + LPR, ... of the row in registers (two-pass
+// mean / variance without re-reading).
+template <int LPR>
+struct ALoadLNT {
     static constexpr int kTag = 1;
     const float* X;         // (M, 192) rows
     int M, T;
@@ -60,8 +64,14 @@ struct ALoadLN {
     const float* beta;
     float eps;
     static constexpr int C = 192;
+    static constexpr int NV = C / 4 / LPR;   // float4 per lane
     struct Ctx { const float* p; const float* ps; const float* pb; float mean, rstd; bool ok; };
     SAID_DEVINL void set_z(int) {}
+    SAID_DEVINL static float group_sum(float v) {
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
     SAID_DEVINL Ctx prep(int m, int kq) const {
         Ctx c;
         c.ok = m < M;
@@ -70,12 +80,11 @@ struct ALoadLN {
         const int b = mm / T;
         c.ps = pre_scale ? pre_scale + (long long)b * C : nullptr;
         c.pb = pre_scale ? pre_shift + (long long)b * C : nullptr;
-        // the 4 lanes sharing this row each hold a quarter (48 floats) in registers
-        float4 v[12];
+        float4 v[NV];
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            const int k = kq * 48 + j * 4;
+        for (int j = 0; j < NV; ++j) {
+            const int k = (kq + LPR * j) * 4;
             float4 x = c.ok ? ldg4(c.p + k) : zero4();
             if (c.ps) {
                 const float4 a = ldg4(c.ps + k), d = ldg4(c.pb + k);
@@ -84,18 +93,14 @@ struct ALoadLN {
             v[j] = x;
             s += (x.x + x.y) + (x.z + x.w);
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        c.mean = s * (1.0f / C);
+        c.mean = group_sum(s) * (1.0f / C);
         float q = 0.f;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
+        for (int j = 0; j < NV; ++j) {
             const float a = v[j].x - c.mean, b2 = v[j].y - c.mean, d = v[j].z - c.mean, e = v[j].w - c.mean;
             q += (a * a + b2 * b2) + (d * d + e * e);
         }
-        q += __shfl_xor_sync(0xffffffffu, q, 1);
-        q += __shfl_xor_sync(0xffffffffu, q, 2);
-        c.rstd = 1.0f / sqrtf(q * (1.0f / C) + eps);
+        c.rstd = 1.0f / sqrtf(group_sum(q) * (1.0f / C) + eps);
         return c;
     }
     SAID_DEVINL float4 load4(const Ctx& c, int k) const {
@@ -113,6 +118,8 @@ struct ALoadLN {
         return x;
     }
 };
+using ALoadLN = ALoadLNT<4>;
+using ALoadLN8 = ALoadLNT<8>;
 
 // Conv1d(k=3, pad=1) over a channel-last signal that is the channel-concatenation of up to two
 // tensors (the UNet skip concat, openaimodel.py:703, is never materialised), with GroupNorm+SiLU
@@ -193,8 +200,21 @@ struct EpiStd {
     SAID_DEVINL void store(int m, int n, const float (&acc)[TN]) const {
         if (n >= N) return;
         float v[TN];
+        if (bias) {
+            if constexpr (TN % 4 == 0) {
 #pragma unroll
-        for (int j = 0; j < TN; ++j) v[j] = acc[j] + (bias ? __ldg(bias + n + j) : 0.f);
+                for (int j = 0; j < TN; j += 4) {
+                    const float4 bq = ldg4(bias + n + j);
+                    v[j] = acc[j] + bq.x; v[j + 1] = acc[j + 1] + bq.y; v[j + 2] = acc[j + 2] + bq.z; v[j + 3] = acc[j + 3] + bq.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) v[j] = acc[j] + __ldg(bias + n + j);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) v[j] = acc[j];
+        }
         if (act == 1) {
 #pragma unroll
             for (int j = 0; j < TN; ++j) v[j] = gelu_erf(v[j]);
@@ -207,20 +227,36 @@ struct EpiStd {
         }
         if (res) {
             const float* r = res + (long long)m * ldr + n;
+            if constexpr (TN % 4 == 0) {
 #pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                float x = __ldg(r + j);
-                if (res_scale) x = x * __ldg(res_scale + (long long)b * res_aff_ld + n + j) + __ldg(res_shift + (long long)b * res_aff_ld + n + j);
-                v[j] = x + v[j];
+                for (int j = 0; j < TN; j += 4) {
+                    float4 x = ldg4(r + j);
+                    if (res_scale) {
+                        const float4 a = ldg4(res_scale + (long long)b * res_aff_ld + n + j);
+                        const float4 d = ldg4(res_shift + (long long)b * res_aff_ld + n + j);
+                        x.x = x.x * a.x + d.x; x.y = x.y * a.y + d.y; x.z = x.z * a.z + d.z; x.w = x.w * a.w + d.w;
+                    }
+                    v[j] = x.x + v[j]; v[j + 1] = x.y + v[j + 1]; v[j + 2] = x.z + v[j + 2]; v[j + 3] = x.w + v[j + 3];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    float x = __ldg(r + j);
+                    if (res_scale) x = x * __ldg(res_scale + (long long)b * res_aff_ld + n + j) + __ldg(res_shift + (long long)b * res_aff_ld + n + j);
+                    v[j] = x + v[j];
+                }
             }
         }
         float* o = out + (long long)m * ldo + n;
-        if constexpr (TN == 4) st4(o, make_float4(v[0], v[1], v[2], v[3]));
-        else {
+        if constexpr (TN % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) st4(o + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
 #pragma unroll
             for (int j = 0; j < TN; ++j) o[j] = v[j];
         }
     }
+    SAID_DEVINL void store16(int m, int n, const float (&acc)[16]) const { store<16>(m, n, acc); }
 };
 
 // GEGLU (attention.py:25-32): weight columns are packed interleaved (2j = value_j, 2j+1 = gate_j),
@@ -241,6 +277,19 @@ struct EpiGeglu {
             const float gate = acc[j + 1] + __ldg(bias + n + j + 1);
             o[j >> 1] = val * gelu_erf(gate);
         }
+    }
+    SAID_DEVINL void store16(int m, int n, const float (&acc)[16]) const {
+        if (n >= N) return;
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 bq = ldg4(bias + n + j);
+            r[j >> 1] = (acc[j] + bq.x) * gelu_erf(acc[j + 1] + bq.y);
+            r[(j >> 1) + 1] = (acc[j + 2] + bq.z) * gelu_erf(acc[j + 3] + bq.w);
+        }
+        float* o = out + (long long)m * ldo + (n >> 1);
+        st4(o, make_float4(r[0], r[1], r[2], r[3]));
+        st4(o + 4, make_float4(r[4], r[5], r[6], r[7]));
     }
 };
 

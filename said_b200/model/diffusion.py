@@ -171,6 +171,10 @@ class SAID(ABC, nn.Module):
         self._engines: Dict[int, Engine] = {}
         self._engine_keys: Dict[int, tuple] = {}
         self.use_cuda_graph = True
+        # contraction precision of the denoiser GEMMs: "tf32x3" (tcgen05, 3xTF32 split: fp32-level accuracy),
+        # "tf32" (tcgen05, single pass) or "fp32" (FFMA); GEMMs below tc_min_rows rows stay on the FFMA kernel
+        self.precision = "tf32x3"
+        self.tc_min_rows = 0
 
     # ------------------------------------------------------------------ state dict compatibility
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -207,6 +211,7 @@ class SAID(ABC, nn.Module):
             )  # ldm/util.py:75-78, evaluated with the same torch ops as the reference
             eng.load_weights(tensors)
             self._engine_keys[idx] = key
+        eng.set_precision(self.precision, self.tc_min_rows)
         return eng
 
     # ------------------------------------------------------------------ reference API
