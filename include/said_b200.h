@@ -104,6 +104,11 @@ SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B,
 /* Number of kernels this engine has launched (graph replays counted node by node). */
 SAID_API long long said_launch_count(const said_engine* e);
 
+/* Diagnostics: average milliseconds of the tcgen05 GEMM (N = 192, plain loader, M x K activations) over
+ * `iters` launches on scratch buffers; dbg bits disable parts of the kernel (1 A loads, 2 weight copies,
+ * 4 epilogue I/O, 8 MMAs) to attribute time.  Synchronises. */
+SAID_API int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int with_residual, int dbg, int iters, float* ms_out);
+
 /* Contraction precision of the denoiser's Linear / Conv1d layers:
  *   0  IEEE fp32 FFMA (CUDA cores);
  *   1  tcgen05 tensor cores, 3xTF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulate): fp32-level accuracy [default];

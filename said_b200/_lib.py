@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "said_op_ddim_step",
     "said_op_self_attention",
     "said_launch_count",
+    "said_op_gemm_tc_bench",
     "said_set_precision",
     "said_profile_begin",
     "said_profile_end",
@@ -104,6 +105,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_launch_count.argtypes = [vp]
     lib.said_launch_count.restype = ctypes.c_longlong
     lib.said_set_precision.argtypes = [vp, ci, ci]
+    lib.said_op_gemm_tc_bench.argtypes = [vp, ci, ci, ci, ci, ci, ci, ctypes.POINTER(cf)]
     lib.said_profile_begin.argtypes = [vp]
     lib.said_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ci]
     _lib = lib
@@ -294,6 +296,12 @@ class Engine:
                                                   row.ctypes.data, _ptr(en), self._stream()))
             torch.cuda.synchronize(self.device)
         return latents
+
+    def op_gemm_tc_bench(self, M: int, K: int, nsplit: int = 3, with_residual: bool = True, dbg: int = 0, iters: int = 10) -> float:
+        ms = ctypes.c_float()
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_op_gemm_tc_bench(self._h, M, K, nsplit, int(with_residual), dbg, iters, ctypes.byref(ms)))
+        return float(ms.value)
 
     def op_self_attention(self, qkv: torch.Tensor, heads: int, head_dim: int) -> torch.Tensor:
         qkv = _check_dev(qkv, self.device, "qkv")

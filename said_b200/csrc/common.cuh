@@ -9,6 +9,12 @@ namespace said {
 #define SAID_DEVINL __device__ __forceinline__
 
 SAID_DEVINL float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// read-only 16-byte load whose L2 miss fetches the surrounding 256-byte segment (long HBM bursts for row-walking readers)
+SAID_DEVINL float4 ldg4_l2pf(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 SAID_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 SAID_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 SAID_DEVINL float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }

@@ -129,19 +129,22 @@ struct said_engine {
         tcmap[key] = TcW{d, K, N, bn};
         return 0;
     }
-    static ALoadLN8 to_tc_loader(const ALoadLN& a) { return ALoadLN8{a.X, a.M, a.T, a.pre_scale, a.pre_shift, a.gamma, a.beta, a.eps}; }
+    // the tcgen05 kernel's loader threads share a row among ROW_CHUNKS lanes
+    static ALoadLNT<tc::ROW_CHUNKS> to_tc_loader(const ALoadLN& a) {
+        return ALoadLNT<tc::ROW_CHUNKS>{a.X, a.M, a.T, a.pre_scale, a.pre_shift, a.gamma, a.beta, a.eps};
+    }
     static const ALoadPlain& to_tc_loader(const ALoadPlain& a) { return a; }
     static const ALoadConv3& to_tc_loader(const ALoadConv3& a) { return a; }
     template <class AL, class EP>
     int gemm_tc_dispatch(cudaStream_t st, int M, int N, int K, const AL& al, const TcW& w, const EP& ep) {
-        const int stride = 2 * w.bn * 32;   // image holds hi + lo tiles
+        const int stride = 2 * w.bn * tc::BK;   // image holds hi + lo tiles
         cudaError_t e = cudaErrorInvalidValue;
         if (w.bn == 192) {
-            e = precision == 1 ? tc::launch_gemm_tc<192, 3>(st, M, N, K, al, w.img, stride, ep)
-                               : tc::launch_gemm_tc<192, 1>(st, M, N, K, al, w.img, stride, ep);
+            e = precision == 1 ? tc::launch_gemm_tc<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
+                               : tc::launch_gemm_tc<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
         } else if (w.bn == 32) {
-            e = precision == 1 ? tc::launch_gemm_tc<32, 3>(st, M, N, K, al, w.img, stride, ep)
-                               : tc::launch_gemm_tc<32, 1>(st, M, N, K, al, w.img, stride, ep);
+            e = precision == 1 ? tc::launch_gemm_tc<32, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
+                               : tc::launch_gemm_tc<32, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
         }
         if (e != cudaSuccess) return fail(std::string("tcgen05 gemm launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
@@ -190,7 +193,7 @@ struct said_engine {
     std::vector<EncLayerW> enc;
 
     // ---- workspaces ----
-    DevBuf act[7], qkv, ao, q2, ffb, eps, ss, ss_st, emb_tab, tvals, step_tab, kv, vnull, lat, init_lat, vnull_tmp;
+    DevBuf act[7], gnbuf, qkv, ao, q2, ffb, eps, ss, ss_st, emb_tab, tvals, step_tab, kv, vnull, lat, init_lat, vnull_tmp;
     DevBuf e_a, e_b, e_c, e_d, e_qkv, e_ff, e_xp, e_emb;
     double* c0_partial = nullptr;
     size_t c0_partial_cap = 0;
@@ -766,6 +769,7 @@ int said_engine::prepare_context(const float* emb, int B, int T, int with_uncond
 int said_engine::ensure_denoiser_ws(int Bp, int T) {
     const size_t M = (size_t)Bp * T;
     for (auto& a : act) CK(a.ensure(M * C));
+    CK(gnbuf.ensure(M * 2 * C));
     CK(qkv.ensure(M * 3 * C));
     CK(ao.ensure(M * C));
     CK(q2.ensure(M * C));
@@ -799,24 +803,31 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         }
         return 0;
     };
-    auto gn = [&](const float* src, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh, int ld, int off) -> int {
+    auto gn = [&](const float* src, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh, int ld, int off,
+                  float* act_out = nullptr, int act_ld = 0, int act_off = 0) -> int {
         cur_tag = TAG_GN;
-        gn_stats_kernel<<<Bp, GN_THREADS, 0, st>>>(src, T, cpg, eps_, g, b, osc, osh, ld, off);
+        gn_stats_kernel<<<Bp, GN_THREADS, 0, st>>>(src, T, cpg, eps_, g, b, osc, osh, ld, off, act_out, act_ld, act_off);
         LAUNCH_CHECK();
         return 0;
     };
+    // Tensor-core path: silu(gn(x)) is materialised once by the statistics kernel (gnbuf) instead of being
+    // recomputed by the conv loader for each of the 3 taps -- the loader's instruction cost, not HBM, is what
+    // bounds the tcgen05 conv GEMMs.
+    const bool mat = precision != 0 && M >= tc_min_rows;
+    float* gnb = gnbuf.p;
     // ResBlock (openaimodel.py:207-227): in (a [, skip]) -> out
     auto resblock = [&](int i, const float* a, const float* skip, float* out) -> int {
         const ResBlockW& W = rb[i];
         const int cin = W.cin;
         if (skip) {
-            CKI(gn(a, 12, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0));
-            CKI(gn(skip, 12, 1e-5f, W.gn1_g + C, W.gn1_b + C, sc, sh, cin, C));
+            CKI(gn(a, 12, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0, mat ? gnb : nullptr, cin, 0));
+            CKI(gn(skip, 12, 1e-5f, W.gn1_g + C, W.gn1_b + C, sc, sh, cin, C, mat ? gnb : nullptr, cin, C));
         } else {
-            CKI(gn(a, 6, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0));
+            CKI(gn(a, 6, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0, mat ? gnb : nullptr, cin, 0));
         }
         {
             ALoadConv3 al{a, skip, C, skip ? C : 0, cin, T, M, Bp, sc, sh, 3 * cin};
+            if (mat) al = ALoadConv3{gnb, nullptr, cin, 0, cin, T, M, Bp, nullptr, nullptr, 3 * cin};
             EpiStd ep = mk_epi(t1, C, C);
             ep.bias = W.b1;
             ep.emb = emb_table + (size_t)i * C;
@@ -825,27 +836,26 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ep.T = T;
             CKI(gemm(st, M, C, 3 * cin, al, W.w1, C, ep));
         }
-        CKI(gn(t1, 6, 1e-5f, W.gn2_g, W.gn2_b, sc, sh, C, 0));
+        CKI(gn(t1, 6, 1e-5f, W.gn2_g, W.gn2_b, sc, sh, C, 0, mat ? gnb : nullptr, C, 0));
+        ALoadConv3 al2c{t1, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
+        if (mat) al2c = ALoadConv3{gnb, nullptr, C, 0, C, T, M, Bp, nullptr, nullptr, 3 * C};
         if (skip) {
-            // second conv over t1 with the 1x1 skip over the raw concat fused as extra contraction rows.
-            // One loader cannot address three tensors, so the skip part runs as a second GEMM that
-            // accumulates through the residual input.
-            ALoadConv3 al{t1, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
+            // second conv over t1, then the 1x1 skip_connection over the raw concat as a second GEMM that
+            // accumulates through the residual input (one loader cannot address three tensors)
             EpiStd ep = mk_epi(x1, C, C);
             ep.bias = W.b2;
-            CKI(gemm(st, M, C, 3 * C, al, W.w2, C, ep));
+            CKI(gemm(st, M, C, 3 * C, al2c, W.w2, C, ep));
             ALoadConv3 al2{a, skip, C, C, cin, T, M, Bp, nullptr, nullptr, 0};   // K3 = 0: raw centre tap only
             EpiStd ep2 = mk_epi(out, C, C);
             ep2.res = x1;
             ep2.ldr = C;
             CKI(gemm(st, M, C, cin, al2, W.w2 + (size_t)3 * C * C, C, ep2));
         } else {
-            ALoadConv3 al{t1, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
             EpiStd ep = mk_epi(out, C, C);
             ep.bias = W.b2;
             ep.res = a;
             ep.ldr = C;
-            CKI(gemm(st, M, C, 3 * C, al, W.w2, C, ep));
+            CKI(gemm(st, M, C, 3 * C, al2c, W.w2, C, ep));
         }
         return 0;
     };
@@ -931,8 +941,9 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
     CKI(resblock(4, Bb, h0, A));           CKI(tap(A));
     CKI(transformer(3, A, Bb));            CKI(tap(Bb));
     {   // out: GN + SiLU + conv3 -> in_ch   (openaimodel.py:665-669)
-        CKI(gn(Bb, 6, 1e-5f, out_gn_g, out_gn_b, sc, sh, C, 0));
+        CKI(gn(Bb, 6, 1e-5f, out_gn_g, out_gn_b, sc, sh, C, 0, mat ? gnb : nullptr, C, 0));
         ALoadConv3 al{Bb, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
+        if (mat) al = ALoadConv3{gnb, nullptr, C, 0, C, T, M, Bp, nullptr, nullptr, 3 * C};
         EpiStd ep = mk_epi(eps_out, in_ch, in_ch);
         ep.bias = b_out;
         CKI(gemm(st, M, in_ch, 3 * C, al, w_out, in_ch, ep));
@@ -1193,6 +1204,42 @@ int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, i
 }
 
 long long said_launch_count(const said_engine* e) { return e ? e->launches : 0; }
+
+int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int with_residual, int dbg, int iters, float* ms_out) {
+    // diagnostics: times the tcgen05 GEMM (N = 192, plain loader) on scratch buffers with parts of it disabled
+    if (!e) return fail("null engine");
+    CK(cudaSetDevice(e->device));
+    const int N = 192;
+    static DevBuf a, w, o, r;
+    CK(a.ensure((size_t)M * K));
+    CK(o.ensure((size_t)M * N));
+    CK(r.ensure((size_t)M * N));
+    CK(w.ensure((size_t)K * N * 2));
+    CK(cudaMemset(a.p, 0, (size_t)M * K * 4));
+    CK(cudaMemset(r.p, 0, (size_t)M * N * 4));
+    CK(cudaMemset(w.p, 0, (size_t)K * N * 2 * 4));
+    EpiStd ep = mk_epi(o.p, N, N);
+    if (with_residual) { ep.res = r.p; ep.ldr = N; }
+    ALoadPlain al = mk_plain(a.p, K, M);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int stride = 2 * N * tc::BK;
+    for (int it = -2; it < iters; ++it) {
+        if (it == 0) CK(cudaEventRecord(e0, 0));
+        cudaError_t le = nsplit == 3 ? tc::launch_gemm_tc<192, 3>(0, e->num_sms, M, N, K, al, w.p, stride, ep, dbg)
+                                     : tc::launch_gemm_tc<192, 1>(0, e->num_sms, M, N, K, al, w.p, stride, ep, dbg);
+        CK(le);
+    }
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
 
 int said_set_precision(said_engine* e, int mode, int tc_min_rows) {
     if (!e) return fail("null engine");

@@ -45,6 +45,13 @@ struct ALoadPlain {
     SAID_DEVINL void set_z(int z) { A += (long long)(z / zdiv) * zstride + (long long)(z % zdiv) * zstride2; }
     SAID_DEVINL Ctx prep(int m, int) const { return Ctx{A + (long long)m * lda, m < M}; }
     SAID_DEVINL float4 load4(const Ctx& c, int k) const { return c.ok ? ldg4(c.p + k) : zero4(); }
+    // asynchronous-copy interface of the tcgen05 kernel: per-row issue context -> raw source address (+ validity),
+    // then the transform applied in shared memory
+    struct ICtx { const float* p; bool ok; };
+    SAID_DEVINL ICtx iprep(int m) const { return ICtx{A + (long long)(m < M ? m : 0) * lda, m < M}; }
+    SAID_DEVINL const float* isrc(const ICtx& c, int k, bool& valid) const { valid = c.ok; return c.p + k; }
+    SAID_DEVINL bool identity() const { return true; }
+    SAID_DEVINL float4 xform(const Ctx&, int, float4 raw) const { return raw; }
 };
 
 // LayerNorm over the full row (row length == K == 192) applied on load, optionally preceded by a
@@ -117,6 +124,23 @@ struct ALoadLNT {
         x.w = (x.w - c.mean) * c.rstd * g.w + bb.w;
         return x;
     }
+    struct ICtx { const float* p; bool ok; };
+    SAID_DEVINL ICtx iprep(int m) const { return ICtx{X + (long long)(m < M ? m : 0) * C, m < M}; }
+    SAID_DEVINL const float* isrc(const ICtx& c, int k, bool& valid) const { valid = c.ok; return c.p + k; }
+    SAID_DEVINL bool identity() const { return false; }
+    SAID_DEVINL float4 xform(const Ctx& c, int k, float4 x) const {
+        if (!c.ok) return zero4();
+        if (c.ps) {
+            const float4 a = ldg4(c.ps + k), d = ldg4(c.pb + k);
+            x.x = x.x * a.x + d.x; x.y = x.y * a.y + d.y; x.z = x.z * a.z + d.z; x.w = x.w * a.w + d.w;
+        }
+        const float4 g = ldg4(gamma + k), bb = ldg4(beta + k);
+        x.x = (x.x - c.mean) * c.rstd * g.x + bb.x;
+        x.y = (x.y - c.mean) * c.rstd * g.y + bb.y;
+        x.z = (x.z - c.mean) * c.rstd * g.z + bb.z;
+        x.w = (x.w - c.mean) * c.rstd * g.w + bb.w;
+        return x;
+    }
 };
 using ALoadLN = ALoadLNT<4>;
 using ALoadLN8 = ALoadLNT<8>;
@@ -164,6 +188,44 @@ struct ALoadConv3 {
             x.x = silu(x.x * a.x + d.x); x.y = silu(x.y * a.y + d.y);
             x.z = silu(x.z * a.z + d.z); x.w = silu(x.w * a.w + d.w);
         }
+        return x;
+    }
+    struct ICtx { const float* p0; const float* p1; int t; bool ok; };
+    SAID_DEVINL ICtx iprep(int m) const {
+        ICtx c;
+        c.ok = m < M;
+        const int mm = c.ok ? m : 0;
+        const int b = mm / T;
+        c.t = mm - b * T;
+        const long long row = (long long)(b % src_batch) * T + c.t;
+        c.p0 = src0 + row * C0;
+        c.p1 = src1 ? src1 + row * C1 : src0;
+        return c;
+    }
+    SAID_DEVINL const float* isrc(const ICtx& c, int k, bool& valid) const {
+        int tap = 1, ch = k - K3;
+        if (k < K3) {
+            tap = (k >= Cin) + (k >= 2 * Cin);
+            ch = k - tap * Cin;
+        }
+        const int tt = c.t + tap - 1;
+        valid = c.ok && tt >= 0 && tt < T;
+        if (!valid) return src0;
+        return (ch < C0) ? c.p0 + (tap - 1) * C0 + ch : c.p1 + (tap - 1) * C1 + (ch - C0);
+    }
+    SAID_DEVINL bool identity() const { return scale == nullptr; }
+    // SiLU with the hardware exp2 / reciprocal approximations (relative error ~2^-21): tensor-core modes only
+    SAID_DEVINL static float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+    SAID_DEVINL float4 xform(const Ctx& c, int k, float4 x) const {
+        if (!c.ok) return zero4();
+        if (k >= K3 || scale == nullptr) return x;       // raw taps and un-normalised inputs pass through (zeros stay zeros)
+        const int tap = (k >= Cin) + (k >= 2 * Cin);
+        const int ch = k - tap * Cin;
+        const int tt = c.t + tap - 1;
+        if (tt < 0 || tt >= T) return zero4();           // zero padding applies after GN + SiLU
+        const float4 a = ldg4(scale + (long long)c.b * Cin + ch), d = ldg4(shift + (long long)c.b * Cin + ch);
+        x.x = silu_fast(x.x * a.x + d.x); x.y = silu_fast(x.y * a.y + d.y);
+        x.z = silu_fast(x.z * a.z + d.z); x.w = silu_fast(x.w * a.w + d.w);
         return x;
     }
 };
@@ -256,7 +318,84 @@ struct EpiStd {
             for (int j = 0; j < TN; ++j) o[j] = v[j];
         }
     }
-    SAID_DEVINL void store16(int m, int n, const float (&acc)[16]) const { store<16>(m, n, acc); }
+    // tcgen05 epilogue interface (gemm_tc.cuh): one float4 = 4 consecutive columns of one row per call, the
+    // residual float4 loaded ahead of time
+    SAID_DEVINL float4 prefetch4(int m, int n) const {
+        return (res != nullptr && n < N) ? ldg4_l2pf(res + (long long)m * ldr + n) : zero4();
+    }
+    SAID_DEVINL void store4(int m, int n, float4 a, float4 r) const {
+        if (n >= N) return;
+        if (bias) {
+            const float4 bq = ldg4(bias + n);
+            a.x += bq.x; a.y += bq.y; a.z += bq.z; a.w += bq.w;
+        }
+        if (act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+        const int b = (emb || res_scale) ? m / T : 0;
+        if (emb) {
+            const float4 q = ldg4(emb + (long long)(step_ptr ? *step_ptr : b) * emb_ld + n);
+            a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+        }
+        if (res) {
+            if (res_scale) {
+                const float4 sc = ldg4(res_scale + (long long)b * res_aff_ld + n);
+                const float4 sh = ldg4(res_shift + (long long)b * res_aff_ld + n);
+                r.x = r.x * sc.x + sh.x; r.y = r.y * sc.y + sh.y; r.z = r.z * sc.z + sh.z; r.w = r.w * sc.w + sh.w;
+            }
+            a.x = r.x + a.x; a.y = r.y + a.y; a.z = r.z + a.z; a.w = r.w + a.w;
+        }
+        st4(out + (long long)m * ldo + n, a);
+    }
+    struct Pref { float4 r[4]; };
+    SAID_DEVINL Pref prefetch16(int m, int n) const {
+        Pref p;
+        if (res != nullptr && n < N) {
+            const float* r = res + (long long)m * ldr + n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p.r[j] = ldg4_l2pf(r + 4 * j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p.r[j] = zero4();
+        }
+        return p;
+    }
+    SAID_DEVINL void store16(int m, int n, const float (&acc)[16], const Pref& p) const {
+        if (n >= N) return;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            float4 bq = zero4();
+            if (bias) bq = ldg4(bias + n + j);
+            v[j] = acc[j] + bq.x; v[j + 1] = acc[j + 1] + bq.y; v[j + 2] = acc[j + 2] + bq.z; v[j + 3] = acc[j + 3] + bq.w;
+        }
+        if (act == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+        }
+        const int b = (emb || res_scale) ? m / T : 0;
+        if (emb) {
+            const float* e = emb + (long long)(step_ptr ? *step_ptr : b) * emb_ld + n;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 q = ldg4(e + j);
+                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+            }
+        }
+        if (res) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                float4 x = p.r[j >> 2];
+                if (res_scale) {
+                    const float4 a = ldg4(res_scale + (long long)b * res_aff_ld + n + j);
+                    const float4 d = ldg4(res_shift + (long long)b * res_aff_ld + n + j);
+                    x.x = x.x * a.x + d.x; x.y = x.y * a.y + d.y; x.z = x.z * a.z + d.z; x.w = x.w * a.w + d.w;
+                }
+                v[j] = x.x + v[j]; v[j + 1] = x.y + v[j + 1]; v[j + 2] = x.z + v[j + 2]; v[j + 3] = x.w + v[j + 3];
+            }
+        }
+        float* o = out + (long long)m * ldo + n;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) st4(o + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+    }
 };
 
 // GEGLU (attention.py:25-32): weight columns are packed interleaved (2j = value_j, 2j+1 = gate_j),
@@ -278,7 +417,18 @@ struct EpiGeglu {
             o[j >> 1] = val * gelu_erf(gate);
         }
     }
-    SAID_DEVINL void store16(int m, int n, const float (&acc)[16]) const {
+    SAID_DEVINL float4 prefetch4(int, int) const { return zero4(); }
+    SAID_DEVINL void store4(int m, int n, float4 a, float4) const {
+        if (n >= N) return;
+        const float4 bq = ldg4(bias + n);
+        float2 o;
+        o.x = (a.x + bq.x) * gelu_erf(a.y + bq.y);
+        o.y = (a.z + bq.z) * gelu_erf(a.w + bq.w);
+        *reinterpret_cast<float2*>(out + (long long)m * ldo + (n >> 1)) = o;
+    }
+    struct Pref {};
+    SAID_DEVINL Pref prefetch16(int, int) const { return Pref{}; }
+    SAID_DEVINL void store16(int m, int n, const float (&acc)[16], const Pref&) const {
         if (n >= N) return;
         float r[8];
 #pragma unroll

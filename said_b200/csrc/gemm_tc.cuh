@@ -30,9 +30,15 @@ namespace said {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                    // fp32 elements per stage row = 128 bytes = one swizzle row
-constexpr int A_TILE_BYTES = BM * 128;
-constexpr int THREADS = 192;              // warps 0-3 loaders + epilogue, warp 4 MMA, warp 5 weight copies
+constexpr int BK = 32;                    // fp32 elements per stage row: 128 bytes = one SWIZZLE_128B row (16 -> SWIZZLE_64B)
+constexpr int ROW_BYTES = BK * 4;
+constexpr int ROW_CHUNKS = ROW_BYTES / 16;            // 16-byte chunks per row (4)
+constexpr int A_TILE_BYTES = BM * ROW_BYTES;
+// byte offset of 16-byte chunk `c` of row `r` inside a K-major swizzled tile whose base is 1024-byte aligned:
+// the swizzle XORs the chunk index with address bits [7, 7 + log2(ROW_CHUNKS))
+SAID_DEVINL uint32_t swz_off(int r, int c) {
+    return (uint32_t)r * ROW_BYTES + (uint32_t)((c ^ ((r * ROW_BYTES) >> 7)) & (ROW_CHUNKS - 1)) * 16u;
+}
 
 SAID_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -56,11 +62,24 @@ SAID_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking poll (try_wait may suspend the thread for a hardware-defined time)
+SAID_DEVINL bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // A wrong barrier protocol must surface as an error, not as a hung GPU: trap after ~seconds of spinning.
 SAID_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 24)) __trap();
+        if (spins > 8) __nanosleep(40);          // long waits (epilogue, idle roles) must not burn issue slots
     }
 }
 SAID_DEVINL void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -106,14 +125,16 @@ SAID_DEVINL void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-SAID_DEVINL uint64_t make_desc_sw128(uint32_t smem_addr) {
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, rows of ROW_BYTES, hardware swizzle
+// matching the row width (SWIZZLE_64B for 64-byte rows, SWIZZLE_128B for 128-byte rows), 8-row groups
+// 8 * ROW_BYTES apart.
+SAID_DEVINL uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                          // descriptor version 1 (sm_100)
-    d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);         // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;           // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                                // descriptor version 1 (sm_100)
+    d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;       // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
     return d;
 }
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): TF32 x TF32 -> F32, both K-major, M x N
@@ -127,148 +148,318 @@ SAID_DEVINL float rna_tf32(float x) {
     return __uint_as_float(r);
 }
 
+SAID_DEVINL void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {   // src_bytes 0 -> zero fill
+    // L2::256B: a miss brings the whole 256-byte segment of the row into L2, so HBM sees long bursts instead of
+    // the 64/128-byte slices a K-chunked tile load would otherwise request
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+SAID_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+SAID_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct TcDims {
     int M, N, K;
     int w_block_floats;   // floats between consecutive (n-tile, k-chunk) blocks of the weight image
+    int dbg;              // diagnostics (said_op_gemm_tc_bench): 1 skip A loads, 2 skip weight copies, 4 skip epilogue I/O, 8 skip MMAs
 };
+
+constexpr int EPI_WARPS = 8;              // warps 0-7: TMEM lane quarter = warp % 4, column half = warp / 4
+constexpr int LOADER_WARPS = 8;
+constexpr int LOADER_THREADS = LOADER_WARPS * 32;
+constexpr int LOADER_TID0 = (EPI_WARPS + 2) * 32;   // warps 0-7 epilogue, 8 MMA, 9 weights, 10.. loaders
+constexpr int THREADS2 = LOADER_TID0 + LOADER_THREADS;   // 576
+constexpr int LROWS = BM * ROW_CHUNKS / LOADER_THREADS;   // 16-byte slots per loader thread per stage (4)
+constexpr int LROW_STEP = LOADER_THREADS / ROW_CHUNKS;    // row distance between a thread's slots (32)
 
 template <int BN, int NSPLIT>
 struct TcCfg {
     static constexpr int NPARTS = NSPLIT == 3 ? 2 : 1;                 // hi (+ lo) copies of each operand
-    static constexpr int B_TILE_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = NPARTS * (A_TILE_BYTES + B_TILE_BYTES);
-    static constexpr int STAGES = (NSPLIT == 3) ? 2 : 4;
-    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    // floats per (n-tile, k-chunk) block of the packed weight image
-    static constexpr int W_BLOCK_FLOATS = NPARTS * B_TILE_BYTES / 4;
+    static constexpr int B_TILE_BYTES = BN * ROW_BYTES;
+    static constexpr int A_STAGE_BYTES = NPARTS * A_TILE_BYTES;
+    static constexpr int B_STAGE_BYTES = NPARTS * B_TILE_BYTES;
+    static constexpr int A_STAGES = NSPLIT == 3 ? 3 : 6;               // activations: cp.async lands directly in the stage
+    static constexpr int B_STAGES = NSPLIT == 3 ? 2 : 4;               // weights: bulk copies
+    static constexpr int ACC_STRIDE = 256;                             // TMEM columns between the two accumulators
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 16 * 4;    // per warp: 32 rows x 16 columns fp32 (transpose staging)
+    static constexpr size_t SMEM_BYTES = (size_t)A_STAGES * A_STAGE_BYTES + (size_t)B_STAGES * B_STAGE_BYTES + EPI_STAGE_BYTES +
+                                         1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int W_BLOCK_FLOATS = NPARTS * B_TILE_BYTES / 4;   // floats copied per (n-tile, k-chunk)
 };
 
+// Persistent, warp-specialised:
+//   warps 0-7   epilogue: drain one of two TMEM accumulators while the next tile's MMAs fill the other
+//   warp  8     MMA issuer (one elected thread)
+//   warp  9     weight-tile copies (one elected thread, cp.async.bulk) into their own ring
+//   warps 10-17 A producers: cp.async 16-byte chunks straight into the swizzled hi tile of a 3-deep ring (two
+//               items in flight across tile boundaries; each thread later touches only the chunks it copied, so
+//               cp.async.wait_group is the only synchronisation), then in place: transform (if any), TF32 lo part
 template <int BN, int NSPLIT, class AL, class EP>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS2, 1)
 gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     using Cfg = TcCfg<BN, NSPLIT>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    const uint32_t acc_bar = bar_base + 8u * (2 * STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
-    auto a_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
-    auto b_hi = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::NPARTS * A_TILE_BYTES; };
+    const uint32_t b_base = smem_base + AS * Cfg::A_STAGE_BYTES;
+    const uint32_t epi_base = b_base + BS * Cfg::B_STAGE_BYTES;
+    const uint32_t bar_base = epi_base + Cfg::EPI_STAGE_BYTES;
+    auto fulla_bar = [&](int s) { return bar_base + 8u * s; };
+    auto emptya_bar = [&](int s) { return bar_base + 8u * (AS + s); };
+    auto fullb_bar = [&](int s) { return bar_base + 8u * (2 * AS + s); };
+    auto emptyb_bar = [&](int s) { return bar_base + 8u * (2 * AS + BS + s); };
+    auto accf_bar = [&](int b) { return bar_base + 8u * (2 * AS + 2 * BS + b); };
+    auto acce_bar = [&](int b) { return bar_base + 8u * (2 * AS + 2 * BS + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * AS + 2 * BS + 4);
+    auto a_hi = [&](int s) { return smem_base + s * Cfg::A_STAGE_BYTES; };
+    auto b_hi = [&](int s) { return b_base + s * Cfg::B_STAGE_BYTES; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * BM;
-    const int nt = blockIdx.y;
     const int nk = d.K / BK;
+    const int n_tiles = (d.N + BN - 1) / BN;
+    const int total_tiles = ((d.M + BM - 1) / BM) * n_tiles;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (tid == 128) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 128 + 1);   // 128 loader threads + the weight-copy thread (with tx bytes)
-            mbar_init(empty_bar(s), 1);        // one tcgen05.commit
+    if (tid == EPI_WARPS * 32) {
+        for (int s = 0; s < AS; ++s) {
+            mbar_init(fulla_bar(s), LOADER_THREADS);      // every loader thread, after its chunks are final
+            mbar_init(emptya_bar(s), 1);                  // one tcgen05.commit
         }
-        mbar_init(acc_bar, 1);
+        for (int s = 0; s < BS; ++s) {
+            mbar_init(fullb_bar(s), 1);                   // the weight-copy thread's arrive.expect_tx (+ tx bytes)
+            mbar_init(emptyb_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accf_bar(b), 1);                    // tcgen05.commit after the tile's last MMA
+            mbar_init(acce_bar(b), EPI_WARPS * 32);       // every epilogue thread after draining
+        }
         fence_mbar_init();
     }
     __syncwarp();
-    if (warp == 4) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == EPI_WARPS) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp < 4) {
-        // ===================== A producers =====================
-        const int c = tid & 7;                 // 16-byte chunk of the 128-byte row this thread owns
-        const int rbase = tid >> 3;            // rows rbase + 16 i
-        const uint32_t swz = (uint32_t)((c ^ (rbase & 7)) << 4);
-        typename AL::Ctx ctx[8];
+    if (warp < EPI_WARPS) {
+        // ===================== epilogue =====================
+        // 8 warps: warp w drains TMEM lanes [32 (w%4), +32) (= rows of the tile) and the 16-column chunks j with
+        // j % 2 == w / 4.  tcgen05.ld hands each lane one row; a warp-private swizzled smem transpose turns that
+        // into 4 lanes per row (64 contiguous bytes per row, 8 rows per instruction) so residual loads and output
+        // stores are sector-coalesced instead of 32 scattered 16-byte accesses per instruction.  Residual float4s
+        // are loaded EPI_PF chunks ahead (before the accumulator is even complete).
+        constexpr int NCH = BN / 16;
+        constexpr int MYCH = (NCH + 1) / 2;                // chunks per warp (column half)
+        constexpr int EPI_PF = MYCH < 2 ? MYCH : 2;
+        const int q = warp & 3, half = warp >> 2;
+        const int lr = lane >> 2, lq = lane & 3;           // after the transpose: rows lr + 8 i, float4 column lq
+        const uint32_t stg = epi_base + (uint32_t)warp * (32 * 16 * 4);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+            const int buf = i & 1;
+            const int mrow0 = mt * BM + q * 32 + lr;       // + 8 ii
+            float4 pf[EPI_PF][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ctx[i] = al.prep(m0 + rbase + 16 * i, c);
-        for (int kc = 0; kc < nk; ++kc) {
-            const int s = kc % STAGES;
-            const uint32_t u = (uint32_t)(kc / STAGES);
-            float4 x[8];
+            for (int jj = 0; jj < EPI_PF; ++jj) {
+                const int j = 2 * jj + half;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = al.load4(ctx[i], kc * BK + c * 4);
-            mbar_wait(empty_bar(s), (u & 1u) ^ 1u);
-            const uint32_t abase = a_hi(s);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t off = (uint32_t)(rbase + 16 * i) * 128u + swz;
-                float4 h;
-                h.x = rna_tf32(x[i].x); h.y = rna_tf32(x[i].y); h.z = rna_tf32(x[i].z); h.w = rna_tf32(x[i].w);
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(abase + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                if constexpr (NSPLIT == 3) {
-                    float4 l;
-                    l.x = rna_tf32(x[i].x - h.x); l.y = rna_tf32(x[i].y - h.y);
-                    l.z = rna_tf32(x[i].z - h.z); l.w = rna_tf32(x[i].w - h.w);
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(abase + A_TILE_BYTES + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int m = mrow0 + 8 * ii;
+                    pf[jj][ii] = (j < NCH && m < d.M && !(d.dbg & 4)) ? ep.prefetch4(m, nt * BN + j * 16 + lq * 4) : zero4();
                 }
             }
-            fence_proxy_async();
-            mbar_arrive(full_bar(s));
+            mbar_wait(accf_bar(buf), (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::ACC_STRIDE);
+#pragma unroll
+            for (int jj = 0; jj < MYCH; ++jj) {
+                const int j = 2 * jj + half;
+                if (j < NCH) {                             // warp-uniform
+                    float v[16];
+                    tmem_ld16(taddr + j * 16, v);
+                    // lane = row `lane`: write 4 float4 with the float4-column XOR-swizzled by (row >> 1) & 3
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const uint32_t a = stg + (uint32_t)lane * 64u + (uint32_t)((c4 ^ ((lane >> 1) & 3)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v[4 * c4]), "f"(v[4 * c4 + 1]),
+                                     "f"(v[4 * c4 + 2]), "f"(v[4 * c4 + 3]) : "memory");
+                    }
+                    __syncwarp();
+                    const int n = nt * BN + j * 16 + lq * 4;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int r = lr + 8 * ii;
+                        const uint32_t a = stg + (uint32_t)r * 64u + (uint32_t)((lq ^ ((r >> 1) & 3)) << 4);
+                        float4 acc;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "r"(a));
+                        const int m = mrow0 + 8 * ii;
+                        if (m < d.M && !(d.dbg & 4)) ep.store4(m, n, acc, pf[jj % EPI_PF][ii]);
+                    }
+                    __syncwarp();
+                    const int jn = j + 2 * EPI_PF;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int m = mrow0 + 8 * ii;
+                        if (jn < NCH && m < d.M && !(d.dbg & 4)) pf[jj % EPI_PF][ii] = ep.prefetch4(m, nt * BN + jn * 16 + lq * 4);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acce_bar(buf));
         }
-        // ===================== epilogue =====================
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-        const int m = m0 + tid;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-        for (int j = 0; j < BN / 16; ++j) {
-            float v[16];
-            tmem_ld16(taddr + j * 16, v);
-            if (m < d.M) ep.store16(m, nt * BN + j * 16, v);
-        }
-        tc_fence_before();
-    } else if (warp == 4) {
+    } else if (warp == EPI_WARPS) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BM, BN);
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % STAGES;
-                const uint32_t u = (uint32_t)(kc / STAGES);
-                mbar_wait(full_bar(s), u & 1u);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int buf = i & 1;
+                mbar_wait(acce_bar(buf), ((uint32_t)(i >> 1) & 1u) ^ 1u);   // accumulator drained (first use: free)
                 tc_fence_after();
-                const uint64_t da = make_desc_sw128(a_hi(s));
-                const uint64_t db = make_desc_sw128(b_hi(s));
-                const uint64_t dal = make_desc_sw128(a_hi(s) + A_TILE_BYTES);
-                const uint64_t dbl = make_desc_sw128(b_hi(s) + Cfg::B_TILE_BYTES);
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_STRIDE);
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(fulla_bar(sa), pa);
+                    mbar_wait(fullb_bar(sb), pb);
+                    tc_fence_after();
+                    const uint64_t da = make_desc(a_hi(sa));
+                    const uint64_t db = make_desc(b_hi(sb));
+                    const uint64_t dal = make_desc(a_hi(sa) + A_TILE_BYTES);
+                    const uint64_t dbl = make_desc(b_hi(sb) + Cfg::B_TILE_BYTES);
 #pragma unroll
-                for (int k4 = 0; k4 < BK / 8; ++k4) {
-                    const uint64_t adv = (uint64_t)(k4 * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units along K
-                    mma_tf32(tmem_base, da + adv, db + adv, idesc, (kc | k4) != 0 ? 1u : 0u);
-                    if constexpr (NSPLIT == 3) {
-                        mma_tf32(tmem_base, dal + adv, db + adv, idesc, 1u);
-                        mma_tf32(tmem_base, da + adv, dbl + adv, idesc, 1u);
+                    for (int k4 = 0; k4 < ((d.dbg & 8) ? 0 : BK / 8); ++k4) {
+                        const uint64_t adv = (uint64_t)(k4 * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units along K (inside one swizzle row)
+                        mma_tf32(tacc, da + adv, db + adv, idesc, (kc | k4) != 0 ? 1u : 0u);
+                        if constexpr (NSPLIT == 3) {
+                            mma_tf32(tacc, dal + adv, db + adv, idesc, 1u);
+                            mma_tf32(tacc, da + adv, dbl + adv, idesc, 1u);
+                        }
                     }
+                    mma_commit(emptya_bar(sa));   // stages free once these MMAs have read them
+                    mma_commit(emptyb_bar(sb));
+                    if (++sa == AS) { sa = 0; pa ^= 1u; }
+                    if (++sb == BS) { sb = 0; pb ^= 1u; }
                 }
-                mma_commit(empty_bar(s));   // stage free once these MMAs have read it
+                mma_commit(accf_bar(buf));      // accumulator complete
             }
-            mma_commit(acc_bar);            // accumulator complete
+        }
+        __syncwarp();
+    } else if (warp == EPI_WARPS + 1) {
+        // ===================== weight copies =====================
+        if (lane == 0) {
+            constexpr uint32_t bytes = (uint32_t)Cfg::W_BLOCK_FLOATS * 4u;
+            int sb = 0;
+            uint32_t pb = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                const int nt = tile % n_tiles;
+                const float* wsrc = Wp + (size_t)nt * nk * d.w_block_floats;
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(emptyb_bar(sb), pb ^ 1u);
+                    if (d.dbg & 2) {
+                        mbar_arrive(fullb_bar(sb));
+                    } else {
+                        mbar_arrive_expect_tx(fullb_bar(sb), bytes);
+                        bulk_g2s(b_hi(sb), wsrc + (size_t)kc * d.w_block_floats, bytes, fullb_bar(sb));
+                    }
+                    if (++sb == BS) { sb = 0; pb ^= 1u; }
+                }
+            }
         }
         __syncwarp();
     } else {
-        // ===================== weight copies =====================
-        if (lane == 0) {
-            const float* wsrc = Wp + (size_t)nt * nk * d.w_block_floats;
-            constexpr uint32_t bytes = (uint32_t)Cfg::W_BLOCK_FLOATS * 4u;
+        // ===================== A producers =====================
+        const int lt = tid - LOADER_TID0;
+        const int c = lt & (ROW_CHUNKS - 1);   // 16-byte chunk of the row this thread owns
+        const int rb = lt / ROW_CHUNKS;        // rows rb + LROW_STEP * i
+        uint32_t off[LROWS];
+#pragma unroll
+        for (int i = 0; i < LROWS; ++i) off[i] = swz_off(rb + LROW_STEP * i, c);
+        const bool ident = al.identity();
+        // ---- issue pointer (runs AS - 1 items ahead of the transform pointer, across tile boundaries)
+        int ti_i = 0, kc_i = 0, sa_i = 0;
+        uint32_t pa_i = 0;
+        typename AL::ICtx ic[LROWS];
+        // issue(block): cp.async the next item into its stage.  With block == false it gives up (returns false,
+        // commits nothing) when the MMAs that last read the stage have not completed yet, so that the transform of
+        // the current item is never held up behind a busy tensor pipe; the caller then issues after the transform.
+        auto issue = [&](bool block) -> bool {
+            if (ti_i < my_tiles) {
+                if (block) mbar_wait(emptya_bar(sa_i), pa_i ^ 1u);
+                else if (!mbar_test_wait(emptya_bar(sa_i), pa_i ^ 1u)) return false;
+                if (kc_i == 0) {
+                    const int m0 = ((blockIdx.x + ti_i * gridDim.x) / n_tiles) * BM;
+#pragma unroll
+                    for (int i = 0; i < LROWS; ++i) ic[i] = al.iprep(m0 + rb + LROW_STEP * i);
+                }
+                const uint32_t dst = a_hi(sa_i);
+#pragma unroll
+                for (int i = 0; i < LROWS; ++i) {
+                    bool valid;
+                    const float* src = al.isrc(ic[i], kc_i * BK + c * 4, valid);
+                    cp_async16(dst + off[i], src, valid ? 16u : 0u);
+                }
+                if (++kc_i == nk) { kc_i = 0; ++ti_i; }
+                if (++sa_i == AS) { sa_i = 0; pa_i ^= 1u; }
+            }
+            cp_async_commit();                 // (possibly empty) group: keeps the wait_group accounting uniform
+            return true;
+        };
+#pragma unroll
+        for (int j = 0; j < AS - 1; ++j) issue(true);
+        // ---- transform pointer
+        typename AL::Ctx ctx[LROWS];
+        int sa_x = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int m0 = ((blockIdx.x + ti * gridDim.x) / n_tiles) * BM;
             for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % STAGES;
-                const uint32_t u = (uint32_t)(kc / STAGES);
-                mbar_wait(empty_bar(s), (u & 1u) ^ 1u);
-                mbar_arrive_expect_tx(full_bar(s), bytes);
-                bulk_g2s(b_hi(s), wsrc + (size_t)kc * d.w_block_floats, bytes, full_bar(s));
+                const bool early = issue(false);
+                if (early) cp_async_wait<AS - 1>();   // this thread's chunks of the current item have landed
+                else cp_async_wait<AS - 2>();
+                if (kc == 0 && !ident) {
+#pragma unroll
+                    for (int i = 0; i < LROWS; ++i) ctx[i] = al.prep(m0 + rb + LROW_STEP * i, c);
+                }
+                const uint32_t abase = a_hi(sa_x);
+                if (NSPLIT == 3 || !ident) {
+#pragma unroll
+                    for (int i = 0; i < LROWS; ++i) {
+                        float4 x;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(abase + off[i]));
+                        float4 h;
+                        if (!ident) {
+                            x = al.xform(ctx[i], kc * BK + c * 4, x);
+                            h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(abase + off[i]), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                        } else {
+                            // untouched fp32 in the hi tile: the tensor core reads its upper 19 bits (TF32 truncation)
+                            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                        }
+                        if constexpr (NSPLIT == 3) {
+                            float4 l;
+                            l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y);
+                            l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(abase + A_TILE_BYTES + off[i]), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                        }
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(fulla_bar(sa_x));
+                if (++sa_x == AS) sa_x = 0;
+                if (!early) issue(true);
             }
         }
-        __syncwarp();
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == EPI_WARPS) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
@@ -290,19 +481,21 @@ inline float host_rna_tf32(float x) {
 inline void pack_weights_tc(const float* Wt, int K, int N, int ldw, int BN, int nsplit, std::vector<float>& out) {
     const int nparts = nsplit == 3 ? 2 : 1;
     const int ntiles = (N + BN - 1) / BN, nk = K / BK;
-    const size_t block = (size_t)nparts * BN * 32;
+    const size_t tile_floats = (size_t)BN * BK;
+    const size_t block = (size_t)nparts * tile_floats;
     out.assign((size_t)ntiles * nk * block, 0.f);
     for (int nt = 0; nt < ntiles; ++nt)
         for (int kc = 0; kc < nk; ++kc) {
             float* hi = out.data() + ((size_t)nt * nk + kc) * block;
-            float* lo = hi + (size_t)BN * 32;
+            float* lo = hi + tile_floats;
             for (int r = 0; r < BN; ++r) {
                 const int n = nt * BN + r;
                 if (n >= N) continue;
-                for (int kk = 0; kk < 32; ++kk) {
+                for (int kk = 0; kk < BK; ++kk) {
                     const float w = Wt[(size_t)(kc * BK + kk) * ldw + n];
                     const int chunk = kk >> 2;
-                    const size_t idx = (size_t)r * 32 + (size_t)((chunk ^ (r & 7)) << 2) + (kk & 3);
+                    const int sw = (chunk ^ ((r * ROW_BYTES) >> 7)) & (ROW_CHUNKS - 1);
+                    const size_t idx = (size_t)r * BK + (size_t)sw * 4 + (kk & 3);
                     const float h = host_rna_tf32(w);
                     hi[idx] = h;
                     if (nparts == 2) lo[idx] = host_rna_tf32(w - h);
@@ -312,8 +505,8 @@ inline void pack_weights_tc(const float* Wt, int K, int N, int ldw, int BN, int 
 }
 
 template <int BN, int NSPLIT, class AL, class EP>
-inline cudaError_t launch_gemm_tc(cudaStream_t st, int M, int N, int K, const AL& al, const float* Wp, int w_block_floats,
-                                  const EP& ep) {
+inline cudaError_t launch_gemm_tc(cudaStream_t st, int num_sms, int M, int N, int K, const AL& al, const float* Wp,
+                                  int w_block_floats, const EP& ep, int dbg = 0) {
     using Cfg = TcCfg<BN, NSPLIT>;
     static bool configured = false;
     auto kern = gemm_tc_kernel<BN, NSPLIT, AL, EP>;
@@ -322,9 +515,10 @@ inline cudaError_t launch_gemm_tc(cudaStream_t st, int M, int N, int K, const AL
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    TcDims d{M, N, K, w_block_floats};
-    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-    kern<<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(d, al, Wp, ep);
+    TcDims d{M, N, K, w_block_floats, dbg};
+    const int total_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    kern<<<grid, THREADS2, Cfg::SMEM_BYTES, st>>>(d, al, Wp, ep);
     return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ constexpr int GN_THREADS = 768;   // 4 row phases x 192 channels
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const float* __restrict__ x, int T, int cpg, float eps, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
-                int out_ld, int out_off) {
+                int out_ld, int out_off, float* __restrict__ act_out, int act_ld, int act_off) {
     constexpr int C = 192;
     __shared__ double s_sum[4][C];
     __shared__ double s_sq[4][C];
@@ -54,12 +54,19 @@ gn_stats_kernel(const float* __restrict__ x, int T, int cpg, float eps, const fl
         s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * __ldg(gamma + c);
+    const float sh = __ldg(beta + c) - s_mean[g] * sc;
     if (threadIdx.x < C) {
-        const int g = c / cpg;
-        const float sc = s_rstd[g] * __ldg(gamma + c);
-        const float sh = __ldg(beta + c) - s_mean[g] * sc;
         scale[(long long)b * out_ld + out_off + c] = sc;
         shift[(long long)b * out_ld + out_off + c] = sh;
+    }
+    // optional second phase (tensor-core path): materialise silu(gn(x)) once, channel-last with row stride
+    // act_ld at column act_off, so the conv GEMM's operand loader is a plain shifted copy (the sample was just
+    // read, so this pass comes from L2)
+    if (act_out != nullptr) {
+        float* ob = act_out + (long long)b * T * act_ld + act_off + c;
+        for (int t2 = ph; t2 < T; t2 += 4) ob[(long long)t2 * act_ld] = silu(__ldg(xb + (long long)t2 * C + c) * sc + sh);
     }
 }
 

@@ -248,7 +248,7 @@ def test_batched_tensor_core_chain_vs_oracle(gpu_model, state_dict):
     e_or = maxdiff(res["tf32x3"][[0, 39]], ref)
     print("batched tc chain: tf32x3 vs fp32", e_modes, "tf32 vs fp32", e_tf32, "tf32x3 vs oracle", e_or)
     assert e_modes < 5e-4 and e_or < 5e-4
-    assert e_tf32 < 5e-2
+    assert e_tf32 < 1e-1
 
 
 # ------------------------------------------------------------------------------------------------ invariants
