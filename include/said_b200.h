@@ -101,6 +101,9 @@ SAID_API int said_op_ddim_step(said_engine* e, const float* pred_dev, float* lat
 SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, int heads, int head_dim,
                            float* out_dev, void* stream);
 
+/* The tcgen05 (3xTF32) self-attention kernel: head_dim 32, T <= 304 (longer sequences use the FFMA kernel). */
+SAID_API int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int B, int T, int heads, float* out_dev, void* stream);
+
 /* Number of kernels this engine has launched (graph replays counted node by node). */
 SAID_API long long said_launch_count(const said_engine* e);
 

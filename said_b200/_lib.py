@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "said_denoiser_forward",
     "said_op_ddim_step",
     "said_op_self_attention",
+    "said_op_self_attention_tc",
     "said_launch_count",
     "said_op_gemm_tc_bench",
     "said_set_precision",
@@ -102,6 +103,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp]
     lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, vp]
     lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
+    lib.said_op_self_attention_tc.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.said_launch_count.argtypes = [vp]
     lib.said_launch_count.restype = ctypes.c_longlong
     lib.said_set_precision.argtypes = [vp, ci, ci]
@@ -296,6 +298,15 @@ class Engine:
                                                   row.ctypes.data, _ptr(en), self._stream()))
             torch.cuda.synchronize(self.device)
         return latents
+
+    def op_self_attention_tc(self, qkv: torch.Tensor, heads: int) -> torch.Tensor:
+        qkv = _check_dev(qkv, self.device, "qkv")
+        B, T, W = qkv.shape
+        assert W == 3 * heads * 32
+        out = torch.empty((B, T, heads * 32), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_op_self_attention_tc(self._h, qkv.data_ptr(), B, T, heads, out.data_ptr(), self._stream()))
+        return out
 
     def op_gemm_tc_bench(self, M: int, K: int, nsplit: int = 3, with_residual: bool = True, dbg: int = 0, iters: int = 10) -> float:
         ms = ctypes.c_float()

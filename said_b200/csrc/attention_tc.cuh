@@ -1,0 +1,270 @@
+// Self-attention on the 5th-gen tensor cores (tcgen05), head dim 32, up to 304 keys, fp32-level accuracy.
+//
+//   out = softmax(q k^T * scale) v          (CrossAttention.forward with context=None, ldm/attention.py:86-128)
+//
+// One CTA per (head, sample).  The head's K (rows = keys) and V^T (rows = head dims) are staged once in shared
+// memory as TF32 hi/lo pairs in the UMMA K-major SWIZZLE_128B layout (a key's 32 dims, or 32 keys of one dim,
+// are exactly one 128-byte swizzle row).  Then, per tile of 128 queries:
+//   1. Q hi/lo -> smem;  S(128 x Tk) = Q K^T with 3xTF32 (hi*hi + lo*hi + hi*lo) into TMEM (N = 256 + rest)
+//   2. each of 128 threads owns one query row (= TMEM lane): row max over the valid keys, then per chunk of
+//      32 keys p = exp(s*scale - max), row sum, TF32 hi/lo of p -> smem (A operand)
+//   3. O(128 x 32) += P_chunk V_chunk, again 3xTF32, accumulated in TMEM
+//   4. O / rowsum -> global
+// The softmax threads and the single MMA-issuing thread hand work back and forth through two mbarriers
+// (operands ready / MMAs complete); tensor work and softmax of one CTA do not overlap (one CTA per SM fills
+// the shared memory), the chip-level parallelism comes from the 6 x samples CTAs.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace said {
+namespace tc {
+
+static_assert(BK == 32 && ROW_BYTES == 128, "attention tiles assume 128-byte SWIZZLE_128B rows");
+constexpr int ATC_HD = 32;
+constexpr int ATC_MAXKEYS = 304;          // K and V^T hi/lo for the whole head must fit one SM's shared memory
+constexpr int ATC_SM_THREADS = 256;        // warps 0-7: staging / softmax / epilogue, two threads per query row
+constexpr int ATC_THREADS = ATC_SM_THREADS + 32;   // warp 8: MMA issuer
+constexpr int ATC_S_COL = 0;               // TMEM columns [0, Tk): scores
+constexpr int ATC_O_COL = 320;             // TMEM columns [320, 352): output accumulator
+
+inline size_t attention_tc_smem_bytes(int T) {
+    const int Tk = (T + 15) / 16 * 16;
+    const int nch = (T + 31) / 32;
+    return (size_t)2 * Tk * 128            // K hi/lo
+           + (size_t)2 * nch * 32 * 128    // V^T hi/lo, one 32(d) x 32(keys) tile per key chunk
+           + (size_t)2 * 2 * 128 * 128     // two operand buffers (hi/lo): P chunk ping-pong; buffer 1 doubles as the Q tile
+           + 2 * ATC_SM_THREADS * 4        // row max / row sum exchange
+           + 1024 + 64;
+}
+
+SAID_DEVINL float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+SAID_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int T, float scale,
+                         float* __restrict__ out, int ldo) {
+    extern __shared__ uint8_t smem_raw[];
+    const int Tk = (T + 15) / 16 * 16;
+    const int nch = (T + 31) / 32;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t k_hi = base, k_lo = k_hi + (uint32_t)Tk * 128u;
+    const uint32_t kv_end = k_lo + (uint32_t)Tk * 128u;
+    const uint32_t v_hi = (kv_end + 1023u) & ~1023u, v_lo = v_hi + (uint32_t)nch * 4096u;
+    const uint32_t buf0 = v_lo + (uint32_t)nch * 4096u;          // operand buffer b: hi at bufb, lo at bufb + 16 KB
+    const uint32_t buf1 = buf0 + 32768u;                         // buffer 1 also holds the Q tile for the S job
+    const uint32_t xch = buf1 + 32768u;                          // float[2][256]
+    const uint32_t bars = xch + 2u * ATC_SM_THREADS * 4u;
+    const uint32_t bar_s_ready = bars, bar_s_done = bars + 8u;
+    auto bar_p_ready = [&](int b) { return bars + 16u + 8u * b; };
+    auto bar_p_done = [&](int b) { return bars + 32u + 8u * b; };
+    const uint32_t tmem_slot = bars + 48u;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const float* gbase = qkv + (long long)b * T * ld + h * ATC_HD;
+
+    if (tid == ATC_SM_THREADS) {
+        mbar_init(bar_s_ready, ATC_SM_THREADS);
+        mbar_init(bar_s_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_p_ready(i), ATC_SM_THREADS);
+            mbar_init(bar_p_done(i), 1);
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int n_qtiles = (T + 127) / 128;
+
+    if (warp < 8) {
+        // ---------------- stage K (rows = keys) and V^T (rows = dims), TF32 hi/lo ----------------
+        for (int i = tid; i < Tk * 8; i += ATC_SM_THREADS) {
+            const int key = i >> 3, c = i & 7;
+            float4 x = zero4();
+            if (key < T) x = ldg4(gbase + (long long)key * ld + k_off + c * 4);
+            const uint32_t off = (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) << 4);
+            float4 hh, ll;
+            hh.x = rna_tf32(x.x); hh.y = rna_tf32(x.y); hh.z = rna_tf32(x.z); hh.w = rna_tf32(x.w);
+            ll.x = rna_tf32(x.x - hh.x); ll.y = rna_tf32(x.y - hh.y); ll.z = rna_tf32(x.z - hh.z); ll.w = rna_tf32(x.w - hh.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(k_hi + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(k_lo + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
+        }
+        for (int i = tid; i < nch * 32 * 8; i += ATC_SM_THREADS) {
+            const int key = i >> 3, c4 = i & 7;          // 4 dims c4*4 .. +3 of one key
+            float4 x = zero4();
+            if (key < T) x = ldg4(gbase + (long long)key * ld + v_off + c4 * 4);
+            const float xv[4] = {x.x, x.y, x.z, x.w};
+            const int chunk = key >> 5, kk = key & 31;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int dd = c4 * 4 + e;
+                const uint32_t off = (uint32_t)chunk * 4096u + (uint32_t)dd * 128u + (uint32_t)(((kk >> 2) ^ (dd & 7)) << 4) + (uint32_t)(kk & 3) * 4u;
+                const float hh = rna_tf32(xv[e]);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(v_hi + off), "f"(hh) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(v_lo + off), "f"(rna_tf32(xv[e] - hh)) : "memory");
+            }
+        }
+        const int row = tid & 127, half = tid >> 7;       // two threads per query row: column halves of every 32-key chunk
+        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const float sl2 = scale * 1.4426950408889634f;    // softmax in base 2: exp(x) = 2^(x log2 e)
+        uint32_t s_jobs = 0, p_use[2] = {0u, 0u};
+        for (int qt = 0; qt < n_qtiles; ++qt) {
+            // ---------------- Q tile (into operand buffer 1) ----------------
+            for (int i = tid; i < 128 * 8; i += ATC_SM_THREADS) {
+                const int r = i >> 3, c = i & 7;
+                float4 x = zero4();
+                if (qt * 128 + r < T) x = ldg4(gbase + (long long)(qt * 128 + r) * ld + q_off + c * 4);
+                const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+                float4 hh, ll;
+                hh.x = rna_tf32(x.x); hh.y = rna_tf32(x.y); hh.z = rna_tf32(x.z); hh.w = rna_tf32(x.w);
+                ll.x = rna_tf32(x.x - hh.x); ll.y = rna_tf32(x.y - hh.y); ll.z = rna_tf32(x.z - hh.z); ll.w = rna_tf32(x.w - hh.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf1 + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf1 + 16384u + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
+            }
+            fence_proxy_async();
+            mbar_arrive(bar_s_ready);                     // job: S = Q K^T
+            mbar_wait(bar_s_done, s_jobs & 1u);
+            ++s_jobs;
+            tc_fence_after();
+            // ---------------- row max over the valid keys (each thread: every other 16-column group) ----------------
+            float mx = -INFINITY;
+            for (int j0 = half * 16; j0 < Tk; j0 += 32) {
+                float v[16];
+                tmem_ld16(trow + ATC_S_COL + j0, v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (j0 + e < T) mx = fmaxf(mx, v[e]);
+            }
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)tid * 4u), "f"(mx) : "memory");
+            named_bar_sync(1, ATC_SM_THREADS);
+            {
+                float other;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + (uint32_t)(tid ^ 128) * 4u));
+                mx = fmaxf(mx, other);
+            }
+            const float msl2 = mx * sl2;
+            // ---------------- P chunks (ping-pong buffers) and O += P V ----------------
+            float lsum = 0.f;
+            for (int ch = 0; ch < nch; ++ch) {
+                const int pb = ch & 1;
+                float p[16];
+                const int j0 = ch * 32 + half * 16;
+                if (j0 < Tk) {                             // warp-uniform
+                    float v[16];
+                    tmem_ld16(trow + ATC_S_COL + j0, v);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        p[e] = (j0 + e < T) ? ex2_approx(v[e] * sl2 - msl2) : 0.f;
+                        lsum += p[e];
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) p[e] = 0.f;
+                }
+                // the job that last read this buffer (chunk ch - 2, or the S job for buffer 1) must have completed
+                if (ch >= 2) mbar_wait(bar_p_done(pb), (p_use[pb] - 1u) & 1u);
+                const uint32_t pbase = (pb ? buf1 : buf0) + (uint32_t)row * 128u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t off = pbase + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4);
+                    float4 hh, ll;
+                    hh.x = rna_tf32(p[4 * c]); hh.y = rna_tf32(p[4 * c + 1]); hh.z = rna_tf32(p[4 * c + 2]); hh.w = rna_tf32(p[4 * c + 3]);
+                    ll.x = rna_tf32(p[4 * c] - hh.x); ll.y = rna_tf32(p[4 * c + 1] - hh.y);
+                    ll.z = rna_tf32(p[4 * c + 2] - hh.z); ll.w = rna_tf32(p[4 * c + 3] - hh.w);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(off + 16384u), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(bar_p_ready(pb));             // job: O += P_ch V_ch
+                ++p_use[pb];
+            }
+            // ---------------- wait for the last job on each buffer, then O / rowsum -> global ----------------
+            mbar_wait(bar_p_done(0), (p_use[0] - 1u) & 1u);
+            if (nch >= 2) mbar_wait(bar_p_done(1), (p_use[1] - 1u) & 1u);
+            tc_fence_after();
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(ATC_SM_THREADS + tid) * 4u), "f"(lsum) : "memory");
+            named_bar_sync(1, ATC_SM_THREADS);
+            {
+                float other;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + (uint32_t)(ATC_SM_THREADS + (tid ^ 128)) * 4u));
+                lsum += other;
+            }
+            {
+                float v[16];
+                tmem_ld16(trow + ATC_O_COL + half * 16, v);
+                const int q = qt * 128 + row;
+                if (q < T) {
+                    const float inv = 1.0f / lsum;
+                    float* orow = out + ((long long)b * T + q) * ldo + h * ATC_HD + half * 16;
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) st4(orow + e, make_float4(v[e] * inv, v[e + 1] * inv, v[e + 2] * inv, v[e + 3] * inv));
+                }
+            }
+            tc_fence_before();                            // TMEM reads done before the next tile's MMAs overwrite S / O
+        }
+    } else if (lane == 0) {
+        // ---------------- MMA issuer ----------------
+        uint32_t s_jobs = 0, p_cnt[2] = {0u, 0u};
+        const int n1 = Tk > 256 ? 256 : Tk, n2 = Tk - n1;
+        const uint32_t id1 = make_idesc_tf32(128, n1), id2 = make_idesc_tf32(128, n2 > 0 ? n2 : 16), idv = make_idesc_tf32(128, ATC_HD);
+        const uint64_t dqh = make_desc(buf1), dql = make_desc(buf1 + 16384u);
+        const uint64_t dkh = make_desc(k_hi), dkl = make_desc(k_lo);
+        const uint64_t dkh2 = make_desc(k_hi + 256u * 128u), dkl2 = make_desc(k_lo + 256u * 128u);
+        for (int qt = 0; qt < n_qtiles; ++qt) {
+            mbar_wait(bar_s_ready, s_jobs & 1u);
+            ++s_jobs;
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t adv = (uint64_t)(k4 * 2);
+                const uint32_t acc = k4 != 0 ? 1u : 0u;
+                mma_tf32(tmem_base + ATC_S_COL, dqh + adv, dkh + adv, id1, acc);
+                mma_tf32(tmem_base + ATC_S_COL, dql + adv, dkh + adv, id1, 1u);
+                mma_tf32(tmem_base + ATC_S_COL, dqh + adv, dkl + adv, id1, 1u);
+                if (n2 > 0) {
+                    mma_tf32(tmem_base + ATC_S_COL + 256, dqh + adv, dkh2 + adv, id2, acc);
+                    mma_tf32(tmem_base + ATC_S_COL + 256, dql + adv, dkh2 + adv, id2, 1u);
+                    mma_tf32(tmem_base + ATC_S_COL + 256, dqh + adv, dkl2 + adv, id2, 1u);
+                }
+            }
+            mma_commit(bar_s_done);
+            for (int ch = 0; ch < nch; ++ch) {
+                const int pb = ch & 1;
+                mbar_wait(bar_p_ready(pb), p_cnt[pb] & 1u);
+                ++p_cnt[pb];
+                tc_fence_after();
+                const uint32_t pa = pb ? buf1 : buf0;
+                const uint64_t dph = make_desc(pa), dpl = make_desc(pa + 16384u);
+                const uint64_t dvh = make_desc(v_hi + (uint32_t)ch * 4096u), dvl = make_desc(v_lo + (uint32_t)ch * 4096u);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t adv = (uint64_t)(k4 * 2);
+                    mma_tf32(tmem_base + ATC_O_COL, dph + adv, dvh + adv, idv, (ch | k4) != 0 ? 1u : 0u);
+                    mma_tf32(tmem_base + ATC_O_COL, dpl + adv, dvh + adv, idv, 1u);
+                    mma_tf32(tmem_base + ATC_O_COL, dph + adv, dvl + adv, idv, 1u);
+                }
+                mma_commit(bar_p_done(pb));
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tc
+}  // namespace said

@@ -19,6 +19,7 @@
 
 #include "../../include/said_b200.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "diffusion_kernels.cuh"
 #include "encoder_kernels.cuh"
 #include "gemm_simt.cuh"
@@ -196,6 +197,8 @@ struct said_engine {
     DevBuf act[7], gnbuf, qkv, ao, q2, ffb, eps, ss, ss_st, emb_tab, tvals, step_tab, kv, vnull, lat, init_lat, vnull_tmp;
     DevBuf e_a, e_b, e_c, e_d, e_qkv, e_ff, e_xp, e_emb;
     double* c0_partial = nullptr;
+    double* gn_partial = nullptr;
+    size_t gn_partial_cap = 0;
     size_t c0_partial_cap = 0;
     int* step_ctr = nullptr;
     int ctx_B = 0, ctx_T = 0, ctx_uncond = 0;
@@ -207,6 +210,7 @@ struct said_engine {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (float* p : arena) cudaFree(p);
         if (c0_partial) cudaFree(c0_partial);
+        if (gn_partial) cudaFree(gn_partial);
         if (step_ctr) cudaFree(step_ctr);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -778,8 +782,18 @@ int said_engine::ensure_denoiser_ws(int Bp, int T) {
     CK(ss.ensure((size_t)Bp * 2 * C * 2));
     CK(ss_st.ensure((size_t)Bp * C * 2));
     if (!step_ctr) CK(cudaMalloc((void**)&step_ctr, sizeof(int)));
+    if ((size_t)Bp * GN_SPLIT * 2 * C > gn_partial_cap) {
+        if (gn_partial) cudaFree(gn_partial);
+        gn_partial = nullptr;
+        gn_partial_cap = 0;
+        CK(cudaMalloc((void**)&gn_partial, (size_t)Bp * GN_SPLIT * 2 * C * sizeof(double)));
+        gn_partial_cap = (size_t)Bp * GN_SPLIT * 2 * C;
+    }
     CK(cudaFuncSetAttribute(self_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)attention_smem_bytes<32>()));
+    if (T <= tc::ATC_MAXKEYS)
+        CK(cudaFuncSetAttribute(tc::self_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)tc::attention_tc_smem_bytes(T)));
     return 0;
 }
 
@@ -806,7 +820,11 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
     auto gn = [&](const float* src, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh, int ld, int off,
                   float* act_out = nullptr, int act_ld = 0, int act_off = 0) -> int {
         cur_tag = TAG_GN;
-        gn_stats_kernel<<<Bp, GN_THREADS, 0, st>>>(src, T, cpg, eps_, g, b, osc, osh, ld, off, act_out, act_ld, act_off);
+        gn_partial_kernel<<<dim3(GN_SPLIT, Bp), GN_THREADS, 0, st>>>(src, T, gn_partial);
+        LAUNCH_CHECK();
+        cur_tag = TAG_GN;
+        gn_finish_kernel<<<dim3(act_out ? GN_SPLIT : 1, Bp), GN_THREADS, 0, st>>>(src, T, cpg, eps_, gn_partial, g, b, osc, osh, ld, off,
+                                                                                  act_out, act_ld, act_off);
         LAUNCH_CHECK();
         return 0;
     };
@@ -869,8 +887,13 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             CKI(gemm(st, M, 3 * C, C, al, W.wqkv, 3 * C, ep));
         }
         cur_tag = TAG_ATTN;
-        self_attention_kernel<32><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, Bp), ATT_THREADS,
-                                    attention_smem_bytes<32>(), st>>>(qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
+        if (mat && T <= tc::ATC_MAXKEYS) {
+            tc::self_attention_tc_kernel<<<dim3(HEADS, Bp), tc::ATC_THREADS, tc::attention_tc_smem_bytes(T), st>>>(
+                qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
+        } else {
+            self_attention_kernel<32><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, Bp), ATT_THREADS,
+                                        attention_smem_bytes<32>(), st>>>(qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
+        }
         LAUNCH_CHECK();
         {   // x1 = to_out(attn) + GN(h)
             EpiStd ep = mk_epi(x1, C, C);
@@ -1198,6 +1221,20 @@ int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, i
     } else {
         return fail("self_attention: head_dim must be 32 or 64");
     }
+    ++e->launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int B, int T, int heads, float* out_dev, void* stream) {
+    if (!e) return fail("null engine");
+    if (T > tc::ATC_MAXKEYS) return fail("self_attention_tc: at most 304 keys");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Cw = heads * 32;
+    CK(cudaFuncSetAttribute(tc::self_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::attention_tc_smem_bytes(T)));
+    tc::self_attention_tc_kernel<<<dim3(heads, B), tc::ATC_THREADS, tc::attention_tc_smem_bytes(T), st>>>(
+        qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw);
     ++e->launches;
     CK(cudaGetLastError());
     return 0;

@@ -6,31 +6,36 @@ namespace said {
 
 // GroupNorm statistics -> per-(sample, channel) scale/shift so that  gn(x)[c] = x[c]*scale + shift.
 // (GroupNorm32, ldm/util.py:111-122: 32 groups, biased variance over channels-in-group x T, fp32;
-//  attention.py:63-66 Normalize: same with eps 1e-6.)  One CTA per sample; x is (B', T, C) channel-last,
-// C == 192; `cpg` channels per group (6 for a 192-channel tensor, 12 for one half of a 384-channel
-// concat).  Sums are accumulated in fp64 so E[x^2]-mean^2 has no cancellation problem.
-// scale/shift are written at [b * out_ld + out_off + c].
+//  attention.py:63-66 Normalize: same with eps 1e-6.)  x is (B', T, C) channel-last, C == 192; `cpg`
+// channels per group (6 for a 192-channel tensor, 12 for one half of a 384-channel concat).
+// Two launches, GN_SPLIT CTAs per sample each (a sample is only 230 KB, but one CTA per sample leaves the
+// chip latency-bound and, for a single clip, idle):
+//   gn_partial_kernel  per-channel sum / sum-of-squares of a quarter of the frames, fp64 (no cancellation
+//                      problem in E[x^2]-mean^2), deterministic (no atomics)
+//   gn_finish_kernel   reduces the partials, writes scale/shift at [b*out_ld + out_off + c] and, on the
+//                      tensor-core path, materialises silu(gn(x)) for its quarter of the frames so the conv
+//                      GEMM's operand loader is a plain shifted copy (the data was just read: L2 hits)
 constexpr int GN_THREADS = 768;   // 4 row phases x 192 channels
+constexpr int GN_SPLIT = 4;
 __global__ void __launch_bounds__(GN_THREADS)
-gn_stats_kernel(const float* __restrict__ x, int T, int cpg, float eps, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
-                int out_ld, int out_off, float* __restrict__ act_out, int act_ld, int act_off) {
+gn_partial_kernel(const float* __restrict__ x, int T, double* __restrict__ partial /*(B', GN_SPLIT, 2, 192)*/) {
     constexpr int C = 192;
     __shared__ double s_sum[4][C];
     __shared__ double s_sq[4][C];
-    __shared__ float s_mean[32], s_rstd[32];
-    const int b = blockIdx.x;
+    const int sp = blockIdx.x, b = blockIdx.y;
     const int c = threadIdx.x % C, ph = threadIdx.x / C;
+    const int rows = (T + GN_SPLIT - 1) / GN_SPLIT;
+    const int t0 = sp * rows, t1 = min(T, t0 + rows);
     const float* xb = x + (long long)b * T * C;
     double s = 0.0, q = 0.0;
-    int t = ph;
-    for (; t + 12 < T; t += 16) {   // 4 independent loads in flight
+    int t = t0 + ph;
+    for (; t + 12 < t1; t += 16) {   // 4 independent loads in flight
         const float v0 = __ldg(xb + (long long)t * C + c), v1 = __ldg(xb + (long long)(t + 4) * C + c);
         const float v2 = __ldg(xb + (long long)(t + 8) * C + c), v3 = __ldg(xb + (long long)(t + 12) * C + c);
         s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
         q += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
     }
-    for (; t < T; t += 4) {
+    for (; t < t1; t += 4) {
         const float v = __ldg(xb + (long long)t * C + c);
         s += v;
         q += (double)v * v;
@@ -38,13 +43,39 @@ gn_stats_kernel(const float* __restrict__ x, int T, int cpg, float eps, const fl
     s_sum[ph][c] = s;
     s_sq[ph][c] = q;
     __syncthreads();
+    if (threadIdx.x < C) {
+        double* pp = partial + ((long long)b * GN_SPLIT + sp) * 2 * C;
+        pp[c] = (s_sum[0][c] + s_sum[1][c]) + (s_sum[2][c] + s_sum[3][c]);
+        pp[C + c] = (s_sq[0][c] + s_sq[1][c]) + (s_sq[2][c] + s_sq[3][c]);
+    }
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_finish_kernel(const float* __restrict__ x, int T, int cpg, float eps, const double* __restrict__ partial,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale,
+                 float* __restrict__ shift, int out_ld, int out_off, float* __restrict__ act_out, int act_ld, int act_off) {
+    constexpr int C = 192;
+    __shared__ double s_sum[C], s_sq[C];
+    __shared__ float s_mean[32], s_rstd[32];
+    const int sp = blockIdx.x, b = blockIdx.y;
+    const int c = threadIdx.x % C, ph = threadIdx.x / C;
+    if (threadIdx.x < C) {
+        double s = 0.0, q = 0.0;
+        for (int k = 0; k < GN_SPLIT; ++k) {
+            const double* pp = partial + ((long long)b * GN_SPLIT + k) * 2 * C;
+            s += pp[c];
+            q += pp[C + c];
+        }
+        s_sum[c] = s;
+        s_sq[c] = q;
+    }
+    __syncthreads();
     const int ng = C / cpg;
     if ((int)threadIdx.x < ng) {
         double gs = 0.0, gq = 0.0;
         for (int j = 0; j < cpg; ++j) {
-            const int cc = threadIdx.x * cpg + j;
-            gs += (s_sum[0][cc] + s_sum[1][cc]) + (s_sum[2][cc] + s_sum[3][cc]);
-            gq += (s_sq[0][cc] + s_sq[1][cc]) + (s_sq[2][cc] + s_sq[3][cc]);
+            gs += s_sum[threadIdx.x * cpg + j];
+            gq += s_sq[threadIdx.x * cpg + j];
         }
         const double n = (double)cpg * T;
         const double mean = gs / n;
@@ -57,16 +88,16 @@ gn_stats_kernel(const float* __restrict__ x, int T, int cpg, float eps, const fl
     const int g = c / cpg;
     const float sc = s_rstd[g] * __ldg(gamma + c);
     const float sh = __ldg(beta + c) - s_mean[g] * sc;
-    if (threadIdx.x < C) {
+    if (sp == 0 && threadIdx.x < C) {
         scale[(long long)b * out_ld + out_off + c] = sc;
         shift[(long long)b * out_ld + out_off + c] = sh;
     }
-    // optional second phase (tensor-core path): materialise silu(gn(x)) once, channel-last with row stride
-    // act_ld at column act_off, so the conv GEMM's operand loader is a plain shifted copy (the sample was just
-    // read, so this pass comes from L2)
     if (act_out != nullptr) {
+        const int rows = (T + GN_SPLIT - 1) / GN_SPLIT;
+        const int t0 = sp * rows, t1 = min(T, t0 + rows);
+        const float* xb = x + (long long)b * T * C + c;
         float* ob = act_out + (long long)b * T * act_ld + act_off + c;
-        for (int t2 = ph; t2 < T; t2 += 4) ob[(long long)t2 * act_ld] = silu(__ldg(xb + (long long)t2 * C + c) * sc + sh);
+        for (int t2 = t0 + ph; t2 < t1; t2 += 4) ob[(long long)t2 * act_ld] = silu(__ldg(xb + (long long)t2 * C) * sc + sh);
     }
 }
 

@@ -88,6 +88,23 @@ def test_self_attention_vs_torch(gpu_model, heads, hd, T, B):
     assert maxdiff(out, ref) < 3e-6   # fp32 kernel vs fp64 math on O(1) values
 
 
+@pytest.mark.parametrize("T,B", [(300, 2), (60, 3), (128, 1), (257, 1), (304, 1), (17, 2)])
+def test_self_attention_tensor_core_vs_torch(gpu_model, T, B):
+    """tcgen05 attention (3xTF32 QK^T and PV, fp32 softmax) against fp64 math; tolerance 2e-5 (fp32 kernel: 3e-6)."""
+    eng = gpu_model()._engine(torch.device(DEV))
+    heads, hd = 6, 32
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn(B, T, 3 * heads * hd, generator=g).to(DEV)
+    out = eng.op_self_attention_tc(qkv, heads)
+    q, k, v = qkv.double().chunk(3, dim=-1)
+    sh = lambda t: t.reshape(B, T, heads, hd).transpose(1, 2)  # noqa: E731
+    ref = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) * hd**-0.5, dim=-1) @ sh(v)
+    ref = ref.transpose(1, 2).reshape(B, T, heads * hd)
+    err = maxdiff(out, ref)
+    print("tc attention", T, err)
+    assert err < 2e-5
+
+
 # ------------------------------------------------------------------------------------------------ denoiser
 TAP_ORDER = ["input_blocks.0", "input_blocks.1.0", "input_blocks.1.1", "middle_block.0", "middle_block.1",
              "middle_block.2", "output_blocks.0.0", "output_blocks.0.1", "output_blocks.1.0", "output_blocks.1.1"]
@@ -249,6 +266,23 @@ def test_batched_tensor_core_chain_vs_oracle(gpu_model, state_dict):
     print("batched tc chain: tf32x3 vs fp32", e_modes, "tf32 vs fp32", e_tf32, "tf32x3 vs oracle", e_or)
     assert e_modes < 5e-4 and e_or < 5e-4
     assert e_tf32 < 1e-1
+
+
+def test_long_clip_mixed_kernels_vs_oracle(gpu_model, state_dict):
+    """6 s clips (T = 360 > 304 keys): tcgen05 GEMMs with the FFMA attention kernel; one clip checked against the oracle."""
+    from oracle import said_oracle as O
+    from said_b200.synth import synthetic_batch
+
+    m = gpu_model("epsilon")
+    wave = synthetic_batch(4, 6.0)
+    g = torch.Generator().manual_seed(13)
+    noise = torch.randn(4, 360, 32, generator=g)
+    res = run(m, wave, noise, steps=4).result.cpu()
+    with torch.no_grad():
+        ref, _ = O.inference(state_dict, wave[[3]], num_inference_steps=4, guidance_scale=2.0, noise=noise[[3]])
+    e = maxdiff(res[[3]], ref)
+    print("long clip", e)
+    assert e < 5e-4
 
 
 # ------------------------------------------------------------------------------------------------ invariants
