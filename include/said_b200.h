@@ -116,8 +116,11 @@ SAID_API int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int
  *   0  IEEE fp32 FFMA (CUDA cores);
  *   1  tcgen05 tensor cores, 3xTF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulate): fp32-level accuracy [default];
  *   2  tcgen05 tensor cores, single TF32 pass (what the reference gets from cuDNN for its convs on a GPU).
- * GEMMs with fewer than tc_min_rows rows (<= 0: keep the current threshold) stay on the FFMA kernel. */
-SAID_API int said_set_precision(said_engine* e, int mode, int tc_min_rows);
+ * GEMMs with fewer than tc_min_rows rows (<= 0: keep the current threshold) stay on the FFMA kernel, so results
+ * are bit-reproducible across batch sizes only within one regime (mode 0 is reproducible across all sizes).
+ * encoder_mode: the same choice for the Wav2Vec2 encoder's GEMMs (default 0: the encoder runs once per clip, and
+ * its long contractions (K up to 3072) lose about a decimal digit under the tensor cores' truncating accumulation). */
+SAID_API int said_set_precision(said_engine* e, int mode, int tc_min_rows, int encoder_mode);
 
 /* Per-kernel-family timing for bench.py's roofline: between begin and end every launch is followed by a
  * CUDA event on its stream (run said_denoise with use_graph = 0 in between).  said_profile_end

@@ -106,7 +106,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_op_self_attention_tc.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.said_launch_count.argtypes = [vp]
     lib.said_launch_count.restype = ctypes.c_longlong
-    lib.said_set_precision.argtypes = [vp, ci, ci]
+    lib.said_set_precision.argtypes = [vp, ci, ci, ci]
     lib.said_op_gemm_tc_bench.argtypes = [vp, ci, ci, ci, ci, ci, ci, ctypes.POINTER(cf)]
     lib.said_profile_begin.argtypes = [vp]
     lib.said_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ci]
@@ -182,10 +182,10 @@ class Engine:
 
     PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
 
-    def set_precision(self, mode: str, tc_min_rows: int = 0) -> None:
-        if mode not in self.PRECISIONS:
+    def set_precision(self, mode: str, tc_min_rows: int = 0, encoder_mode: str = "fp32") -> None:
+        if mode not in self.PRECISIONS or encoder_mode not in self.PRECISIONS:
             raise ValueError(f"precision must be one of {list(self.PRECISIONS)}")
-        self._call(self.lib.said_set_precision(self._h, self.PRECISIONS[mode], int(tc_min_rows)))
+        self._call(self.lib.said_set_precision(self._h, self.PRECISIONS[mode], int(tc_min_rows), self.PRECISIONS[encoder_mode]))
 
     def profile_begin(self) -> None:
         self._call(self.lib.said_profile_begin(self._h))

@@ -49,11 +49,11 @@ conv0_stats_kernel(const float* __restrict__ wave, int T_a, int L0, const float*
     pp[C0_CH + c] = q;
 }
 
-// grid (ceil(L0 / C0_TILE), B); out: (B, L0, 512)
+// grid (ceil(L0 / C0_TILE), B); out: (B, out_stride frames, 512), frames [0, L0) of each clip written
 __global__ void __launch_bounds__(C0_CH)
 conv0_apply_kernel(const float* __restrict__ wave, int T_a, int L0, const float* __restrict__ w,
                    const double* __restrict__ partial, int nchunk, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float eps, float* __restrict__ out) {
+                   const float* __restrict__ beta, float eps, float* __restrict__ out, int out_stride) {
     __shared__ float xs[C0_TILE * C0_S + C0_K];
     const int c = threadIdx.x, b = blockIdx.y;
     const int f0 = blockIdx.x * C0_TILE;
@@ -76,7 +76,7 @@ conv0_apply_kernel(const float* __restrict__ wave, int T_a, int L0, const float*
 #pragma unroll
     for (int k = 0; k < C0_K; ++k) wk[k] = __ldg(w + k * C0_CH + c);
     __syncthreads();
-    float* o = out + ((long long)b * L0 + f0) * C0_CH + c;
+    float* o = out + ((long long)b * out_stride + f0) * C0_CH + c;
     for (int f = 0; f < nf; ++f) {
         float y = 0.f;
 #pragma unroll

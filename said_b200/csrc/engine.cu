@@ -11,10 +11,12 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/said_b200.h"
@@ -121,7 +123,7 @@ struct said_engine {
     std::map<const float*, TcW> tcmap;   // keyed by the SIMT "Wt" device pointer of the same weight
     int precision = 1;                   // 0: fp32 FFMA, 1: 3xTF32 tcgen05 (fp32-level), 2: 1xTF32 tcgen05
     int register_tc(const float* key, const float* host_wt, int K, int N, int ldw) {
-        const int bn = (N % 192 == 0) ? 192 : (N == 32 ? 32 : 0);
+        const int bn = (N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : (N == 32 ? 32 : 0));
         if (bn == 0 || K % tc::BK != 0) return 0;
         std::vector<float> img;
         tc::pack_weights_tc(host_wt, K, N, ldw, bn, 3, img);
@@ -140,7 +142,19 @@ struct said_engine {
     int gemm_tc_dispatch(cudaStream_t st, int M, int N, int K, const AL& al, const TcW& w, const EP& ep) {
         const int stride = 2 * w.bn * tc::BK;   // image holds hi + lo tiles
         cudaError_t e = cudaErrorInvalidValue;
-        if (w.bn == 192) {
+        if (a_in_tmem && w.bn != 128) {   // activations through TMEM (TS MMA): experimental, see gemm_tc.cuh
+            if (w.bn == 192) {
+                e = precision == 1 ? tc::launch_gemm_tca<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
+                                   : tc::launch_gemm_tca<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
+            } else if (w.bn == 32) {
+                e = precision == 1 ? tc::launch_gemm_tca<32, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
+                                   : tc::launch_gemm_tca<32, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
+            }
+        } else if (w.bn == 128) {
+            if constexpr (std::is_same<AL, ALoadPlain>::value && std::is_same<EP, EpiStd>::value)   // encoder conv stack (N = 512)
+                e = precision == 1 ? tc::launch_gemm_tc<128, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
+                                   : tc::launch_gemm_tc<128, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
+        } else if (w.bn == 192) {
             e = precision == 1 ? tc::launch_gemm_tc<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
                                : tc::launch_gemm_tc<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
         } else if (w.bn == 32) {
@@ -150,6 +164,8 @@ struct said_engine {
         if (e != cudaSuccess) return fail(std::string("tcgen05 gemm launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
     }
+    int enc_precision = 0;               // audio encoder GEMMs: IEEE fp32 FFMA by default (exact parity with the goldens)
+    int a_in_tmem = 0;                   // 1: activations through TMEM (TS MMA, gemm_tca_kernel) -- measured slower, kept for study
     int tc_min_rows = 2048;              // below this many rows the small-tile FFMA kernel spreads better over the SMs
     template <class AL, class EP>
     int gemm(cudaStream_t st, int M, int N, int K, const AL& al, const float* Wt, int ldw, const EP& ep, int batch = 1,
@@ -465,6 +481,7 @@ int said_engine::commit_encoder() {
         std::vector<float> w((size_t)ks[i] * C0_CH * C0_CH);
         pack_w(*t, C0_CH, C0_CH, ks[i], w, C0_CH, 0, 0);
         CKI(upload(w, &conv_w[i]));
+        CKI(register_tc(conv_w[i], w.data(), ks[i] * C0_CH, C0_CH, C0_CH));
     }
     // ---- feature projection
     const HostTensor* pw = find(P + "feature_projection.projection.weight");
@@ -479,6 +496,7 @@ int said_engine::commit_encoder() {
         std::vector<float> w((size_t)C0_CH * H);
         pack_w(*pw, H, C0_CH, 1, w, H, 0, 0);
         CKI(upload(w, &fp_w));
+        CKI(register_tc(fp_w, w.data(), C0_CH, H, H));
         CKI(upload_raw(P + "feature_projection.projection.bias", {H}, &fp_b));
     }
     // ---- positional conv: fold weight norm (w = v * g / ||v||, norm over (out, in) per tap), regroup
@@ -538,11 +556,13 @@ int said_engine::commit_encoder() {
             std::copy(t->data.begin(), t->data.end(), bqkv.begin() + (size_t)j * H);
         }
         CKI(upload(wqkv, &L.wqkv));
+        CKI(register_tc(L.wqkv, wqkv.data(), H, 3 * H, 3 * H));
         CKI(upload(bqkv, &L.bqkv));
         std::vector<float> w((size_t)H * H);
         CKI(need(p + "attention.out_proj.weight", {H, H}, &t));
         pack_w(*t, H, H, 1, w, H, 0, 0);
         CKI(upload(w, &L.wo));
+        CKI(register_tc(L.wo, w.data(), H, H, H));
         CKI(upload_raw(p + "attention.out_proj.bias", {H}, &L.bo));
         CKI(upload_raw(p + "layer_norm.weight", {H}, &L.ln1_g));
         CKI(upload_raw(p + "layer_norm.bias", {H}, &L.ln1_b));
@@ -550,11 +570,13 @@ int said_engine::commit_encoder() {
         std::vector<float> w1((size_t)H * enc_ffn);
         pack_w(*t, enc_ffn, H, 1, w1, enc_ffn, 0, 0);
         CKI(upload(w1, &L.wff1));
+        CKI(register_tc(L.wff1, w1.data(), H, enc_ffn, enc_ffn));
         CKI(upload_raw(p + "feed_forward.intermediate_dense.bias", {enc_ffn}, &L.bff1));
         CKI(need(p + "feed_forward.output_dense.weight", {H, enc_ffn}, &t));
         std::vector<float> w2((size_t)enc_ffn * H);
         pack_w(*t, H, enc_ffn, 1, w2, H, 0, 0);
         CKI(upload(w2, &L.wff2));
+        CKI(register_tc(L.wff2, w2.data(), enc_ffn, H, H));
         CKI(upload_raw(p + "feed_forward.output_dense.bias", {H}, &L.bff2));
         CKI(upload_raw(p + "final_layer_norm.weight", {H}, &L.ln2_g));
         CKI(upload_raw(p + "final_layer_norm.bias", {H}, &L.ln2_b));
@@ -613,6 +635,11 @@ ALoadPlain mk_plain(const float* A, long long lda, int M) {
 // Audio encoder
 // =====================================================================================================
 int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* emb_out, cudaStream_t st) {
+    struct PrecisionScope {   // the encoder has its own precision knob
+        int& p; int saved;
+        PrecisionScope(int& p_, int v) : p(p_), saved(p_) { p = v; }
+        ~PrecisionScope() { p = saved; }
+    } scope(precision, enc_precision);
     if (!ready) return fail("weights not committed");
     if (B <= 0 || T <= 0) return fail("encode_audio: empty batch");
     int L[8];
@@ -635,26 +662,40 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         CK(cudaMalloc((void**)&c0_partial, need_partial * sizeof(double)));
         c0_partial_cap = need_partial;
     }
-    CK(e_a.ensure((size_t)B * L[0] * CD));
-    CK(e_b.ensure((size_t)B * L[1] * CD));
+    // Per-clip frame strides S[i] with S[i-1] = 2 S[i] (all strides are 2): output frame j of clip b is then row
+    // m = b*S[i] + j of ONE flat overlapping-row matrix over the previous layer (row m starts at frame 2m), so the
+    // whole batch is a single GEMM (no per-clip launches, tcgen05-eligible).  Rows j >= L[i] are padding: they
+    // read only padding / neighbouring frames and are never read by valid rows.
+    int S[8];
+    {
+        int s_last = 1;
+        for (int i = 0; i < n_conv; ++i) {
+            const int sh = n_conv - 1 - i;
+            s_last = std::max(s_last, (L[i] + (1 << sh) - 1) >> sh);
+        }
+        for (int i = 0; i < n_conv; ++i) S[i] = s_last << (n_conv - 1 - i);
+    }
+    for (int i = 1; i < n_conv; ++i)
+        if (conv_s[i] != 2) return fail("audio encoder: conv strides other than (5,2,2,2,2,2,2) are not supported");
+    CK(e_a.ensure((size_t)(B * S[0] + 4) * CD));
+    CK(e_b.ensure((size_t)(B * S[1] + 4) * CD));
     conv0_stats_kernel<<<dim3(nchunk, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, fpc, c0_partial);
     LAUNCH_CHECK();
     conv0_apply_kernel<<<dim3((L[0] + C0_TILE - 1) / C0_TILE, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, c0_partial, nchunk,
-                                                                                   c0_g, c0_b, 1e-5f, e_a.p);
+                                                                                   c0_g, c0_b, 1e-5f, e_a.p, S[0]);
     LAUNCH_CHECK();
-    // ---- conv1..6 (stride 2, GELU): overlapping-row GEMMs, one batch entry per clip
+    // ---- conv1..6 (stride 2, GELU): one flat overlapping-row GEMM per layer
     float* src = e_a.p;
     float* dst = e_b.p;
     for (int i = 1; i < n_conv; ++i) {
-        ALoadPlain al = mk_plain(src, (long long)conv_s[i] * CD, L[i]);
-        al.zstride = (long long)L[i - 1] * CD;
+        const int rows = B * S[i];
+        ALoadPlain al = mk_plain(src, (long long)conv_s[i] * CD, rows);
         EpiStd ep = mk_epi(dst, CD, CD);
         ep.act = 1;
-        ep.zs0 = (long long)L[i] * CD;
-        CKI(gemm(st, L[i], CD, conv_k[i] * CD, al, conv_w[i], CD, ep, B));
+        CKI(gemm(st, rows, CD, conv_k[i] * CD, al, conv_w[i], CD, ep));
         std::swap(src, dst);
     }
-    // src now holds (B, Lf, CD)
+    // src now holds (B, S_last, CD), valid frames [0, Lf) of each clip
     const int M = B * T;
     CK(e_c.ensure((size_t)M * std::max(CD, H)));
     CK(e_d.ensure((size_t)M * H));
@@ -662,7 +703,7 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
     CK(e_ff.ensure((size_t)M * enc_ffn));
     CK(e_xp.ensure((size_t)B * pos_g * (T + pos_k) * (H / pos_g)));
     // ---- interpolate to T frames + LayerNorm(512)  -> e_c (M, CD)
-    interp_layernorm_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(src, B, Lf, T, CD, 1e-5f, fp_ln_g, fp_ln_b, e_c.p);
+    interp_layernorm_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(src, B, Lf, S[n_conv - 1], T, CD, 1e-5f, fp_ln_g, fp_ln_b, e_c.p);
     LAUNCH_CHECK();
     // ---- projection 512 -> H  -> e_d
     {
@@ -1264,8 +1305,13 @@ int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int with_res
     const int stride = 2 * N * tc::BK;
     for (int it = -2; it < iters; ++it) {
         if (it == 0) CK(cudaEventRecord(e0, 0));
-        cudaError_t le = nsplit == 3 ? tc::launch_gemm_tc<192, 3>(0, e->num_sms, M, N, K, al, w.p, stride, ep, dbg)
-                                     : tc::launch_gemm_tc<192, 1>(0, e->num_sms, M, N, K, al, w.p, stride, ep, dbg);
+        cudaError_t le;
+        if (dbg & 256)   // A-in-TMEM variant
+            le = nsplit == 3 ? tc::launch_gemm_tca<192, 3>(0, e->num_sms, M, N, K, al, w.p, stride, ep)
+                             : tc::launch_gemm_tca<192, 1>(0, e->num_sms, M, N, K, al, w.p, stride, ep);
+        else
+            le = nsplit == 3 ? tc::launch_gemm_tc<192, 3>(0, e->num_sms, M, N, K, al, w.p, stride, ep, dbg)
+                             : tc::launch_gemm_tc<192, 1>(0, e->num_sms, M, N, K, al, w.p, stride, ep, dbg);
         CK(le);
     }
     CK(cudaEventRecord(e1, 0));
@@ -1278,11 +1324,14 @@ int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int with_res
     return 0;
 }
 
-int said_set_precision(said_engine* e, int mode, int tc_min_rows) {
+int said_set_precision(said_engine* e, int mode, int tc_min_rows, int encoder_mode) {
     if (!e) return fail("null engine");
     if (mode < 0 || mode > 2) return fail("said_set_precision: mode must be 0 (fp32 FFMA), 1 (3xTF32 tcgen05) or 2 (TF32 tcgen05)");
+    if (encoder_mode < 0 || encoder_mode > 2) return fail("said_set_precision: encoder_mode must be 0, 1 or 2");
     e->precision = mode;
+    e->enc_precision = encoder_mode;
     if (tc_min_rows > 0) e->tc_min_rows = tc_min_rows;
+    e->a_in_tmem = getenv("SAID_TC_TMEM_A") ? 1 : 0;   // study aid: SAID_TC_TMEM_A=1 selects the A-through-TMEM kernel
     return 0;
 }
 

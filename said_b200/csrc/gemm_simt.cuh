@@ -128,6 +128,41 @@ struct ALoadLNT {
     SAID_DEVINL ICtx iprep(int m) const { return ICtx{X + (long long)(m < M ? m : 0) * C, m < M}; }
     SAID_DEVINL const float* isrc(const ICtx& c, int k, bool& valid) const { valid = c.ok; return c.p + k; }
     SAID_DEVINL bool identity() const { return false; }
+    // row statistics by ONE thread (the A-in-TMEM kernel: a thread owns a whole row): two streaming passes,
+    // the second one served by L1
+    SAID_DEVINL Ctx prep_row(int m) const {
+        Ctx c;
+        c.ok = m < M;
+        const int mm = c.ok ? m : 0;
+        c.p = X + (long long)mm * C;
+        const int b = mm / T;
+        c.ps = pre_scale ? pre_scale + (long long)b * C : nullptr;
+        c.pb = pre_scale ? pre_shift + (long long)b * C : nullptr;
+        float s = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < C; k += 4) {
+            float4 x = ldg4(c.p + k);
+            if (c.ps) {
+                const float4 a = ldg4(c.ps + k), d = ldg4(c.pb + k);
+                x.x = x.x * a.x + d.x; x.y = x.y * a.y + d.y; x.z = x.z * a.z + d.z; x.w = x.w * a.w + d.w;
+            }
+            s += (x.x + x.y) + (x.z + x.w);
+        }
+        c.mean = s * (1.0f / C);
+        float q = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < C; k += 4) {
+            float4 x = ldg4(c.p + k);
+            if (c.ps) {
+                const float4 a = ldg4(c.ps + k), d = ldg4(c.pb + k);
+                x.x = x.x * a.x + d.x; x.y = x.y * a.y + d.y; x.z = x.z * a.z + d.z; x.w = x.w * a.w + d.w;
+            }
+            const float e0 = x.x - c.mean, e1 = x.y - c.mean, e2 = x.z - c.mean, e3 = x.w - c.mean;
+            q += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+        }
+        c.rstd = 1.0f / sqrtf(q * (1.0f / C) + eps);
+        return c;
+    }
     SAID_DEVINL float4 xform(const Ctx& c, int k, float4 x) const {
         if (!c.ok) return zero4();
         if (c.ps) {

@@ -465,6 +465,307 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     }
 }
 
+// =====================================================================================================
+// A-operand-in-TMEM variant ("TS" MMA).  With both operands in shared memory the 3xTF32 kernel above is
+// bound by shared-memory bandwidth, not by the tensor pipe: per 32-wide K chunk the three MMAs read 48 KB of A
+// and 72 KB of B, the producers move another 48 KB, the weight copy writes 48 KB -- 216 KB against 128 B/cycle
+// is ~1700 cycles for 1152 cycles of MMA.  Here the activation tile never touches shared memory: each
+// producer thread owns one row of the tile (= one TMEM lane), loads its 32 K-values straight from global into
+// registers (L2::256B so HBM sees long bursts; the 128-byte row segment is one cache line), transforms and
+// splits them, and writes hi and lo with tcgen05.st into a 2-stage A ring in TMEM (columns 384..511, next to
+// the two 192-column accumulators).  tcgen05.mma then takes A from TMEM and only B from shared memory.
+// MEASURED (profiles/r1_gemm_variants.md): correct, but 20-30 % slower than the shared-memory-A kernel at the
+// 96-register budget of a 576-thread CTA (the per-thread 32-value hi/lo staging spills, and row-per-thread global
+// loads cost 8x the L1 wavefronts of the coalesced cp.async path).  Not the default; selected with SAID_TC_TMEM_A=1.
+// =====================================================================================================
+SAID_DEVINL void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+SAID_DEVINL void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+          "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]),
+          "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]),
+          "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        : "memory");
+}
+SAID_DEVINL void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int BN, int NSPLIT>
+struct TcaCfg {
+    static constexpr int NPARTS = NSPLIT == 3 ? 2 : 1;
+    static constexpr int B_TILE_BYTES = BN * ROW_BYTES;
+    static constexpr int B_STAGE_BYTES = NPARTS * B_TILE_BYTES;
+    static constexpr int B_STAGES = NSPLIT == 3 ? 3 : 6;
+    static constexpr int ACC_STRIDE = 192;                             // TMEM columns between the two accumulators
+    static constexpr int A_COL = 384;                                  // TMEM A ring: stage s at A_COL + 64 s: hi [0,32), lo [32,64)
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 16 * 4;
+    static constexpr size_t SMEM_BYTES = (size_t)B_STAGES * B_STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+    static constexpr int W_BLOCK_FLOATS = NPARTS * B_TILE_BYTES / 4;
+};
+
+template <int BN, int NSPLIT, class AL, class EP>
+__global__ void __launch_bounds__(THREADS2, 1)
+gemm_tca_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
+    using Cfg = TcaCfg<BN, NSPLIT>;
+    constexpr int BS = Cfg::B_STAGES;
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 192, "UMMA N (two accumulators + the A ring must fit 512 TMEM columns)");
+    static_assert(BK == 32, "one A stage = 32 K-values = 32 TMEM columns");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t epi_base = smem_base + BS * Cfg::B_STAGE_BYTES;
+    const uint32_t bar_base = epi_base + Cfg::EPI_STAGE_BYTES;
+    auto fulla_bar = [&](int s) { return bar_base + 8u * s; };
+    auto emptya_bar = [&](int s) { return bar_base + 8u * (2 + s); };
+    auto fullb_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+    auto emptyb_bar = [&](int s) { return bar_base + 8u * (4 + BS + s); };
+    auto accf_bar = [&](int b) { return bar_base + 8u * (4 + 2 * BS + b); };
+    auto acce_bar = [&](int b) { return bar_base + 8u * (4 + 2 * BS + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (4 + 2 * BS + 4);
+    auto b_hi = [&](int s) { return smem_base + s * Cfg::B_STAGE_BYTES; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nk = d.K / BK;
+    const int n_tiles = (d.N + BN - 1) / BN;
+    const int total_tiles = ((d.M + BM - 1) / BM) * n_tiles;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == EPI_WARPS * 32) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(fulla_bar(s), 128);                 // the four producer warps (one per TMEM lane quarter) of that stage
+            mbar_init(emptya_bar(s), 1);
+        }
+        for (int s = 0; s < BS; ++s) {
+            mbar_init(fullb_bar(s), 1);
+            mbar_init(emptyb_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accf_bar(b), 1);
+            mbar_init(acce_bar(b), EPI_WARPS * 32);
+        }
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == EPI_WARPS) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp < EPI_WARPS) {
+        // ===================== epilogue =====================
+        // 8 warps: warp w drains TMEM lanes [32 (w%4), +32) (= rows of the tile) and the 16-column chunks j with
+        // j % 2 == w / 4.  tcgen05.ld hands each lane one row; a warp-private swizzled smem transpose turns that
+        // into 4 lanes per row (64 contiguous bytes per row, 8 rows per instruction) so residual loads and output
+        // stores are sector-coalesced instead of 32 scattered 16-byte accesses per instruction.  Residual float4s
+        // are loaded EPI_PF chunks ahead (before the accumulator is even complete).
+        constexpr int NCH = BN / 16;
+        constexpr int MYCH = (NCH + 1) / 2;                // chunks per warp (column half)
+        constexpr int EPI_PF = MYCH < 2 ? MYCH : 2;
+        const int q = warp & 3, half = warp >> 2;
+        const int lr = lane >> 2, lq = lane & 3;           // after the transpose: rows lr + 8 i, float4 column lq
+        const uint32_t stg = epi_base + (uint32_t)warp * (32 * 16 * 4);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+            const int buf = i & 1;
+            const int mrow0 = mt * BM + q * 32 + lr;       // + 8 ii
+            float4 pf[EPI_PF][4];
+#pragma unroll
+            for (int jj = 0; jj < EPI_PF; ++jj) {
+                const int j = 2 * jj + half;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int m = mrow0 + 8 * ii;
+                    pf[jj][ii] = (j < NCH && m < d.M && !(d.dbg & 4)) ? ep.prefetch4(m, nt * BN + j * 16 + lq * 4) : zero4();
+                }
+            }
+            mbar_wait(accf_bar(buf), (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::ACC_STRIDE);
+#pragma unroll
+            for (int jj = 0; jj < MYCH; ++jj) {
+                const int j = 2 * jj + half;
+                if (j < NCH) {                             // warp-uniform
+                    float v[16];
+                    tmem_ld16(taddr + j * 16, v);
+                    // lane = row `lane`: write 4 float4 with the float4-column XOR-swizzled by (row >> 1) & 3
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const uint32_t a = stg + (uint32_t)lane * 64u + (uint32_t)((c4 ^ ((lane >> 1) & 3)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v[4 * c4]), "f"(v[4 * c4 + 1]),
+                                     "f"(v[4 * c4 + 2]), "f"(v[4 * c4 + 3]) : "memory");
+                    }
+                    __syncwarp();
+                    const int n = nt * BN + j * 16 + lq * 4;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int r = lr + 8 * ii;
+                        const uint32_t a = stg + (uint32_t)r * 64u + (uint32_t)((lq ^ ((r >> 1) & 3)) << 4);
+                        float4 acc;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "r"(a));
+                        const int m = mrow0 + 8 * ii;
+                        if (m < d.M && !(d.dbg & 4)) ep.store4(m, n, acc, pf[jj % EPI_PF][ii]);
+                    }
+                    __syncwarp();
+                    const int jn = j + 2 * EPI_PF;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int m = mrow0 + 8 * ii;
+                        if (jn < NCH && m < d.M && !(d.dbg & 4)) pf[jj % EPI_PF][ii] = ep.prefetch4(m, nt * BN + jn * 16 + lq * 4);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acce_bar(buf));
+        }
+    } else if (warp == EPI_WARPS) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BM, BN);
+            int sb = 0, it = 0;
+            uint32_t pb = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int buf = i & 1;
+                mbar_wait(acce_bar(buf), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_STRIDE);
+                for (int kc = 0; kc < nk; ++kc, ++it) {
+                    const int sa = it & 1;
+                    mbar_wait(fulla_bar(sa), (uint32_t)(it >> 1) & 1u);
+                    mbar_wait(fullb_bar(sb), pb);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + (uint32_t)(Cfg::A_COL + sa * 64);
+                    const uint64_t db = make_desc(b_hi(sb));
+                    const uint64_t dbl = make_desc(b_hi(sb) + Cfg::B_TILE_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / 8; ++k4) {
+                        const uint64_t adv = (uint64_t)(k4 * 2);
+                        mma_tf32_ts(tacc, ta + k4 * 8, db + adv, idesc, (kc | k4) != 0 ? 1u : 0u);
+                        if constexpr (NSPLIT == 3) {
+                            mma_tf32_ts(tacc, ta + 32 + k4 * 8, db + adv, idesc, 1u);
+                            mma_tf32_ts(tacc, ta + k4 * 8, dbl + adv, idesc, 1u);
+                        }
+                    }
+                    mma_commit(emptya_bar(sa));
+                    mma_commit(emptyb_bar(sb));
+                    if (++sb == BS) { sb = 0; pb ^= 1u; }
+                }
+                mma_commit(accf_bar(buf));
+            }
+        }
+        __syncwarp();
+    } else if (warp == EPI_WARPS + 1) {
+        // ===================== weight copies =====================
+        if (lane == 0) {
+            constexpr uint32_t bytes = (uint32_t)Cfg::W_BLOCK_FLOATS * 4u;
+            int sb = 0;
+            uint32_t pb = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                const int nt = tile % n_tiles;
+                const float* wsrc = Wp + (size_t)nt * nk * d.w_block_floats;
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(emptyb_bar(sb), pb ^ 1u);
+                    mbar_arrive_expect_tx(fullb_bar(sb), bytes);
+                    bulk_g2s(b_hi(sb), wsrc + (size_t)kc * d.w_block_floats, bytes, fullb_bar(sb));
+                    if (++sb == BS) { sb = 0; pb ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== A producers: one thread = one row of the tile = one TMEM lane =====================
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int pair = (warp - (EPI_WARPS + 2)) >> 2;    // 0: even items (A stage 0), 1: odd items (A stage 1)
+        const int row = q * 32 + lane;
+        const uint32_t tst = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::A_COL + pair * 64);
+        const int total_items = my_tiles * nk;
+        const bool ident = al.identity();
+        typename AL::ICtx ic;
+        typename AL::Ctx cx;
+        int ic_tile = -1, cx_tile = -1;
+        auto load_item = [&](int j, float4 (&x)[8]) {
+            const int ti = j / nk, kc = j - ti * nk;
+            if (ti != ic_tile) {
+                ic = al.iprep(((blockIdx.x + ti * gridDim.x) / n_tiles) * BM + row);
+                ic_tile = ti;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                bool valid;
+                const float* src = al.isrc(ic, kc * BK + c * 4, valid);
+                x[c] = valid ? ldg4_l2pf(src) : zero4();
+            }
+        };
+        float4 x[8];
+        if (pair < total_items) load_item(pair, x);
+        uint32_t use = 0;
+        for (int j = pair; j < total_items; j += 2, ++use) {
+            const int ti = j / nk, kc = j - ti * nk;
+            if (!ident && ti != cx_tile) {
+                const int m = ((blockIdx.x + ti * gridDim.x) / n_tiles) * BM + row;
+                if constexpr (AL::kTag == 1) cx = al.prep_row(m);
+                else cx = al.prep(m, 0);
+                cx_tile = ti;
+            }
+            float hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 v = x[c];
+                if (!ident) v = al.xform(cx, kc * BK + c * 4, v);
+                hi[4 * c] = rna_tf32(v.x); hi[4 * c + 1] = rna_tf32(v.y); hi[4 * c + 2] = rna_tf32(v.z); hi[4 * c + 3] = rna_tf32(v.w);
+                if constexpr (NSPLIT == 3) {
+                    lo[4 * c] = rna_tf32(v.x - hi[4 * c]); lo[4 * c + 1] = rna_tf32(v.y - hi[4 * c + 1]);
+                    lo[4 * c + 2] = rna_tf32(v.z - hi[4 * c + 2]); lo[4 * c + 3] = rna_tf32(v.w - hi[4 * c + 3]);
+                }
+            }
+            if (j + 2 < total_items) load_item(j + 2, x);         // next item's loads fly while we wait for the stage
+            mbar_wait(emptya_bar(pair), (use & 1u) ^ 1u);         // the MMAs that read this A stage have completed
+            tc_fence_after();
+            tmem_st32(tst, hi);
+            if constexpr (NSPLIT == 3) tmem_st32(tst + 32, lo);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(fulla_bar(pair));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int BN, int NSPLIT, class AL, class EP>
+inline cudaError_t launch_gemm_tca(cudaStream_t st, int num_sms, int M, int N, int K, const AL& al, const float* Wp,
+                                   int w_block_floats, const EP& ep) {
+    using Cfg = TcaCfg<BN, NSPLIT>;
+    static bool configured = false;
+    auto kern = gemm_tca_kernel<BN, NSPLIT, AL, EP>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    TcDims d{M, N, K, w_block_floats, 0};
+    const int total_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    kern<<<grid, THREADS2, Cfg::SMEM_BYTES, st>>>(d, al, Wp, ep);
+    return cudaGetLastError();
+}
+
 // Host: pack a K-major x N weight matrix Wt (K rows, ldw floats per row, columns [0, N)) into the
 // per-(n-tile, k-chunk) shared-memory images the kernel copies verbatim:
 //   block(nt, kc) = [hi tile: BN rows x 128 B, swizzled] [lo tile]      (lo only when nsplit == 3)

@@ -153,11 +153,11 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ r, 
 
 // Linear interpolation over frames (align_corners=True; said/model/wav2vec2.py:41-44, ATen
 // upsample_linear1d: src = j * (L-1)/(T-1), lambda1 = src - floor(src)) fused with the feature
-// projection's LayerNorm(512) (TF modeling_wav2vec2.py:429-434).  x: (B, L, C) -> y: (B, T, C).
+// projection's LayerNorm(512) (TF modeling_wav2vec2.py:429-434).  x: (B, Lstride >= L frames, C) -> y: (B, T, C).
 // One warp per output row; T < 0 disables interpolation semantics (never used: T is always given).
 template <int MAXV>
 __global__ void __launch_bounds__(256)
-interp_layernorm_kernel(const float* __restrict__ x, int B, int L, int T, int C, float eps,
+interp_layernorm_kernel(const float* __restrict__ x, int B, int L, int Lstride, int T, int C, float eps,
                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * T) return;
@@ -167,8 +167,8 @@ interp_layernorm_kernel(const float* __restrict__ x, int B, int L, int T, int C,
     const int i0 = (int)src;
     const int i1 = i0 + ((i0 < L - 1) ? 1 : 0);
     const float l1 = src - (float)i0, l0 = 1.0f - l1;
-    const float* x0 = x + ((long long)b * L + i0) * C;
-    const float* x1 = x + ((long long)b * L + i1) * C;
+    const float* x0 = x + ((long long)b * Lstride + i0) * C;
+    const float* x1 = x + ((long long)b * Lstride + i1) * C;
     float4 v[MAXV];
     float s = 0.f;
 #pragma unroll

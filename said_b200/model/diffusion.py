@@ -174,6 +174,7 @@ class SAID(ABC, nn.Module):
         # contraction precision of the denoiser GEMMs: "tf32x3" (tcgen05, 3xTF32 split: fp32-level accuracy),
         # "tf32" (tcgen05, single pass) or "fp32" (FFMA); GEMMs below tc_min_rows rows stay on the FFMA kernel
         self.precision = "tf32x3"
+        self.encoder_precision = "fp32"   # the audio encoder runs once per clip: IEEE fp32 unless asked otherwise
         self.tc_min_rows = 0
 
     # ------------------------------------------------------------------ state dict compatibility
@@ -211,7 +212,7 @@ class SAID(ABC, nn.Module):
             )  # ldm/util.py:75-78, evaluated with the same torch ops as the reference
             eng.load_weights(tensors)
             self._engine_keys[idx] = key
-        eng.set_precision(self.precision, self.tc_min_rows)
+        eng.set_precision(self.precision, self.tc_min_rows, self.encoder_precision)
         return eng
 
     # ------------------------------------------------------------------ reference API

@@ -138,12 +138,12 @@ def test_denoiser_forward_precision_modes(golden_dir, gpu_model, mode, tol):
     gd = load(golden_dir, "denoiser_forward.npz")
     m = gpu_model()
     eng = m._engine(torch.device(DEV))
-    eng.set_precision(mode, 1)
+    eng.set_precision(mode, 1, "fp32")
     try:
         out, taps = eng.denoiser_forward(torch.from_numpy(gd["x"]).to(DEV), torch.from_numpy(gd["t"]),
                                          torch.from_numpy(gd["ctx"]).to(DEV), taps=True)
     finally:
-        eng.set_precision(m.precision, 2048)
+        eng.set_precision(m.precision, 2048, m.encoder_precision)
     errs = {name: maxdiff(taps[i].transpose(1, 2), gd["act_" + name]) for i, name in enumerate(TAP_ORDER) if "act_" + name in gd.files}
     errs["out"] = maxdiff(out, gd["y64"])
     print(mode, errs)
@@ -170,6 +170,46 @@ def test_audio_encoder_golden(golden_dir, gpu_model):
     e32, e64 = maxdiff(emb, gd["emb"]), maxdiff(emb, gd["emb64"])
     print("encoder", e32, e64)
     assert e32 < 5e-5 and e64 < 5e-5
+
+
+def test_audio_encoder_tensor_core_mode(golden_dir, gpu_model):
+    """Opt-in tcgen05 (3xTF32) encoder: 8 x 1 s clips, every GEMM on the tensor cores, against the fp32 mode.
+    The 12-layer stack with contractions up to K = 3072 loses about a digit (measured 3e-4 on O(1) features):
+    tolerance 1e-3, which is why fp32 is the encoder's default."""
+    from said_b200.synth import synthetic_batch
+
+    m = gpu_model()
+    wave = synthetic_batch(8, 1.0).to(DEV)
+    ref = m.get_audio_embedding(wave, 60)
+    m.encoder_precision, m.tc_min_rows = "tf32x3", 1
+    try:
+        got = m.get_audio_embedding(wave, 60)
+    finally:
+        m.encoder_precision, m.tc_min_rows = "fp32", 0
+        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, "fp32")
+    e = maxdiff(got, ref)
+    print("encoder tf32x3 vs fp32", e)
+    assert 0 < e < 1e-3
+
+
+@pytest.mark.parametrize("pt", ["v_prediction"])
+def test_chain_1000_steps_tensor_core_mode(golden_dir, gpu_model, pt):
+    """The 1000-step free-running chain with EVERY denoiser GEMM and attention on the tensor cores (3xTF32),
+    forced on for this single clip: tolerance 1e-3 against the reference (the fp32 kernels: 3e-4)."""
+    from said_b200.synth import normalise_waveform, synthetic_waveform
+
+    gd = load(golden_dir, f"chain_5s_1000steps_{pt}.npz")
+    wave = torch.from_numpy(normalise_waveform(synthetic_waveform(0, 5.0)))[None]
+    m = gpu_model(pt)
+    m.tc_min_rows = 1
+    try:
+        out = run(m, wave, gd["noise"], steps=1000)
+    finally:
+        m.tc_min_rows = 0
+        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, "fp32")
+    e32, e64 = maxdiff(out.result, gd["result"]), maxdiff(out.result, gd["result64"])
+    print("tensor-core chain", pt, e32, e64)
+    assert e32 < 1e-3 and e64 < 1e-3
 
 
 # ------------------------------------------------------------------------------------------------ chains
@@ -289,7 +329,7 @@ def test_long_clip_mixed_kernels_vs_oracle(gpu_model, state_dict):
 def test_invariants(gpu_model):
     from said_b200.synth import synthetic_batch
 
-    m = gpu_model("epsilon")
+    m = gpu_model("epsilon")   # (4 clips x 60 frames: every GEMM is below the tensor-core row threshold, one kernel regime)
     wave = synthetic_batch(4, 1.0)
     g = torch.Generator().manual_seed(3)
     noise = torch.randn(4, 60, 32, generator=g)
