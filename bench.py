@@ -304,11 +304,17 @@ def main():
     loop_ms = sum(v["ms"] for v in prof.values())
     gemm_flops_per_step = 2 * B * fl["gemm"]
     achieved_tflops = (gemm_flops_per_step * prof_steps) / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if args.precision == "tf32x3" and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]
     roofline = {
         "kernel": ("gemm_tc_kernel (tcgen05, " + args.precision + ")" if args.precision != "fp32" else "gemm_simt_kernel (fp32 FFMA)")
                   + ": all loader/epilogue instantiations = every Linear/Conv1d of the UNet",
         "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-        "frac": achieved_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+        "frac": achieved_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
+        "traffic_source": "profiles/r1_ncu_traffic.json (bytes per launch, ncu --set full capture of the same kernels)" if traffic else None,
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
         "flops_per_launch_avg": gemm_flops_per_step * prof_steps / max(1, gemm_launches),
         "avg_launch_ms": gemm_ms / max(1, gemm_launches),
