@@ -87,6 +87,7 @@ struct ResBlockW {
 struct TransformerW {
     float *gn_g, *gn_b, *ln1_g, *ln1_b, *wqkv, *wo1, *bo1, *ln2_g, *ln2_b, *wq2, *wo2, *bo2;
     float *ln3_g, *ln3_b, *wff1, *bff1, *wff2, *bff2, *wproj, *bproj;
+    float *wffp, *bffp;        // ff.net.2 and proj_out folded into one (768 + 192) x 192 GEMM: [ff | x] [W2 Wp ; Wp]
 };
 struct EncLayerW {
     float *wqkv, *bqkv, *wo, *bo, *ln1_g, *ln1_b, *wff1, *bff1, *wff2, *bff2, *ln2_g, *ln2_b;
@@ -210,6 +211,7 @@ struct said_engine {
     std::vector<EncLayerW> enc;
 
     // ---- workspaces ----
+    DevBuf cnull;
     DevBuf act[7], gnbuf, qkv, ao, q2, ffb, eps, ss, ss_st, emb_tab, tvals, step_tab, kv, vnull, lat, init_lat, vnull_tmp;
     DevBuf e_a, e_b, e_c, e_d, e_qkv, e_ff, e_xp, e_emb;
     double* c0_partial = nullptr;
@@ -425,6 +427,28 @@ int said_engine::commit_denoiser() {
         CKI(upload(w, &s.wproj));
         CKI(register_tc(s.wproj, w.data(), C, C, C));
         CKI(upload_raw(p + "proj_out.bias", {C}, &s.bproj));
+        {   // out = (ff W2 + b2 + x) Wp + bp + h  ==  [ff | x] [W2 Wp ; Wp] + (b2 Wp + bp) + h   (products in fp64)
+            std::vector<float> wc((size_t)(FF + C) * C), bc((size_t)C);
+            const std::vector<float>& wp = w;   // (192 k, 192 n) K-major
+            for (int k = 0; k < FF; ++k)
+                for (int n = 0; n < C; ++n) {
+                    double acc = 0.0;
+                    for (int j = 0; j < C; ++j) acc += (double)wff2[(size_t)k * C + j] * (double)wp[(size_t)j * C + n];
+                    wc[(size_t)k * C + n] = (float)acc;
+                }
+            std::copy(wp.begin(), wp.end(), wc.begin() + (size_t)FF * C);
+            const HostTensor *b2t, *bpt;
+            CKI(need(b + "ff.net.2.bias", {C}, &b2t));
+            CKI(need(p + "proj_out.bias", {C}, &bpt));
+            for (int n = 0; n < C; ++n) {
+                double acc = bpt->data[n];
+                for (int j = 0; j < C; ++j) acc += (double)b2t->data[j] * (double)wp[(size_t)j * C + n];
+                bc[n] = (float)acc;
+            }
+            CKI(upload(wc, &s.wffp));
+            CKI(register_tc(s.wffp, wc.data(), FF + C, C, C));
+            CKI(upload(bc, &s.bffp));
+        }
     }
     CKI(upload(wkv, &w_kv));
     CKI(register_tc(w_kv, wkv.data(), ctx_dim, 8 * C, 8 * C));
@@ -624,6 +648,9 @@ ALoadPlain mk_plain(const float* A, long long lda, int M) {
     a.zdiv = 1;
     a.zstride2 = 0;
     a.M = M;
+    a.A2 = nullptr;
+    a.lda2 = 0;
+    a.K0 = 0x7fffffff;
     return a;
 }
 
@@ -791,6 +818,7 @@ int said_engine::prepare_context(const float* emb, int B, int T, int with_uncond
     const int M = B * T, N = 8 * C;
     CK(kv.ensure((size_t)M * N));
     CK(vnull.ensure((size_t)4 * C));
+    CK(cnull.ensure((size_t)4 * C));
     CK(vnull_tmp.ensure((size_t)N));
     {
         EpiStd ep = mk_epi(kv.p, N, N);
@@ -801,6 +829,12 @@ int said_engine::prepare_context(const float* emb, int B, int T, int with_uncond
         CKI(gemm(st, 1, N, ctx_dim, mk_plain(null_emb, ctx_dim, 1), w_kv, N, ep));
         for (int l = 0; l < 4; ++l)
             CK(cudaMemcpyAsync(vnull.p + l * C, vnull_tmp.p + l * 2 * C + C, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        // c_null[l] = to_out(v_null[l]) + bias: what the null-condition branch adds to its residual stream in block l
+        for (int l = 0; l < 4; ++l) {
+            EpiStd ep2 = mk_epi(cnull.p + l * C, C, C);
+            ep2.bias = tr[l].bo2;
+            CKI(gemm(st, 1, C, C, mk_plain(vnull.p + l * C, C, 1), tr[l].wo2, C, ep2));
+        }
     }
     ctx_B = B;
     ctx_T = T;
@@ -955,21 +989,34 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         {
             const long long tot = (long long)M * HEADS;
             cur_tag = TAG_XATTN;
-            cross_attention3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q2.p, kv.p, 8 * C, i * 2 * C, vnull.p + i * C,
+            cross_attention3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q2.p, kv.p, 8 * C, i * 2 * C, cnull.p + i * C, x1, x2,
                                                                                   n_uncond, Bp, T, att_scale, ao.p);
             LAUNCH_CHECK();
         }
-        {   // x2 = to_out(attn2) + x1
-            EpiStd ep = mk_epi(x2, C, C);
+        if (Mc > 0) {   // x2 = to_out(attn2) + x1 on the conditional rows (the kernel above wrote the unconditional ones)
+            const size_t r0 = (size_t)n_uncond * T * C;
+            EpiStd ep = mk_epi(x2 + r0, C, C);
             ep.bias = W.bo2;
-            ep.res = x1;
+            ep.res = x1 + r0;
             ep.ldr = C;
-            CKI(gemm(st, M, C, C, mk_plain(ao.p, C, M), W.wo2, C, ep));
+            CKI(gemm(st, Mc, C, C, mk_plain(ao.p + r0, C, Mc), W.wo2, C, ep));
         }
         {   // GEGLU
             ALoadLN al{x2, M, T, nullptr, nullptr, W.ln3_g, W.ln3_b, 1e-5f};
             EpiGeglu ep{ffb.p, FF, 2 * FF, W.bff1};
             CKI(gemm(st, M, 2 * FF, C, al, W.wff1, 2 * FF, ep));
+        }
+        if (mat) {   // out = proj_out(ff2(ff) + x2) + h as ONE GEMM over [ff | x2] with the folded weights
+            ALoadPlain al = mk_plain(ffb.p, FF, M);
+            al.A2 = x2;
+            al.lda2 = C;
+            al.K0 = FF;
+            EpiStd ep = mk_epi(out, C, C);
+            ep.bias = W.bffp;
+            ep.res = h;
+            ep.ldr = C;
+            CKI(gemm(st, M, C, FF + C, al, W.wffp, C, ep));
+            return 0;
         }
         {   // x3 = ff2 + x2  -> x1
             EpiStd ep = mk_epi(x1, C, C);

@@ -41,15 +41,23 @@ struct ALoadPlain {
     int zdiv;
     long long zstride2;     // floats between A sub-batches (blockIdx.z % zdiv)
     int M;
-    struct Ctx { const float* p; bool ok; };
+    // optional second matrix concatenated along K: columns k >= K0 come from A2[m*lda2 + (k - K0)]  (two chained
+    // Linear layers folded into one GEMM: [ff | x] [W2 Wp ; Wp])
+    const float* A2;
+    long long lda2;
+    int K0;
+    struct Ctx { const float* p; const float* p2; bool ok; };
     SAID_DEVINL void set_z(int z) { A += (long long)(z / zdiv) * zstride + (long long)(z % zdiv) * zstride2; }
-    SAID_DEVINL Ctx prep(int m, int) const { return Ctx{A + (long long)m * lda, m < M}; }
-    SAID_DEVINL float4 load4(const Ctx& c, int k) const { return c.ok ? ldg4(c.p + k) : zero4(); }
+    SAID_DEVINL Ctx prep(int m, int) const { return Ctx{A + (long long)m * lda, A2 ? A2 + (long long)m * lda2 - K0 : nullptr, m < M}; }
+    SAID_DEVINL float4 load4(const Ctx& c, int k) const { return c.ok ? ldg4((k < K0 ? c.p : c.p2) + k) : zero4(); }
     // asynchronous-copy interface of the tcgen05 kernel: per-row issue context -> raw source address (+ validity),
     // then the transform applied in shared memory
-    struct ICtx { const float* p; bool ok; };
-    SAID_DEVINL ICtx iprep(int m) const { return ICtx{A + (long long)(m < M ? m : 0) * lda, m < M}; }
-    SAID_DEVINL const float* isrc(const ICtx& c, int k, bool& valid) const { valid = c.ok; return c.p + k; }
+    struct ICtx { const float* p; const float* p2; bool ok; };
+    SAID_DEVINL ICtx iprep(int m) const {
+        const long long mm = m < M ? m : 0;
+        return ICtx{A + mm * lda, A2 ? A2 + mm * lda2 - K0 : nullptr, m < M};
+    }
+    SAID_DEVINL const float* isrc(const ICtx& c, int k, bool& valid) const { valid = c.ok; return (k < K0 ? c.p : c.p2) + k; }
     SAID_DEVINL bool identity() const { return true; }
     SAID_DEVINL float4 xform(const Ctx&, int, float4 raw) const { return raw; }
 };

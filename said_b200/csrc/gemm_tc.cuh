@@ -219,7 +219,11 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     const int nk = d.K / BK;
     const int n_tiles = (d.N + BN - 1) / BN;
     const int total_tiles = ((d.M + BM - 1) / BM) * n_tiles;
-    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // blocked assignment: CTA c owns a contiguous run of tiles (n fastest), so the n-tiles of one row block are
+    // processed back to back by the same CTA (row statistics computed once, activation rows hot in L1/L2)
+    const int tq = total_tiles / (int)gridDim.x, tr = total_tiles % (int)gridDim.x;
+    const int my_tiles = tq + ((int)blockIdx.x < tr ? 1 : 0);
+    const int tile0 = (int)blockIdx.x * tq + min((int)blockIdx.x, tr);
 
     if (tid == EPI_WARPS * 32) {
         for (int s = 0; s < AS; ++s) {
@@ -258,7 +262,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
         const int lr = lane >> 2, lq = lane & 3;           // after the transpose: rows lr + 8 i, float4 column lq
         const uint32_t stg = epi_base + (uint32_t)warp * (32 * 16 * 4);
         for (int i = 0; i < my_tiles; ++i) {
-            const int tile = blockIdx.x + i * gridDim.x;
+            const int tile = tile0 + i;
             const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
             const int buf = i & 1;
             const int mrow0 = mt * BM + q * 32 + lr;       // + 8 ii
@@ -355,7 +359,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
             int sb = 0;
             uint32_t pb = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                const int tile = blockIdx.x + i * gridDim.x;
+                const int tile = tile0 + i;
                 const int nt = tile % n_tiles;
                 const float* wsrc = Wp + (size_t)nt * nk * d.w_block_floats;
                 for (int kc = 0; kc < nk; ++kc) {
@@ -392,7 +396,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                 if (block) mbar_wait(emptya_bar(sa_i), pa_i ^ 1u);
                 else if (!mbar_test_wait(emptya_bar(sa_i), pa_i ^ 1u)) return false;
                 if (kc_i == 0) {
-                    const int m0 = ((blockIdx.x + ti_i * gridDim.x) / n_tiles) * BM;
+                    const int m0 = ((tile0 + ti_i) / n_tiles) * BM;
 #pragma unroll
                     for (int i = 0; i < LROWS; ++i) ic[i] = al.iprep(m0 + rb + LROW_STEP * i);
                 }
@@ -415,12 +419,13 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
         typename AL::Ctx ctx[LROWS];
         int sa_x = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
-            const int m0 = ((blockIdx.x + ti * gridDim.x) / n_tiles) * BM;
+            const int m0 = ((tile0 + ti) / n_tiles) * BM;
+            const bool new_rows = ti == 0 || (tile0 + ti) / n_tiles != (tile0 + ti - 1) / n_tiles;
             for (int kc = 0; kc < nk; ++kc) {
                 const bool early = issue(false);
                 if (early) cp_async_wait<AS - 1>();   // this thread's chunks of the current item have landed
                 else cp_async_wait<AS - 2>();
-                if (kc == 0 && !ident) {
+                if (kc == 0 && !ident && new_rows) {
 #pragma unroll
                     for (int i = 0; i < LROWS; ++i) ctx[i] = al.prep(m0 + rb + LROW_STEP * i, c);
                 }
