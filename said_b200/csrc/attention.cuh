@@ -183,7 +183,7 @@ self_attention_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_of
 __global__ void __launch_bounds__(256)
 cross_attention3_kernel(const float* __restrict__ q, const float* __restrict__ kv, int kv_ld, int kv_off,
                         const float* __restrict__ c_null, const float* __restrict__ x_res, float* __restrict__ x_out,
-                        int n_uncond, int Bp, int T, float scale, float* __restrict__ out) {
+                        int res_rows, int n_uncond, int Bp, int T, float scale, float* __restrict__ out) {
     constexpr int C = 192, HD = 32, H = 6;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)Bp * T * H) return;
@@ -194,7 +194,7 @@ cross_attention3_kernel(const float* __restrict__ q, const float* __restrict__ k
     if (b < n_uncond) {
         // null-condition branch: attention output is the constant v_null for every query, so the whole
         // "to_out(attn2) + x" step collapses to  x_out = x_res + c_null  with c_null = W_o v_null + b_o
-        const float* xr = x_res + row * C + h * HD;
+        const float* xr = x_res + (row % res_rows) * C + h * HD;   // x_res may hold only the shared (conditional) samples
         float* xo = x_out + row * C + h * HD;
 #pragma unroll
         for (int d = 0; d < HD; d += 4) {

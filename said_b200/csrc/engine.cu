@@ -879,6 +879,13 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
                          const float* emb_table, const int* step_ptr, float* eps_out, float* taps) {
     const int M = Bp * T;
     const int Mc = (Bp - n_uncond) * T;
+    // Under classifier-free guidance both branches are fed the same latents (diffusion.py:421-423) and differ only
+    // from the first cross-attention on, so the input conv, the first ResBlock and the first block's
+    // GroupNorm / self-attention / out-projection are computed ONCE for the Bs = B conditional samples and read by
+    // both branches (sample b of a shared tensor = row block b % Bs).
+    const bool share = n_uncond > 0 && 2 * n_uncond == Bp && taps == nullptr;
+    const int Bs = share ? Bp - n_uncond : Bp;
+    const int Ms = Bs * T;
     float* h0 = act[0].p; float* h1 = act[1].p; float* A = act[2].p; float* Bb = act[3].p;
     float* t1 = act[4].p; float* x1 = act[5].p; float* x2 = act[6].p;
     float* sc = ss.p; float* sh = ss.p + (size_t)Bp * 2 * C;
@@ -892,14 +899,15 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         }
         return 0;
     };
-    auto gn = [&](const float* src, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh, int ld, int off,
-                  float* act_out = nullptr, int act_ld = 0, int act_off = 0) -> int {
+    // GroupNorm of `nb` samples whose data is sample (b % src_nb) of src
+    auto gn = [&](const float* src, int src_nb, int nb, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh,
+                  int ld, int off, float* act_out = nullptr, int act_ld = 0, int act_off = 0) -> int {
         cur_tag = TAG_GN;
-        gn_partial_kernel<<<dim3(GN_SPLIT, Bp), GN_THREADS, 0, st>>>(src, T, gn_partial);
+        gn_partial_kernel<<<dim3(GN_SPLIT, nb), GN_THREADS, 0, st>>>(src, src_nb, T, gn_partial);
         LAUNCH_CHECK();
         cur_tag = TAG_GN;
-        gn_finish_kernel<<<dim3(act_out ? GN_SPLIT : 1, Bp), GN_THREADS, 0, st>>>(src, T, cpg, eps_, gn_partial, g, b, osc, osh, ld, off,
-                                                                                  act_out, act_ld, act_off);
+        gn_finish_kernel<<<dim3(act_out ? GN_SPLIT : 1, nb), GN_THREADS, 0, st>>>(src, src_nb, T, cpg, eps_, gn_partial, g, b, osc, osh,
+                                                                                  ld, off, act_out, act_ld, act_off);
         LAUNCH_CHECK();
         return 0;
     };
@@ -908,65 +916,70 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
     // bounds the tcgen05 conv GEMMs.
     const bool mat = precision != 0 && M >= tc_min_rows;
     float* gnb = gnbuf.p;
-    // ResBlock (openaimodel.py:207-227): in (a [, skip]) -> out
-    auto resblock = [&](int i, const float* a, const float* skip, float* out) -> int {
+    // ResBlock (openaimodel.py:207-227) over nb samples: in (a [, skip]) -> out; a holds a_nb samples, skip skip_nb
+    auto resblock = [&](int i, const float* a, int a_nb, const float* skip, int skip_nb, int nb, float* out) -> int {
         const ResBlockW& W = rb[i];
         const int cin = W.cin;
+        const int m = nb * T;
         if (skip) {
-            CKI(gn(a, 12, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0, mat ? gnb : nullptr, cin, 0));
-            CKI(gn(skip, 12, 1e-5f, W.gn1_g + C, W.gn1_b + C, sc, sh, cin, C, mat ? gnb : nullptr, cin, C));
+            CKI(gn(a, a_nb, nb, 12, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0, mat ? gnb : nullptr, cin, 0));
+            CKI(gn(skip, skip_nb, nb, 12, 1e-5f, W.gn1_g + C, W.gn1_b + C, sc, sh, cin, C, mat ? gnb : nullptr, cin, C));
         } else {
-            CKI(gn(a, 6, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0, mat ? gnb : nullptr, cin, 0));
+            CKI(gn(a, a_nb, nb, 6, 1e-5f, W.gn1_g, W.gn1_b, sc, sh, cin, 0, mat ? gnb : nullptr, cin, 0));
         }
         {
-            ALoadConv3 al{a, skip, C, skip ? C : 0, cin, T, M, Bp, sc, sh, 3 * cin};
-            if (mat) al = ALoadConv3{gnb, nullptr, cin, 0, cin, T, M, Bp, nullptr, nullptr, 3 * cin};
+            ALoadConv3 al{a, skip, C, skip ? C : 0, cin, T, m, a_nb, sc, sh, 3 * cin, skip_nb};
+            if (mat) al = ALoadConv3{gnb, nullptr, cin, 0, cin, T, m, nb, nullptr, nullptr, 3 * cin, 0};
             EpiStd ep = mk_epi(t1, C, C);
             ep.bias = W.b1;
             ep.emb = emb_table + (size_t)i * C;
             ep.emb_ld = 5 * C;
             ep.step_ptr = step_ptr;
             ep.T = T;
-            CKI(gemm(st, M, C, 3 * cin, al, W.w1, C, ep));
+            CKI(gemm(st, m, C, 3 * cin, al, W.w1, C, ep));
         }
-        CKI(gn(t1, 6, 1e-5f, W.gn2_g, W.gn2_b, sc, sh, C, 0, mat ? gnb : nullptr, C, 0));
-        ALoadConv3 al2c{t1, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
-        if (mat) al2c = ALoadConv3{gnb, nullptr, C, 0, C, T, M, Bp, nullptr, nullptr, 3 * C};
+        CKI(gn(t1, nb, nb, 6, 1e-5f, W.gn2_g, W.gn2_b, sc, sh, C, 0, mat ? gnb : nullptr, C, 0));
+        ALoadConv3 al2c{t1, nullptr, C, 0, C, T, m, nb, sc, sh, 3 * C, 0};
+        if (mat) al2c = ALoadConv3{gnb, nullptr, C, 0, C, T, m, nb, nullptr, nullptr, 3 * C, 0};
         if (skip) {
             // second conv over t1, then the 1x1 skip_connection over the raw concat as a second GEMM that
             // accumulates through the residual input (one loader cannot address three tensors)
             EpiStd ep = mk_epi(x1, C, C);
             ep.bias = W.b2;
-            CKI(gemm(st, M, C, 3 * C, al2c, W.w2, C, ep));
-            ALoadConv3 al2{a, skip, C, C, cin, T, M, Bp, nullptr, nullptr, 0};   // K3 = 0: raw centre tap only
+            CKI(gemm(st, m, C, 3 * C, al2c, W.w2, C, ep));
+            ALoadConv3 al2{a, skip, C, C, cin, T, m, a_nb, nullptr, nullptr, 0, skip_nb};   // K3 = 0: raw centre tap only
             EpiStd ep2 = mk_epi(out, C, C);
             ep2.res = x1;
             ep2.ldr = C;
-            CKI(gemm(st, M, C, cin, al2, W.w2 + (size_t)3 * C * C, C, ep2));
+            CKI(gemm(st, m, C, cin, al2, W.w2 + (size_t)3 * C * C, C, ep2));
         } else {
             EpiStd ep = mk_epi(out, C, C);
             ep.bias = W.b2;
             ep.res = a;
             ep.ldr = C;
-            CKI(gemm(st, M, C, 3 * C, al2c, W.w2, C, ep));
+            ep.res_mod = a_nb * T;
+            CKI(gemm(st, m, C, 3 * C, al2c, W.w2, C, ep));
         }
         return 0;
     };
-    // SpatialTransformer + BasicTransformerBlock (attention.py:223-234, 167-193): h -> out
-    auto transformer = [&](int i, const float* h, float* out) -> int {
+    // SpatialTransformer + BasicTransformerBlock (attention.py:223-234, 167-193): h (h_nb samples) -> out (Bp samples).
+    // When h_nb < Bp (shared CFG prefix) everything up to the first cross-attention runs on the h_nb samples.
+    auto transformer = [&](int i, const float* h, int h_nb, float* out) -> int {
         const TransformerW& W = tr[i];
-        CKI(gn(h, 6, 1e-6f, W.gn_g, W.gn_b, sc_st, sh_st, C, 0));
+        const int mh = h_nb * T;
+        const bool shared_front = h_nb < Bp;
+        CKI(gn(h, h_nb, h_nb, 6, 1e-6f, W.gn_g, W.gn_b, sc_st, sh_st, C, 0));
         {   // q,k,v = LN1(GN(h)) W   (no bias)
-            ALoadLN al{h, M, T, sc_st, sh_st, W.ln1_g, W.ln1_b, 1e-5f};
+            ALoadLN al{h, mh, T, sc_st, sh_st, W.ln1_g, W.ln1_b, 1e-5f};
             EpiStd ep = mk_epi(qkv.p, 3 * C, 3 * C);
-            CKI(gemm(st, M, 3 * C, C, al, W.wqkv, 3 * C, ep));
+            CKI(gemm(st, mh, 3 * C, C, al, W.wqkv, 3 * C, ep));
         }
         cur_tag = TAG_ATTN;
         if (mat && T <= tc::ATC_MAXKEYS) {
-            tc::self_attention_tc_kernel<<<dim3(HEADS, Bp), tc::ATC_THREADS, tc::attention_tc_smem_bytes(T), st>>>(
+            tc::self_attention_tc_kernel<<<dim3(HEADS, h_nb), tc::ATC_THREADS, tc::attention_tc_smem_bytes(T), st>>>(
                 qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
         } else {
-            self_attention_kernel<32><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, Bp), ATT_THREADS,
+            self_attention_kernel<32><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, h_nb), ATT_THREADS,
                                         attention_smem_bytes<32>(), st>>>(qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
         }
         LAUNCH_CHECK();
@@ -979,10 +992,12 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ep.res_shift = sh_st;
             ep.res_aff_ld = C;
             ep.T = T;
-            CKI(gemm(st, M, C, C, mk_plain(ao.p, C, M), W.wo1, C, ep));
+            CKI(gemm(st, mh, C, C, mk_plain(ao.p, C, mh), W.wo1, C, ep));
         }
+        // rows of x1 that belong to the conditional samples: all of them when the front is shared
+        const size_t x1c = shared_front ? 0 : (size_t)n_uncond * T * C;
         if (Mc > 0) {   // cross-attention queries, conditional samples only
-            ALoadLN al{x1 + (size_t)n_uncond * T * C, Mc, T, nullptr, nullptr, W.ln2_g, W.ln2_b, 1e-5f};
+            ALoadLN al{x1 + x1c, Mc, T, nullptr, nullptr, W.ln2_g, W.ln2_b, 1e-5f};
             EpiStd ep = mk_epi(q2.p, C, C);
             CKI(gemm(st, Mc, C, C, al, W.wq2, C, ep));
         }
@@ -990,14 +1005,14 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             const long long tot = (long long)M * HEADS;
             cur_tag = TAG_XATTN;
             cross_attention3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q2.p, kv.p, 8 * C, i * 2 * C, cnull.p + i * C, x1, x2,
-                                                                                  n_uncond, Bp, T, att_scale, ao.p);
+                                                                                  mh, n_uncond, Bp, T, att_scale, ao.p);
             LAUNCH_CHECK();
         }
         if (Mc > 0) {   // x2 = to_out(attn2) + x1 on the conditional rows (the kernel above wrote the unconditional ones)
             const size_t r0 = (size_t)n_uncond * T * C;
             EpiStd ep = mk_epi(x2 + r0, C, C);
             ep.bias = W.bo2;
-            ep.res = x1 + r0;
+            ep.res = x1 + x1c;
             ep.ldr = C;
             CKI(gemm(st, Mc, C, C, mk_plain(ao.p + r0, C, Mc), W.wo2, C, ep));
         }
@@ -1015,11 +1030,13 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ep.bias = W.bffp;
             ep.res = h;
             ep.ldr = C;
+            ep.res_mod = mh;
             CKI(gemm(st, M, C, FF + C, al, W.wffp, C, ep));
             return 0;
         }
-        {   // x3 = ff2 + x2  -> x1
-            EpiStd ep = mk_epi(x1, C, C);
+        float* x3 = shared_front ? t1 : x1;   // x1 may hold only the shared rows
+        {   // x3 = ff2 + x2
+            EpiStd ep = mk_epi(x3, C, C);
             ep.bias = W.bff2;
             ep.res = x2;
             ep.ldr = C;
@@ -1030,31 +1047,32 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ep.bias = W.bproj;
             ep.res = h;
             ep.ldr = C;
-            CKI(gemm(st, M, C, C, mk_plain(x1, C, M), W.wproj, C, ep));
+            ep.res_mod = mh;
+            CKI(gemm(st, M, C, C, mk_plain(x3, C, M), W.wproj, C, ep));
         }
         return 0;
     };
 
     {   // input conv (openaimodel.py:473-479)
-        ALoadConv3 al{x, nullptr, in_ch, 0, in_ch, T, M, src_batch, nullptr, nullptr, 3 * in_ch};
+        ALoadConv3 al{x, nullptr, in_ch, 0, in_ch, T, Ms, src_batch, nullptr, nullptr, 3 * in_ch, 0};
         EpiStd ep = mk_epi(h0, C, C);
         ep.bias = b_in;
-        CKI(gemm(st, M, C, 3 * in_ch, al, w_in, C, ep));
+        CKI(gemm(st, Ms, C, 3 * in_ch, al, w_in, C, ep));
     }
     CKI(tap(h0));
-    CKI(resblock(0, h0, nullptr, A));      CKI(tap(A));
-    CKI(transformer(0, A, h1));            CKI(tap(h1));
-    CKI(resblock(1, h1, nullptr, Bb));     CKI(tap(Bb));
-    CKI(transformer(1, Bb, A));            CKI(tap(A));
-    CKI(resblock(2, A, nullptr, Bb));      CKI(tap(Bb));
-    CKI(resblock(3, Bb, h1, A));           CKI(tap(A));
-    CKI(transformer(2, A, Bb));            CKI(tap(Bb));
-    CKI(resblock(4, Bb, h0, A));           CKI(tap(A));
-    CKI(transformer(3, A, Bb));            CKI(tap(Bb));
+    CKI(resblock(0, h0, Bs, nullptr, 0, Bs, A));       CKI(tap(A));
+    CKI(transformer(0, A, Bs, h1));                    CKI(tap(h1));
+    CKI(resblock(1, h1, Bp, nullptr, 0, Bp, Bb));      CKI(tap(Bb));
+    CKI(transformer(1, Bb, Bp, A));                    CKI(tap(A));
+    CKI(resblock(2, A, Bp, nullptr, 0, Bp, Bb));       CKI(tap(Bb));
+    CKI(resblock(3, Bb, Bp, h1, Bp, Bp, A));           CKI(tap(A));
+    CKI(transformer(2, A, Bp, Bb));                    CKI(tap(Bb));
+    CKI(resblock(4, Bb, Bp, h0, Bs, Bp, A));           CKI(tap(A));
+    CKI(transformer(3, A, Bp, Bb));                    CKI(tap(Bb));
     {   // out: GN + SiLU + conv3 -> in_ch   (openaimodel.py:665-669)
-        CKI(gn(Bb, 6, 1e-5f, out_gn_g, out_gn_b, sc, sh, C, 0, mat ? gnb : nullptr, C, 0));
-        ALoadConv3 al{Bb, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C};
-        if (mat) al = ALoadConv3{gnb, nullptr, C, 0, C, T, M, Bp, nullptr, nullptr, 3 * C};
+        CKI(gn(Bb, Bp, Bp, 6, 1e-5f, out_gn_g, out_gn_b, sc, sh, C, 0, mat ? gnb : nullptr, C, 0));
+        ALoadConv3 al{Bb, nullptr, C, 0, C, T, M, Bp, sc, sh, 3 * C, 0};
+        if (mat) al = ALoadConv3{gnb, nullptr, C, 0, C, T, M, Bp, nullptr, nullptr, 3 * C, 0};
         EpiStd ep = mk_epi(eps_out, in_ch, in_ch);
         ep.bias = b_out;
         CKI(gemm(st, M, in_ch, 3 * C, al, w_out, in_ch, ep));

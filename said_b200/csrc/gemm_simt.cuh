@@ -203,7 +203,8 @@ struct ALoadConv3 {
     const float* scale;     // (B', Cin) or null: no norm / activation
     const float* shift;
     int K3;                 // 3*Cin
-    struct Ctx { int b, t; long long row; bool ok; };
+    int src1_batch;         // same for src1 (0: use src_batch) -- the UNet skip tensor of the shared CFG prefix
+    struct Ctx { int b, t; long long row, row1; bool ok; };
     SAID_DEVINL void set_z(int) {}
     SAID_DEVINL Ctx prep(int m, int) const {
         Ctx c;
@@ -212,6 +213,7 @@ struct ALoadConv3 {
         c.b = mm / T;
         c.t = mm - c.b * T;
         c.row = (long long)(c.b % src_batch) * T + c.t;
+        c.row1 = (long long)(c.b % (src1_batch ? src1_batch : src_batch)) * T + c.t;
         return c;
     }
     SAID_DEVINL float4 load4(const Ctx& c, int k) const {
@@ -224,8 +226,7 @@ struct ALoadConv3 {
         }
         const int tt = c.t + tap - 1;
         if (tt < 0 || tt >= T) return zero4();
-        const long long r = c.row + (tap - 1);
-        float4 x = (ch < C0) ? ldg4(src0 + r * C0 + ch) : ldg4(src1 + r * C1 + (ch - C0));
+        float4 x = (ch < C0) ? ldg4(src0 + (c.row + (tap - 1)) * C0 + ch) : ldg4(src1 + (c.row1 + (tap - 1)) * C1 + (ch - C0));
         if (scale != nullptr && !raw) {
             const float4 a = ldg4(scale + (long long)c.b * Cin + ch), d = ldg4(shift + (long long)c.b * Cin + ch);
             x.x = silu(x.x * a.x + d.x); x.y = silu(x.y * a.y + d.y);
@@ -241,8 +242,9 @@ struct ALoadConv3 {
         const int b = mm / T;
         c.t = mm - b * T;
         const long long row = (long long)(b % src_batch) * T + c.t;
+        const long long row1 = (long long)(b % (src1_batch ? src1_batch : src_batch)) * T + c.t;
         c.p0 = src0 + row * C0;
-        c.p1 = src1 ? src1 + row * C1 : src0;
+        c.p1 = src1 ? src1 + row1 * C1 : src0;
         return c;
     }
     SAID_DEVINL const float* isrc(const ICtx& c, int k, bool& valid) const {
@@ -293,6 +295,7 @@ struct EpiStd {
     const float* res_shift;
     int T;                   // frames per sample (for sample index of a row)
     int res_aff_ld;          // row stride (channels) of res_scale / res_shift
+    int res_mod;             // > 0: the residual tensor has only res_mod rows, row m reads row m % res_mod (shared CFG prefix)
     int zdiv;                // batched: out/res += (z / zdiv) * zs0 + (z % zdiv) * zs1, bias += (z % zdiv) * bias_zs
     long long zs0, zs1, bias_zs;
     SAID_DEVINL void set_z(int z) {
@@ -331,7 +334,7 @@ struct EpiStd {
             for (int j = 0; j < TN; ++j) v[j] += __ldg(e + j);
         }
         if (res) {
-            const float* r = res + (long long)m * ldr + n;
+            const float* r = res + (long long)(res_mod > 0 ? m % res_mod : m) * ldr + n;
             if constexpr (TN % 4 == 0) {
 #pragma unroll
                 for (int j = 0; j < TN; j += 4) {
@@ -364,7 +367,7 @@ struct EpiStd {
     // tcgen05 epilogue interface (gemm_tc.cuh): one float4 = 4 consecutive columns of one row per call, the
     // residual float4 loaded ahead of time
     SAID_DEVINL float4 prefetch4(int m, int n) const {
-        return (res != nullptr && n < N) ? ldg4_l2pf(res + (long long)m * ldr + n) : zero4();
+        return (res != nullptr && n < N) ? ldg4_l2pf(res + (long long)(res_mod > 0 ? m % res_mod : m) * ldr + n) : zero4();
     }
     SAID_DEVINL void store4(int m, int n, float4 a, float4 r) const {
         if (n >= N) return;
@@ -392,7 +395,7 @@ struct EpiStd {
     SAID_DEVINL Pref prefetch16(int m, int n) const {
         Pref p;
         if (res != nullptr && n < N) {
-            const float* r = res + (long long)m * ldr + n;
+            const float* r = res + (long long)(res_mod > 0 ? m % res_mod : m) * ldr + n;
 #pragma unroll
             for (int j = 0; j < 4; ++j) p.r[j] = ldg4_l2pf(r + 4 * j);
         } else {

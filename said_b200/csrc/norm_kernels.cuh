@@ -18,7 +18,7 @@ namespace said {
 constexpr int GN_THREADS = 768;   // 4 row phases x 192 channels
 constexpr int GN_SPLIT = 4;
 __global__ void __launch_bounds__(GN_THREADS)
-gn_partial_kernel(const float* __restrict__ x, int T, double* __restrict__ partial /*(B', GN_SPLIT, 2, 192)*/) {
+gn_partial_kernel(const float* __restrict__ x, int src_samples, int T, double* __restrict__ partial /*(B', GN_SPLIT, 2, 192)*/) {
     constexpr int C = 192;
     __shared__ double s_sum[4][C];
     __shared__ double s_sq[4][C];
@@ -26,7 +26,7 @@ gn_partial_kernel(const float* __restrict__ x, int T, double* __restrict__ parti
     const int c = threadIdx.x % C, ph = threadIdx.x / C;
     const int rows = (T + GN_SPLIT - 1) / GN_SPLIT;
     const int t0 = sp * rows, t1 = min(T, t0 + rows);
-    const float* xb = x + (long long)b * T * C;
+    const float* xb = x + (long long)(b % src_samples) * T * C;   // sample b reads source sample b % src_samples (shared CFG prefix)
     double s = 0.0, q = 0.0;
     int t = t0 + ph;
     for (; t + 12 < t1; t += 16) {   // 4 independent loads in flight
@@ -51,7 +51,7 @@ gn_partial_kernel(const float* __restrict__ x, int T, double* __restrict__ parti
 }
 
 __global__ void __launch_bounds__(GN_THREADS)
-gn_finish_kernel(const float* __restrict__ x, int T, int cpg, float eps, const double* __restrict__ partial,
+gn_finish_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, float eps, const double* __restrict__ partial,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale,
                  float* __restrict__ shift, int out_ld, int out_off, float* __restrict__ act_out, int act_ld, int act_off) {
     constexpr int C = 192;
@@ -95,7 +95,7 @@ gn_finish_kernel(const float* __restrict__ x, int T, int cpg, float eps, const d
     if (act_out != nullptr) {
         const int rows = (T + GN_SPLIT - 1) / GN_SPLIT;
         const int t0 = sp * rows, t1 = min(T, t0 + rows);
-        const float* xb = x + (long long)b * T * C + c;
+        const float* xb = x + (long long)(b % src_samples) * T * C + c;
         float* ob = act_out + (long long)b * T * act_ld + act_off + c;
         for (int t2 = t0 + ph; t2 < t1; t2 += 4) ob[(long long)t2 * act_ld] = silu(__ldg(xb + (long long)t2 * C) * sc + sh);
     }
