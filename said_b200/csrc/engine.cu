@@ -857,12 +857,12 @@ int said_engine::ensure_denoiser_ws(int Bp, int T) {
     CK(ss.ensure((size_t)Bp * 2 * C * 2));
     CK(ss_st.ensure((size_t)Bp * C * 2));
     if (!step_ctr) CK(cudaMalloc((void**)&step_ctr, sizeof(int)));
-    if ((size_t)Bp * GN_SPLIT * 2 * C > gn_partial_cap) {
+    if ((size_t)Bp * GN_SPLIT_MAX * 2 * C > gn_partial_cap) {
         if (gn_partial) cudaFree(gn_partial);
         gn_partial = nullptr;
         gn_partial_cap = 0;
-        CK(cudaMalloc((void**)&gn_partial, (size_t)Bp * GN_SPLIT * 2 * C * sizeof(double)));
-        gn_partial_cap = (size_t)Bp * GN_SPLIT * 2 * C;
+        CK(cudaMalloc((void**)&gn_partial, (size_t)Bp * GN_SPLIT_MAX * 2 * C * sizeof(double)));
+        gn_partial_cap = (size_t)Bp * GN_SPLIT_MAX * 2 * C;
     }
     CK(cudaFuncSetAttribute(self_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)attention_smem_bytes<32>()));
@@ -902,12 +902,13 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
     // GroupNorm of `nb` samples whose data is sample (b % src_nb) of src
     auto gn = [&](const float* src, int src_nb, int nb, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh,
                   int ld, int off, float* act_out = nullptr, int act_ld = 0, int act_off = 0) -> int {
+        const int nsp = nb * GN_SPLIT >= num_sms ? GN_SPLIT : GN_SPLIT_MAX;   // few samples: more CTAs each
         cur_tag = TAG_GN;
-        gn_partial_kernel<<<dim3(GN_SPLIT, nb), GN_THREADS, 0, st>>>(src, src_nb, T, gn_partial);
+        gn_partial_kernel<<<dim3(nsp, nb), GN_THREADS, 0, st>>>(src, src_nb, T, gn_partial);
         LAUNCH_CHECK();
         cur_tag = TAG_GN;
-        gn_finish_kernel<<<dim3(act_out ? GN_SPLIT : 1, nb), GN_THREADS, 0, st>>>(src, src_nb, T, cpg, eps_, gn_partial, g, b, osc, osh,
-                                                                                  ld, off, act_out, act_ld, act_off);
+        gn_finish_kernel<<<dim3(act_out ? nsp : 1, nb), GN_THREADS, 0, st>>>(src, src_nb, T, cpg, eps_, gn_partial, nsp, g, b, osc, osh,
+                                                                             ld, off, act_out, act_ld, act_off);
         LAUNCH_CHECK();
         return 0;
     };

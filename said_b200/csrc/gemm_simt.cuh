@@ -492,19 +492,22 @@ struct EpiGeglu {
 // ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
-template <int BM, int BN, int TM, int TN, class AL, class EP>
+// BKT: K extent of one smem tile.  Loads of the two following tiles are in flight (two register stages) while
+// one tile is being multiplied, so a single clip's small grids are not a chain of exposed global-load latencies.
+template <int BM, int BN, int TM, int TN, int BKT, class AL, class EP>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_simt_kernel(GemmDims d, AL al, const float* __restrict__ Wt, EP ep) {
     static_assert((BM / TM) * (BN / TN) == GEMM_THREADS, "thread tiling");
     static_assert(TM == 2 || TM == 4 || TM == 8, "TM");
     static_assert(TN == 2 || TN == 4, "TN");
+    constexpr int KQ = BKT / 4;                                        // float4 per tile row = lanes sharing a row
     constexpr int ASTR = BM + 4;
-    constexpr int A_SLOTS = BM * 4;                                    // float4 slots in an A tile
+    constexpr int A_SLOTS = BM * KQ;                                   // float4 slots in an A tile
     constexpr int NA = (A_SLOTS + GEMM_THREADS - 1) / GEMM_THREADS;
-    constexpr int B_SLOTS = GEMM_BK * BN / 4;
+    constexpr int B_SLOTS = BKT * BN / 4;
     constexpr int NB = (B_SLOTS + GEMM_THREADS - 1) / GEMM_THREADS;
-    __shared__ __align__(16) float As[GEMM_BK][ASTR];
-    __shared__ __align__(16) float Bs[GEMM_BK][BN];
+    __shared__ __align__(16) float As[BKT][ASTR];
+    __shared__ __align__(16) float Bs[BKT][BN];
 
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * BM;
@@ -514,18 +517,18 @@ gemm_simt_kernel(GemmDims d, AL al, const float* __restrict__ Wt, EP ep) {
     Wt += (long long)(blockIdx.z % d.wz_mod) * d.w_zstride;
 
     typename AL::Ctx ctx[NA];
-    float4 ra[NA], rb[NB];
+    float4 ra[2][NA], rb[2][NB];
 #pragma unroll
     for (int s = 0; s < NA; ++s) {
         const int slot = tid + s * GEMM_THREADS;
-        if ((A_SLOTS % GEMM_THREADS == 0) || slot < A_SLOTS) ctx[s] = al.prep(m0 + (slot >> 2), slot & 3);
+        if ((A_SLOTS % GEMM_THREADS == 0) || slot < A_SLOTS) ctx[s] = al.prep(m0 + slot / KQ, slot % KQ);
     }
 
-    auto gload = [&](int k0) {
+    auto gload = [&](int k0, float4 (&qa)[NA], float4 (&qb)[NB]) {
 #pragma unroll
         for (int s = 0; s < NA; ++s) {
             const int slot = tid + s * GEMM_THREADS;
-            if ((A_SLOTS % GEMM_THREADS == 0) || slot < A_SLOTS) ra[s] = al.load4(ctx[s], k0 + (slot & 3) * 4);
+            if ((A_SLOTS % GEMM_THREADS == 0) || slot < A_SLOTS) qa[s] = al.load4(ctx[s], k0 + (slot % KQ) * 4);
         }
 #pragma unroll
         for (int s = 0; s < NB; ++s) {
@@ -533,17 +536,17 @@ gemm_simt_kernel(GemmDims d, AL al, const float* __restrict__ Wt, EP ep) {
             if ((B_SLOTS % GEMM_THREADS == 0) || slot < B_SLOTS) {
                 const int kr = slot / (BN / 4), c4 = slot % (BN / 4);
                 const int n = n0 + c4 * 4;
-                rb[s] = (n < d.N) ? ldg4(Wt + (long long)(k0 + kr) * d.ldw + n) : zero4();
+                qb[s] = (n < d.N) ? ldg4(Wt + (long long)(k0 + kr) * d.ldw + n) : zero4();
             }
         }
     };
-    auto sstore = [&]() {
+    auto sstore = [&](const float4 (&qa)[NA], const float4 (&qb)[NB]) {
 #pragma unroll
         for (int s = 0; s < NA; ++s) {
             const int slot = tid + s * GEMM_THREADS;
             if ((A_SLOTS % GEMM_THREADS == 0) || slot < A_SLOTS) {
-                const int r = slot >> 2, kq = (slot & 3) * 4;
-                As[kq + 0][r] = ra[s].x; As[kq + 1][r] = ra[s].y; As[kq + 2][r] = ra[s].z; As[kq + 3][r] = ra[s].w;
+                const int r = slot / KQ, kq = (slot % KQ) * 4;
+                As[kq + 0][r] = qa[s].x; As[kq + 1][r] = qa[s].y; As[kq + 2][r] = qa[s].z; As[kq + 3][r] = qa[s].w;
             }
         }
 #pragma unroll
@@ -551,7 +554,7 @@ gemm_simt_kernel(GemmDims d, AL al, const float* __restrict__ Wt, EP ep) {
             const int slot = tid + s * GEMM_THREADS;
             if ((B_SLOTS % GEMM_THREADS == 0) || slot < B_SLOTS) {
                 const int kr = slot / (BN / 4), c4 = slot % (BN / 4);
-                st4(&Bs[kr][c4 * 4], rb[s]);
+                st4(&Bs[kr][c4 * 4], qb[s]);
             }
         }
     };
@@ -563,14 +566,9 @@ gemm_simt_kernel(GemmDims d, AL al, const float* __restrict__ Wt, EP ep) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    const int nk = d.K / GEMM_BK;
-    gload(0);
-    for (int kt = 0; kt < nk; ++kt) {
-        sstore();
-        __syncthreads();
-        if (kt + 1 < nk) gload((kt + 1) * GEMM_BK);
+    auto compute = [&]() {
 #pragma unroll
-        for (int kk = 0; kk < GEMM_BK; ++kk) {
+        for (int kk = 0; kk < BKT; ++kk) {
             float a[TM], b[TN];
             if constexpr (TM == 8) {
                 const float4 a0 = ld4(&As[kk][ty * 8]), a1 = ld4(&As[kk][ty * 8 + 4]);
@@ -595,7 +593,24 @@ gemm_simt_kernel(GemmDims d, AL al, const float* __restrict__ Wt, EP ep) {
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
+    };
+
+    const int nk = d.K / BKT;
+    gload(0, ra[0], rb[0]);
+    if (nk > 1) gload(BKT, ra[1], rb[1]);
+    for (int kt = 0; kt < nk; kt += 2) {
+        sstore(ra[0], rb[0]);
         __syncthreads();
+        if (kt + 2 < nk) gload((kt + 2) * BKT, ra[0], rb[0]);
+        compute();
+        __syncthreads();
+        if (kt + 1 < nk) {
+            sstore(ra[1], rb[1]);
+            __syncthreads();
+            if (kt + 3 < nk) gload((kt + 3) * BKT, ra[1], rb[1]);
+            compute();
+            __syncthreads();
+        }
     }
 
 #pragma unroll
@@ -605,6 +620,18 @@ gemm_simt_kernel(GemmDims d, AL al, const float* __restrict__ Wt, EP ep) {
     }
 }
 
+// loaders whose lanes cooperate per row must know how many lanes share a row (= float4 per tile row)
+template <int LPR, class AL>
+struct RebindLanes {
+    using type = AL;
+    static const AL& conv(const AL& a) { return a; }
+};
+template <int LPR, int L0>
+struct RebindLanes<LPR, ALoadLNT<L0>> {
+    using type = ALoadLNT<LPR>;
+    static type conv(const ALoadLNT<L0>& a) { return type{a.X, a.M, a.T, a.pre_scale, a.pre_shift, a.gamma, a.beta, a.eps}; }
+};
+
 // Host-side launcher: picks the tile shape from the problem size (small M -> small tiles so that a
 // single clip still spreads over the SMs).
 template <class AL, class EP>
@@ -613,12 +640,14 @@ inline cudaError_t launch_gemm(cudaStream_t st, int M, int N, int K, const AL& a
     if (M <= 0 || batch <= 0) return cudaSuccess;
     GemmDims d{M, N, K, ldw, wz_mod, w_zstride};
     const long long big_ctas = (long long)((M + 127) / 128) * ((N + 63) / 64) * batch;
-    if (big_ctas >= 120) {
+    if (big_ctas >= 120 || K % 32 != 0) {
+        using R = RebindLanes<4, AL>;
         dim3 grid((M + 127) / 128, (N + 63) / 64, batch);
-        gemm_simt_kernel<128, 64, 8, 4, AL, EP><<<grid, GEMM_THREADS, 0, st>>>(d, al, Wt, ep);
+        gemm_simt_kernel<128, 64, 8, 4, 16, typename R::type, EP><<<grid, GEMM_THREADS, 0, st>>>(d, R::conv(al), Wt, ep);
     } else {
+        using R = RebindLanes<8, AL>;
         dim3 grid((M + 31) / 32, (N + 31) / 32, batch);
-        gemm_simt_kernel<32, 32, 2, 2, AL, EP><<<grid, GEMM_THREADS, 0, st>>>(d, al, Wt, ep);
+        gemm_simt_kernel<32, 32, 2, 2, 32, typename R::type, EP><<<grid, GEMM_THREADS, 0, st>>>(d, R::conv(al), Wt, ep);
     }
     return cudaGetLastError();
 }

@@ -16,7 +16,8 @@ namespace said {
 //                      tensor-core path, materialises silu(gn(x)) for its quarter of the frames so the conv
 //                      GEMM's operand loader is a plain shifted copy (the data was just read: L2 hits)
 constexpr int GN_THREADS = 768;   // 4 row phases x 192 channels
-constexpr int GN_SPLIT = 4;
+constexpr int GN_SPLIT = 4;        // CTAs per sample at batch scale
+constexpr int GN_SPLIT_MAX = 16;   // ... for a handful of samples (single-clip latency)
 __global__ void __launch_bounds__(GN_THREADS)
 gn_partial_kernel(const float* __restrict__ x, int src_samples, int T, double* __restrict__ partial /*(B', GN_SPLIT, 2, 192)*/) {
     constexpr int C = 192;
@@ -24,7 +25,8 @@ gn_partial_kernel(const float* __restrict__ x, int src_samples, int T, double* _
     __shared__ double s_sq[4][C];
     const int sp = blockIdx.x, b = blockIdx.y;
     const int c = threadIdx.x % C, ph = threadIdx.x / C;
-    const int rows = (T + GN_SPLIT - 1) / GN_SPLIT;
+    const int nsp = gridDim.x;
+    const int rows = (T + nsp - 1) / nsp;
     const int t0 = sp * rows, t1 = min(T, t0 + rows);
     const float* xb = x + (long long)(b % src_samples) * T * C;   // sample b reads source sample b % src_samples (shared CFG prefix)
     double s = 0.0, q = 0.0;
@@ -44,14 +46,14 @@ gn_partial_kernel(const float* __restrict__ x, int src_samples, int T, double* _
     s_sq[ph][c] = q;
     __syncthreads();
     if (threadIdx.x < C) {
-        double* pp = partial + ((long long)b * GN_SPLIT + sp) * 2 * C;
+        double* pp = partial + ((long long)b * nsp + sp) * 2 * C;
         pp[c] = (s_sum[0][c] + s_sum[1][c]) + (s_sum[2][c] + s_sum[3][c]);
         pp[C + c] = (s_sq[0][c] + s_sq[1][c]) + (s_sq[2][c] + s_sq[3][c]);
     }
 }
 
 __global__ void __launch_bounds__(GN_THREADS)
-gn_finish_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, float eps, const double* __restrict__ partial,
+gn_finish_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, float eps, const double* __restrict__ partial, int nsp,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale,
                  float* __restrict__ shift, int out_ld, int out_off, float* __restrict__ act_out, int act_ld, int act_off) {
     constexpr int C = 192;
@@ -61,8 +63,8 @@ gn_finish_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, f
     const int c = threadIdx.x % C, ph = threadIdx.x / C;
     if (threadIdx.x < C) {
         double s = 0.0, q = 0.0;
-        for (int k = 0; k < GN_SPLIT; ++k) {
-            const double* pp = partial + ((long long)b * GN_SPLIT + k) * 2 * C;
+        for (int k = 0; k < nsp; ++k) {
+            const double* pp = partial + ((long long)b * nsp + k) * 2 * C;
             s += pp[c];
             q += pp[C + c];
         }
@@ -93,7 +95,7 @@ gn_finish_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, f
         shift[(long long)b * out_ld + out_off + c] = sh;
     }
     if (act_out != nullptr) {
-        const int rows = (T + GN_SPLIT - 1) / GN_SPLIT;
+        const int rows = (T + (int)gridDim.x - 1) / (int)gridDim.x;
         const int t0 = sp * rows, t1 = min(T, t0 + rows);
         const float* xb = x + (long long)(b % src_samples) * T * C + c;
         float* ob = act_out + (long long)b * T * act_ld + act_off + c;
