@@ -61,7 +61,8 @@ time_embed_table_kernel(const float* __restrict__ tvals, TimeEmbedWeights w, flo
 // One diffusion-step epilogue (diffusion.py:430-456): classifier-free-guidance combine, optional
 // rescale_noise_cfg, DDIMScheduler.step (diffusers 0.19 scheduling_ddim.py, restated in
 // said_b200/scheduler.py), optional eta noise, optional editing blend, optional intermediate dump.
-// One CTA per clip (per-clip std reductions for the rescale).  All per-step scalars come from a
+// grid (clip, DDIM_SPLIT): each CTA updates a slice of the clip (for the rescale every CTA of a clip reduces the
+// whole clip itself, redundantly but deterministically).  All per-step scalars come from a
 // host-built table row indexed by the device-resident step counter so that one captured CUDA graph
 // serves every step.  Arithmetic uses explicit round-to-nearest mul/add (no FMA contraction) in the
 // reference's operation order, so the step is bit-identical to the fp32 CPU formulas.
@@ -86,6 +87,7 @@ struct StepParams {
     float* result;              // (B, n): clamp(latents / latent_scale, 0, 1), written on the last step
 };
 
+constexpr int DDIM_SPLIT = 8;
 __global__ void __launch_bounds__(256)
 ddim_step_kernel(StepParams p) {
     __shared__ double red[4][8];
@@ -126,7 +128,9 @@ ddim_step_kernel(StepParams p) {
 
     const long long soff = ((long long)step * p.B + b) * p.n;
     const bool last = step == p.n_steps - 1;
-    for (int i = tid; i < p.n; i += blockDim.x) {
+    const int per = (p.n + gridDim.y - 1) / gridDim.y;
+    const int i_end = min(p.n, (int)(blockIdx.y + 1) * per);
+    for (int i = blockIdx.y * per + tid; i < i_end; i += blockDim.x) {
         const float x = lat[i];
         if (p.intermediates) p.intermediates[soff + i] = __fdiv_rn(x, p.latent_scale);
         float e = cond[i];

@@ -1141,7 +1141,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         auto one_step = [&]() -> int {
             CKI(forward(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
             cur_tag = TAG_STEP;
-            ddim_step_kernel<<<B, 256, 0, st>>>(sp);
+            ddim_step_kernel<<<dim3(B, DDIM_SPLIT), 256, 0, st>>>(sp);
             LAUNCH_CHECK();
             add_int_kernel<<<1, 1, 0, st>>>(step_ctr, 1);
             LAUNCH_CHECK();
@@ -1305,7 +1305,7 @@ int said_op_ddim_step(said_engine* e, const float* pred_dev, float* latents_dev,
     sp.n_steps = 2;   // never "last": no result write
     sp.eta_noise = eta_noise_dev;
     sp.latent_scale = 1.0f;
-    ddim_step_kernel<<<B, 256, 0, st>>>(sp);
+    ddim_step_kernel<<<dim3(B, DDIM_SPLIT), 256, 0, st>>>(sp);
     e->launches += 2;
     CK(cudaGetLastError());
     return 0;
