@@ -87,30 +87,59 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
 
     if (warp < 8) {
         // ---------------- stage K (rows = keys) and V^T (rows = dims), TF32 hi/lo ----------------
-        for (int i = tid; i < Tk * 8; i += ATC_SM_THREADS) {
-            const int key = i >> 3, c = i & 7;
-            float4 x = zero4();
-            if (key < T) x = ldg4(gbase + (long long)key * ld + k_off + c * 4);
-            const uint32_t off = (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) << 4);
-            float4 hh, ll;
-            hh.x = rna_tf32(x.x); hh.y = rna_tf32(x.y); hh.z = rna_tf32(x.z); hh.w = rna_tf32(x.w);
-            ll.x = rna_tf32(x.x - hh.x); ll.y = rna_tf32(x.y - hh.y); ll.z = rna_tf32(x.z - hh.z); ll.w = rna_tf32(x.w - hh.w);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(k_hi + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(k_lo + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
+        // All global loads of a batch are issued before the first shared-memory store (the volatile stores would
+        // otherwise serialise one load round trip per iteration: staging was ~1/3 of the CTA's lifetime).
+        float4 qreg[4];                                    // raw Q rows of the next query tile (prefetched)
+        auto load_q = [&](int qt) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = tid + u * ATC_SM_THREADS, r = i >> 3, c = i & 7;
+                qreg[u] = (qt * 128 + r < T) ? ldg4(gbase + (long long)(qt * 128 + r) * ld + q_off + c * 4) : zero4();
+            }
+        };
+        load_q(0);
+        constexpr int KB = 5;
+        for (int i0 = tid; i0 < Tk * 8; i0 += ATC_SM_THREADS * KB) {
+            float4 x[KB];
+#pragma unroll
+            for (int u = 0; u < KB; ++u) {
+                const int i = i0 + u * ATC_SM_THREADS, key = i >> 3, c = i & 7;
+                x[u] = (key < T) ? ldg4(gbase + (long long)key * ld + k_off + c * 4) : zero4();
+            }
+#pragma unroll
+            for (int u = 0; u < KB; ++u) {
+                const int i = i0 + u * ATC_SM_THREADS, key = i >> 3, c = i & 7;
+                if (i < Tk * 8) {
+                    const uint32_t off = (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) << 4);
+                    float4 hh, ll;
+                    hh.x = rna_tf32(x[u].x); hh.y = rna_tf32(x[u].y); hh.z = rna_tf32(x[u].z); hh.w = rna_tf32(x[u].w);
+                    ll.x = rna_tf32(x[u].x - hh.x); ll.y = rna_tf32(x[u].y - hh.y); ll.z = rna_tf32(x[u].z - hh.z); ll.w = rna_tf32(x[u].w - hh.w);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(k_hi + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(k_lo + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
+                }
+            }
         }
-        for (int i = tid; i < nch * 32 * 8; i += ATC_SM_THREADS) {
-            const int key = i >> 3, c4 = i & 7;          // 4 dims c4*4 .. +3 of one key
-            float4 x = zero4();
-            if (key < T) x = ldg4(gbase + (long long)key * ld + v_off + c4 * 4);
-            const float xv[4] = {x.x, x.y, x.z, x.w};
-            const int chunk = key >> 5, kk = key & 31;
+        // V^T: one item = 4 consecutive keys x 4 dims, transposed in registers -> one 16-byte store per dim
+        for (int i0 = tid; i0 < nch * 64; i0 += ATC_SM_THREADS) {
+            const int kg = i0 >> 3, c4 = i0 & 7;             // key group (4 keys), dims c4*4 .. +3
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int key = kg * 4 + u;
+                x[u] = (key < T) ? ldg4(gbase + (long long)key * ld + v_off + c4 * 4) : zero4();
+            }
+            const int chunk = kg >> 3, kq = kg & 7;
+            const float xv[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
+                                    {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int dd = c4 * 4 + e;
-                const uint32_t off = (uint32_t)chunk * 4096u + (uint32_t)dd * 128u + (uint32_t)(((kk >> 2) ^ (dd & 7)) << 4) + (uint32_t)(kk & 3) * 4u;
-                const float hh = rna_tf32(xv[e]);
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(v_hi + off), "f"(hh) : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(v_lo + off), "f"(rna_tf32(xv[e] - hh)) : "memory");
+                const uint32_t off = (uint32_t)chunk * 4096u + (uint32_t)dd * 128u + (uint32_t)((kq ^ (dd & 7)) << 4);
+                float4 hh, ll;
+                hh.x = rna_tf32(xv[e][0]); hh.y = rna_tf32(xv[e][1]); hh.z = rna_tf32(xv[e][2]); hh.w = rna_tf32(xv[e][3]);
+                ll.x = rna_tf32(xv[e][0] - hh.x); ll.y = rna_tf32(xv[e][1] - hh.y); ll.z = rna_tf32(xv[e][2] - hh.z); ll.w = rna_tf32(xv[e][3] - hh.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(v_hi + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(v_lo + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
             }
         }
         const int row = tid & 127, half = tid >> 7;       // two threads per query row: column halves of every 32-key chunk
@@ -118,11 +147,11 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
         const float sl2 = scale * 1.4426950408889634f;    // softmax in base 2: exp(x) = 2^(x log2 e)
         uint32_t s_jobs = 0, p_use[2] = {0u, 0u};
         for (int qt = 0; qt < n_qtiles; ++qt) {
-            // ---------------- Q tile (into operand buffer 1) ----------------
-            for (int i = tid; i < 128 * 8; i += ATC_SM_THREADS) {
-                const int r = i >> 3, c = i & 7;
-                float4 x = zero4();
-                if (qt * 128 + r < T) x = ldg4(gbase + (long long)(qt * 128 + r) * ld + q_off + c * 4);
+            // ---------------- Q tile (into operand buffer 1) from the prefetched registers ----------------
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = tid + u * ATC_SM_THREADS, r = i >> 3, c = i & 7;
+                const float4 x = qreg[u];
                 const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
                 float4 hh, ll;
                 hh.x = rna_tf32(x.x); hh.y = rna_tf32(x.y); hh.z = rna_tf32(x.z); hh.w = rna_tf32(x.w);
@@ -132,17 +161,24 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
             }
             fence_proxy_async();
             mbar_arrive(bar_s_ready);                     // job: S = Q K^T
+            if (qt + 1 < n_qtiles) load_q(qt + 1);        // in flight during the MMAs and the softmax of this tile
             mbar_wait(bar_s_done, s_jobs & 1u);
             ++s_jobs;
             tc_fence_after();
             // ---------------- row max over the valid keys (each thread: every other 16-column group) ----------------
             float mx = -INFINITY;
-            for (int j0 = half * 16; j0 < Tk; j0 += 32) {
-                float v[16];
-                tmem_ld16(trow + ATC_S_COL + j0, v);
+            for (int j0 = half * 16; j0 < Tk; j0 += 64) {
+                float v[16], w[16];
+                const bool two = j0 + 32 < Tk;             // warp-uniform
+                tmem_ld16_issue(trow + ATC_S_COL + j0, v);
+                if (two) tmem_ld16_issue(trow + ATC_S_COL + j0 + 32, w);
+                tmem_ld_wait16(v);
+                if (two) tmem_ld_wait16(w);
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
+                for (int e = 0; e < 16; ++e) {
                     if (j0 + e < T) mx = fmaxf(mx, v[e]);
+                    if (two && j0 + 32 + e < T) mx = fmaxf(mx, w[e]);
+                }
             }
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)tid * 4u), "f"(mx) : "memory");
             named_bar_sync(1, ATC_SM_THREADS);

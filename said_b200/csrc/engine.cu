@@ -98,6 +98,7 @@ struct EncLayerW {
 struct said_engine {
     int device = 0;
     int num_sms = 0;
+    bool gn_fused = getenv("SAID_GN_TWO_PASS") == nullptr;   // cluster GroupNorm (one launch); the env switch keeps the two-kernel version reachable for A/B timing
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     long long launches = 0;
@@ -902,6 +903,28 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
     // GroupNorm of `nb` samples whose data is sample (b % src_nb) of src
     auto gn = [&](const float* src, int src_nb, int nb, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh,
                   int ld, int off, float* act_out = nullptr, int act_ld = 0, int act_off = 0) -> int {
+        {   // one launch, one cluster per sample (4 CTAs at batch scale, 8 for a handful of samples)
+            const int cl = nb * GN_SPLIT >= num_sms ? GN_SPLIT : 8;
+            const int rows = (T + cl - 1) / cl;
+            if (gn_fused && (rows + 7) / 8 <= GNF_MAXR) {
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(cl, nb);
+                cfg.blockDim = dim3(GNF_THREADS);
+                cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = cl;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                cur_tag = TAG_GN;
+                CK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, src, src_nb, T, cpg, eps_, g, b, osc, osh, ld, off, act_out, act_ld, act_off));
+                LAUNCH_CHECK();
+                return 0;
+            }
+        }
         const int nsp = nb * GN_SPLIT >= num_sms ? GN_SPLIT : GN_SPLIT_MAX;   // few samples: more CTAs each
         cur_tag = TAG_GN;
         gn_partial_kernel<<<dim3(nsp, nb), GN_THREADS, 0, st>>>(src, src_nb, T, gn_partial);

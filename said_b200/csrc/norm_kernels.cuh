@@ -1,5 +1,7 @@
 // Normalisation statistics and row-wise normalisation kernels.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace said {
@@ -100,6 +102,100 @@ gn_finish_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, f
         const float* xb = x + (long long)(b % src_samples) * T * C + c;
         float* ob = act_out + (long long)b * T * act_ld + act_off + c;
         for (int t2 = t0 + ph; t2 < t1; t2 += 4) ob[(long long)t2 * act_ld] = silu(__ldg(xb + (long long)t2 * C) * sc + sh);
+    }
+}
+
+// Single-launch GroupNorm: one thread-block CLUSTER per sample.  Each of the cluster's CTAs holds its share of the
+// sample's frames in registers (float4 per thread, all loads issued before the first use: ~57 KB in flight per CTA
+// instead of a scalar load chain), reduces per-channel sum / sum-of-squares in fp64, publishes its per-group partials in
+// shared memory, and after one cluster barrier every CTA reads all partials through distributed shared memory in rank
+// order (deterministic), derives scale / shift and writes silu(gn(x)) for its frames from the registers.
+// x is read once and the activation written once (the two-kernel version reads x twice), one launch instead of two.
+// Requires ceil(ceil(T / cluster) / 8) <= GNF_MAXR.
+constexpr int GNF_THREADS = 384;   // 8 row phases x 48 channel quads
+constexpr int GNF_MAXR = 10;       // frames per thread
+__global__ void __launch_bounds__(GNF_THREADS)
+gn_fused_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, float eps, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int out_ld, int out_off,
+                float* __restrict__ act_out, int act_ld, int act_off) {
+    constexpr int C = 192, Q = C / 4, PH = GNF_THREADS / Q;
+    __shared__ double s_red[PH][2][C];
+    __shared__ double s_part[2][32];     // this CTA's per-group sum / sum of squares (read by the whole cluster)
+    __shared__ float s_mean[32], s_rstd[32];
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const int nsp = (int)cluster.num_blocks(), sp = (int)cluster.block_rank(), b = blockIdx.y;
+    const int q = threadIdx.x % Q, ph = threadIdx.x / Q;
+    const int rows = (T + nsp - 1) / nsp;
+    const int t0 = sp * rows, t1 = min(T, t0 + rows);
+    const float* xb = x + (long long)(b % src_samples) * T * C + q * 4;
+    float4 v[GNF_MAXR];
+#pragma unroll
+    for (int i = 0; i < GNF_MAXR; ++i) {
+        const int t = t0 + ph + PH * i;
+        v[i] = t < t1 ? ldg4(xb + (long long)t * C) : zero4();
+    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < GNF_MAXR; ++i) {
+        s0 += (double)v[i].x; q0 += (double)v[i].x * (double)v[i].x;
+        s1 += (double)v[i].y; q1 += (double)v[i].y * (double)v[i].y;
+        s2 += (double)v[i].z; q2 += (double)v[i].z * (double)v[i].z;
+        s3 += (double)v[i].w; q3 += (double)v[i].w * (double)v[i].w;
+    }
+    s_red[ph][0][q * 4 + 0] = s0; s_red[ph][0][q * 4 + 1] = s1; s_red[ph][0][q * 4 + 2] = s2; s_red[ph][0][q * 4 + 3] = s3;
+    s_red[ph][1][q * 4 + 0] = q0; s_red[ph][1][q * 4 + 1] = q1; s_red[ph][1][q * 4 + 2] = q2; s_red[ph][1][q * 4 + 3] = q3;
+    __syncthreads();
+    const int ng = C / cpg;
+    if ((int)threadIdx.x < 2 * ng) {     // thread (g, which): group g, sum (0) or sum of squares (1)
+        const int g = threadIdx.x % ng, w = threadIdx.x / ng;
+        double a = 0.0;
+        for (int j = 0; j < cpg; ++j) {
+            const int c = g * cpg + j;
+            double cs = 0.0;
+#pragma unroll
+            for (int p2 = 0; p2 < PH; ++p2) cs += s_red[p2][w][c];
+            a += cs;
+        }
+        s_part[w][g] = a;
+    }
+    cluster.sync();
+    if ((int)threadIdx.x < ng) {
+        double gs = 0.0, gq = 0.0;
+        for (int r = 0; r < nsp; ++r) {
+            const double* rp = cluster.map_shared_rank(&s_part[0][0], r);
+            gs += rp[threadIdx.x];
+            gq += rp[32 + threadIdx.x];
+        }
+        const double n = (double)cpg * T;
+        const double mean = gs / n;
+        double var = gq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    cluster.sync();                      // also: no CTA leaves while its partials may still be read remotely
+    const float4 gm = ldg4(gamma + q * 4), bt = ldg4(beta + q * 4);
+    float4 sc, sh;
+    {
+        const int g0 = (q * 4) / cpg, g1 = (q * 4 + 1) / cpg, g2 = (q * 4 + 2) / cpg, g3 = (q * 4 + 3) / cpg;
+        sc.x = s_rstd[g0] * gm.x; sh.x = bt.x - s_mean[g0] * sc.x;
+        sc.y = s_rstd[g1] * gm.y; sh.y = bt.y - s_mean[g1] * sc.y;
+        sc.z = s_rstd[g2] * gm.z; sh.z = bt.z - s_mean[g2] * sc.z;
+        sc.w = s_rstd[g3] * gm.w; sh.w = bt.w - s_mean[g3] * sc.w;
+    }
+    if (sp == 0 && ph == 0) {
+        st4(scale + (long long)b * out_ld + out_off + q * 4, sc);
+        st4(shift + (long long)b * out_ld + out_off + q * 4, sh);
+    }
+    if (act_out != nullptr) {
+        float* ob = act_out + (long long)b * T * act_ld + act_off + q * 4;
+#pragma unroll
+        for (int i = 0; i < GNF_MAXR; ++i) {
+            const int t = t0 + ph + PH * i;
+            if (t < t1)
+                st4(ob + (long long)t * act_ld, make_float4(silu(v[i].x * sc.x + sh.x), silu(v[i].y * sc.y + sh.y),
+                                                            silu(v[i].z * sc.z + sh.z), silu(v[i].w * sc.w + sh.w)));
+        }
     }
 }
 
