@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from said_b200._lib import Engine
 eng = Engine(torch.device("cuda:0"))
-for M in (38400, 37888, 19200):
+for M in (38400, 37888):
     print("M=%d N=192; ms per launch (dbg bits: 2 skip weights, 4 skip epilogue IO, 8 skip MMAs)" % M)
     for K in (192, 576, 768, 1152):
         for ns in (3, 1):

@@ -112,8 +112,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 if (i < Tk * 8) {
                     const uint32_t off = (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) << 4);
                     float4 hh, ll;
-                    hh.x = rna_tf32(x[u].x); hh.y = rna_tf32(x[u].y); hh.z = rna_tf32(x[u].z); hh.w = rna_tf32(x[u].w);
-                    ll.x = rna_tf32(x[u].x - hh.x); ll.y = rna_tf32(x[u].y - hh.y); ll.z = rna_tf32(x[u].z - hh.z); ll.w = rna_tf32(x[u].w - hh.w);
+                    tf32_split4(x[u], hh, ll);
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(k_hi + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(k_lo + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
                 }
@@ -136,8 +135,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 const int dd = c4 * 4 + e;
                 const uint32_t off = (uint32_t)chunk * 4096u + (uint32_t)dd * 128u + (uint32_t)((kq ^ (dd & 7)) << 4);
                 float4 hh, ll;
-                hh.x = rna_tf32(xv[e][0]); hh.y = rna_tf32(xv[e][1]); hh.z = rna_tf32(xv[e][2]); hh.w = rna_tf32(xv[e][3]);
-                ll.x = rna_tf32(xv[e][0] - hh.x); ll.y = rna_tf32(xv[e][1] - hh.y); ll.z = rna_tf32(xv[e][2] - hh.z); ll.w = rna_tf32(xv[e][3] - hh.w);
+                tf32_split4(make_float4(xv[e][0], xv[e][1], xv[e][2], xv[e][3]), hh, ll);
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(v_hi + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(v_lo + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
             }
@@ -154,8 +152,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 const float4 x = qreg[u];
                 const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
                 float4 hh, ll;
-                hh.x = rna_tf32(x.x); hh.y = rna_tf32(x.y); hh.z = rna_tf32(x.z); hh.w = rna_tf32(x.w);
-                ll.x = rna_tf32(x.x - hh.x); ll.y = rna_tf32(x.y - hh.y); ll.z = rna_tf32(x.z - hh.z); ll.w = rna_tf32(x.w - hh.w);
+                tf32_split4(x, hh, ll);
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf1 + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf1 + 16384u + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
             }
@@ -213,9 +210,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t off = pbase + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4);
                     float4 hh, ll;
-                    hh.x = rna_tf32(p[4 * c]); hh.y = rna_tf32(p[4 * c + 1]); hh.z = rna_tf32(p[4 * c + 2]); hh.w = rna_tf32(p[4 * c + 3]);
-                    ll.x = rna_tf32(p[4 * c] - hh.x); ll.y = rna_tf32(p[4 * c + 1] - hh.y);
-                    ll.z = rna_tf32(p[4 * c + 2] - hh.z); ll.w = rna_tf32(p[4 * c + 3] - hh.w);
+                    tf32_split4(make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]), hh, ll);
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(off + 16384u), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
                 }

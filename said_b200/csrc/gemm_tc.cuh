@@ -165,6 +165,17 @@ SAID_DEVINL float rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// TF32 hi / lo split of a finite fp32 value, 3 ALU instructions per value (cvt.rna.tf32.f32 alone is 4: add, inf/nan
+// test, select, mask; the split with two of them is 9):
+//   hi = round-to-nearest (ties away) to 10 mantissa bits, by integer add + mask on the bit pattern
+//   lo = x - hi exactly (fp32 subtraction of nearby values is exact); the tensor core ignores the low 13 mantissa bits
+//        of its TF32 inputs, so lo is effectively truncated to 11 significant bits: |error| <= 2^-10 |lo| <= 2^-21 |x|,
+//        the same order as the dropped lo*lo term of the 3xTF32 product.
+SAID_DEVINL float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+SAID_DEVINL void tf32_split4(const float4& x, float4& h, float4& l) {
+    h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+}
 
 SAID_DEVINL void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {   // src_bytes 0 -> zero fill
     // L2::256B: a miss brings the whole 256-byte segment of the row into L2, so HBM sees long bursts instead of
@@ -178,7 +189,7 @@ SAID_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(
 struct TcDims {
     int M, N, K;
     int w_block_floats;   // floats between consecutive (n-tile, k-chunk) blocks of the weight image
-    int dbg;              // diagnostics (said_op_gemm_tc_bench): 1 skip A loads, 2 skip weight copies, 4 skip epilogue I/O, 8 skip MMAs
+    int dbg;              // diagnostics (said_op_gemm_tc_bench): 2 skip weight copies, 4 skip epilogue I/O, 8 skip MMAs
 };
 
 constexpr int EPI_WARPS = 8;              // warps 0-7: TMEM lane quarter = warp % 4, column half = warp / 4
@@ -193,14 +204,19 @@ template <int BN, int NSPLIT>
 struct TcCfg {
     static constexpr int NPARTS = NSPLIT == 3 ? 2 : 1;                 // hi (+ lo) copies of each operand
     static constexpr int B_TILE_BYTES = BN * ROW_BYTES;
-    static constexpr int A_STAGE_BYTES = NPARTS * A_TILE_BYTES;
     static constexpr int B_STAGE_BYTES = NPARTS * B_TILE_BYTES;
-    static constexpr int A_STAGES = NSPLIT == 3 ? 3 : 6;               // activations: cp.async lands directly in the stage
+    // Activations: cp.async lands directly in a "hi" stage (raw fp32 = the TF32 hi operand); the lo tiles live in their
+    // own, shorter ring because a lo tile only exists between the transform and the completion of its MMAs.  The hi
+    // ring depth is what hides the global-load latency: item i + A_STAGES - 1 is issued when MMA(i - 1) completes, so
+    // the latency budget is (A_STAGES - 2) chunk times of MMA (with 3 coupled hi+lo stages it was ONE, and the MMA
+    // thread spent ~half of its time waiting for the producers: profiles/r1_gemm_pipeline.md).
+    static constexpr int A_STAGES = NSPLIT == 3 ? 5 : 6;
+    static constexpr int A_LO_STAGES = NSPLIT == 3 ? 2 : 0;
     static constexpr int B_STAGES = NSPLIT == 3 ? 2 : 4;               // weights: bulk copies
     static constexpr int ACC_STRIDE = 256;                             // TMEM columns between the two accumulators
     static constexpr int TMEM_COLS = 512;
     static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 16 * 4;    // per warp: 32 rows x 16 columns fp32 (transpose staging)
-    static constexpr size_t SMEM_BYTES = (size_t)A_STAGES * A_STAGE_BYTES + (size_t)B_STAGES * B_STAGE_BYTES + EPI_STAGE_BYTES +
+    static constexpr size_t SMEM_BYTES = (size_t)(A_STAGES + A_LO_STAGES) * A_TILE_BYTES + (size_t)B_STAGES * B_STAGE_BYTES + EPI_STAGE_BYTES +
                                          1024 /*alignment slack*/ + 256 /*barriers*/;
     static constexpr int W_BLOCK_FLOATS = NPARTS * B_TILE_BYTES / 4;   // floats copied per (n-tile, k-chunk)
 };
@@ -216,11 +232,13 @@ template <int BN, int NSPLIT, class AL, class EP>
 __global__ void __launch_bounds__(THREADS2, 1)
 gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     using Cfg = TcCfg<BN, NSPLIT>;
-    constexpr int AS = Cfg::A_STAGES, BS = Cfg::B_STAGES;
+    constexpr int AS = Cfg::A_STAGES, ALS = Cfg::A_LO_STAGES, BS = Cfg::B_STAGES;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+    static_assert(NSPLIT != 3 || ALS >= 2, "3xTF32 needs a lo ring");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_base = smem_base + AS * Cfg::A_STAGE_BYTES;
+    const uint32_t alo_base = smem_base + AS * A_TILE_BYTES;
+    const uint32_t b_base = alo_base + ALS * A_TILE_BYTES;
     const uint32_t epi_base = b_base + BS * Cfg::B_STAGE_BYTES;
     const uint32_t bar_base = epi_base + Cfg::EPI_STAGE_BYTES;
     auto fulla_bar = [&](int s) { return bar_base + 8u * s; };
@@ -230,7 +248,8 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     auto accf_bar = [&](int b) { return bar_base + 8u * (2 * AS + 2 * BS + b); };
     auto acce_bar = [&](int b) { return bar_base + 8u * (2 * AS + 2 * BS + 2 + b); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * AS + 2 * BS + 4);
-    auto a_hi = [&](int s) { return smem_base + s * Cfg::A_STAGE_BYTES; };
+    auto a_hi = [&](int s) { return smem_base + s * A_TILE_BYTES; };
+    auto a_lo = [&](int s) { return alo_base + s * A_TILE_BYTES; };
     auto b_hi = [&](int s) { return b_base + s * Cfg::B_STAGE_BYTES; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -337,7 +356,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(BM, BN);
-            int sa = 0, sb = 0;
+            int sa = 0, sb = 0, sl = 0;
             uint32_t pa = 0, pb = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int buf = i & 1;
@@ -350,7 +369,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                     tc_fence_after();
                     const uint64_t da = make_desc(a_hi(sa));
                     const uint64_t db = make_desc(b_hi(sb));
-                    const uint64_t dal = make_desc(a_hi(sa) + A_TILE_BYTES);
+                    const uint64_t dal = make_desc(a_lo(sl));
                     const uint64_t dbl = make_desc(b_hi(sb) + Cfg::B_TILE_BYTES);
 #pragma unroll
                     for (int k4 = 0; k4 < ((d.dbg & 8) ? 0 : BK / 8); ++k4) {
@@ -365,6 +384,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                     mma_commit(emptyb_bar(sb));
                     if (++sa == AS) { sa = 0; pa ^= 1u; }
                     if (++sb == BS) { sb = 0; pb ^= 1u; }
+                    if (ALS > 0 && ++sl == ALS) sl = 0;
                 }
                 mma_commit(accf_bar(buf));      // accumulator complete
             }
@@ -402,53 +422,68 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
 #pragma unroll
         for (int i = 0; i < LROWS; ++i) off[i] = swz_off(rb + LROW_STEP * i, c);
         const bool ident = al.identity();
-        // ---- issue pointer (runs AS - 1 items ahead of the transform pointer, across tile boundaries)
-        int ti_i = 0, kc_i = 0, sa_i = 0;
+        const int total_items = my_tiles * nk;
+        // ---- issue pointer: item `ii` (tile ti_i, chunk kc_i) goes to hi stage sa_i; runs up to AS - 1 items ahead of
+        //      the transform pointer, across tile boundaries
+        int ii = 0, ti_i = 0, kc_i = 0, sa_i = 0;
         uint32_t pa_i = 0;
         typename AL::ICtx ic[LROWS];
-        // issue(block): cp.async the next item into its stage.  With block == false it gives up (returns false,
-        // commits nothing) when the MMAs that last read the stage have not completed yet, so that the transform of
-        // the current item is never held up behind a busy tensor pipe; the caller then issues after the transform.
-        auto issue = [&](bool block) -> bool {
-            if (ti_i < my_tiles) {
-                if (block) mbar_wait(emptya_bar(sa_i), pa_i ^ 1u);
-                else if (!mbar_test_wait(emptya_bar(sa_i), pa_i ^ 1u)) return false;
-                if (kc_i == 0) {
-                    const int m0 = ((tile0 + ti_i) / n_tiles) * BM;
+        auto issue_one = [&]() {                 // the stage must be free (MMAs of item ii - AS complete)
+            if (kc_i == 0) {
+                const int m0 = ((tile0 + ti_i) / n_tiles) * BM;
 #pragma unroll
-                    for (int i = 0; i < LROWS; ++i) ic[i] = al.iprep(m0 + rb + LROW_STEP * i);
-                }
-                const uint32_t dst = a_hi(sa_i);
-#pragma unroll
-                for (int i = 0; i < LROWS; ++i) {
-                    bool valid;
-                    const float* src = al.isrc(ic[i], kc_i * BK + c * 4, valid);
-                    cp_async16(dst + off[i], src, valid ? 16u : 0u);
-                }
-                if (++kc_i == nk) { kc_i = 0; ++ti_i; }
-                if (++sa_i == AS) { sa_i = 0; pa_i ^= 1u; }
+                for (int i = 0; i < LROWS; ++i) ic[i] = al.iprep(m0 + rb + LROW_STEP * i);
             }
-            cp_async_commit();                 // (possibly empty) group: keeps the wait_group accounting uniform
-            return true;
-        };
+            const uint32_t dst = a_hi(sa_i);
 #pragma unroll
-        for (int j = 0; j < AS - 1; ++j) issue(true);
+            for (int i = 0; i < LROWS; ++i) {
+                bool valid;
+                const float* src = al.isrc(ic[i], kc_i * BK + c * 4, valid);
+                cp_async16(dst + off[i], src, valid ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (++kc_i == nk) { kc_i = 0; ++ti_i; }
+            if (++sa_i == AS) { sa_i = 0; pa_i ^= 1u; }
+            ++ii;
+        };
+        for (int j = 0; j < AS - 1 && ii < total_items; ++j) issue_one();   // first use of every stage: free
         // ---- transform pointer
         typename AL::Ctx ctx[LROWS];
-        int sa_x = 0;
+        int it = 0, sa_x = 0, sl_x = 0;
+        int sj = 0;                              // hi stage (and its phase) of item it - ALS, whose MMAs free lo stage sl_x
+        uint32_t pj = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int m0 = ((tile0 + ti) / n_tiles) * BM;
             const bool new_rows = ti == 0 || (tile0 + ti) / n_tiles != (tile0 + ti - 1) / n_tiles;
-            for (int kc = 0; kc < nk; ++kc) {
-                const bool early = issue(false);
-                if (early) cp_async_wait<AS - 1>();   // this thread's chunks of the current item have landed
-                else cp_async_wait<AS - 2>();
+            for (int kc = 0; kc < nk; ++kc, ++it) {
+                // keep the ring full without blocking: a stage is free once the MMAs that read it have completed
+                while (ii < total_items && ii - it < AS && mbar_test_wait(emptya_bar(sa_i), pa_i ^ 1u)) issue_one();
+                if (ii == it) {                  // nothing in flight for the current item: must block
+                    mbar_wait(emptya_bar(sa_i), pa_i ^ 1u);
+                    issue_one();
+                }
+                // this thread's chunks of item `it` have landed when at most ii - it - 1 newer groups are pending
+                switch (ii - it - 1) {
+                    case 0: cp_async_wait<0>(); break;
+                    case 1: cp_async_wait<1>(); break;
+                    case 2: cp_async_wait<2>(); break;
+                    case 3: cp_async_wait<3>(); break;
+                    case 4: cp_async_wait<4>(); break;
+                    default: cp_async_wait<5>(); break;
+                }
                 if (kc == 0 && !ident && new_rows) {
 #pragma unroll
                     for (int i = 0; i < LROWS; ++i) ctx[i] = al.prep(m0 + rb + LROW_STEP * i, c);
                 }
                 const uint32_t abase = a_hi(sa_x);
                 if (NSPLIT == 3 || !ident) {
+                    if constexpr (NSPLIT == 3) {
+                        if (it >= ALS) {         // lo stage sl_x was last read by the MMAs of item it - ALS
+                            mbar_wait(emptya_bar(sj), pj);
+                            if (++sj == AS) { sj = 0; pj ^= 1u; }
+                        }
+                    }
+                    const uint32_t lbase = a_lo(sl_x);
 #pragma unroll
                     for (int i = 0; i < LROWS; ++i) {
                         float4 x;
@@ -456,7 +491,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                         float4 h;
                         if (!ident) {
                             x = al.xform(ctx[i], kc * BK + c * 4, x);
-                            h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+                            h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
                             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(abase + off[i]), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
                         } else {
                             // untouched fp32 in the hi tile: the tensor core reads its upper 19 bits (TF32 truncation)
@@ -466,17 +501,16 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                             h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
                         }
                         if constexpr (NSPLIT == 3) {
-                            float4 l;
-                            l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y);
-                            l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
-                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(abase + A_TILE_BYTES + off[i]), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                            float4 l;      // unrounded: the tensor core truncates it (see tf32_split4)
+                            l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lbase + off[i]), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
                         }
                     }
                 }
                 fence_proxy_async();
                 mbar_arrive(fulla_bar(sa_x));
                 if (++sa_x == AS) sa_x = 0;
-                if (!early) issue(true);
+                if (ALS > 0 && ++sl_x == ALS) sl_x = 0;
             }
         }
     }
