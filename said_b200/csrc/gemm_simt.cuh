@@ -364,27 +364,38 @@ struct EpiStd {
             for (int j = 0; j < TN; ++j) o[j] = v[j];
         }
     }
-    // tcgen05 epilogue interface (gemm_tc.cuh): one float4 = 4 consecutive columns of one row per call, the
-    // residual float4 loaded ahead of time
-    SAID_DEVINL float4 prefetch4(int m, int n) const {
-        return (res != nullptr && n < N) ? ldg4_l2pf(res + (long long)(res_mod > 0 ? m % res_mod : m) * ldr + n) : zero4();
+    // tcgen05 epilogue interface (gemm_tc.cuh): one float4 = 4 consecutive columns of one row per call, the residual
+    // float4 loaded ahead of time.  Everything that depends only on the row (residual row address with its modulo,
+    // sample index, time-embedding row) is computed once per (row, tile) into a RowCtx, and the residual load itself
+    // is UNCONDITIONAL (row / column clamped into range): a `cond ? load : zero` form compiles to branches plus
+    // register zeroing whose scoreboard waits serialise the loads, which made the epilogue the critical path of the
+    // K = 192 GEMMs (profiles/r1_gemm_pipeline.md).
+    struct RowCtx { const float* res; const float* emb_row; int b; };
+    SAID_DEVINL bool tc_has_res() const { return res != nullptr; }
+    SAID_DEVINL RowCtx tc_row(int m, int M) const {
+        RowCtx c;
+        const int mm = m < M ? m : M - 1;
+        c.res = res ? res + (long long)(res_mod > 0 ? mm % res_mod : mm) * ldr : nullptr;
+        c.b = (emb || res_scale) ? mm / T : 0;
+        c.emb_row = emb ? emb + (long long)(step_ptr ? *step_ptr : c.b) * emb_ld : nullptr;
+        return c;
     }
-    SAID_DEVINL void store4(int m, int n, float4 a, float4 r) const {
+    SAID_DEVINL float4 tc_prefetch4(const RowCtx& c, int n) const { return ldg4_l2pf(c.res + (n < N ? n : 0)); }
+    SAID_DEVINL void store4(const RowCtx& c, int m, int n, float4 a, float4 r) const {
         if (n >= N) return;
         if (bias) {
             const float4 bq = ldg4(bias + n);
             a.x += bq.x; a.y += bq.y; a.z += bq.z; a.w += bq.w;
         }
         if (act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
-        const int b = (emb || res_scale) ? m / T : 0;
         if (emb) {
-            const float4 q = ldg4(emb + (long long)(step_ptr ? *step_ptr : b) * emb_ld + n);
+            const float4 q = ldg4(c.emb_row + n);
             a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
         }
         if (res) {
             if (res_scale) {
-                const float4 sc = ldg4(res_scale + (long long)b * res_aff_ld + n);
-                const float4 sh = ldg4(res_shift + (long long)b * res_aff_ld + n);
+                const float4 sc = ldg4(res_scale + (long long)c.b * res_aff_ld + n);
+                const float4 sh = ldg4(res_shift + (long long)c.b * res_aff_ld + n);
                 r.x = r.x * sc.x + sh.x; r.y = r.y * sc.y + sh.y; r.z = r.z * sc.z + sh.z; r.w = r.w * sc.w + sh.w;
             }
             a.x = r.x + a.x; a.y = r.y + a.y; a.z = r.z + a.z; a.w = r.w + a.w;
@@ -463,8 +474,11 @@ struct EpiGeglu {
             o[j >> 1] = val * gelu_erf(gate);
         }
     }
-    SAID_DEVINL float4 prefetch4(int, int) const { return zero4(); }
-    SAID_DEVINL void store4(int m, int n, float4 a, float4) const {
+    struct RowCtx {};
+    SAID_DEVINL bool tc_has_res() const { return false; }
+    SAID_DEVINL RowCtx tc_row(int, int) const { return RowCtx{}; }
+    SAID_DEVINL float4 tc_prefetch4(const RowCtx&, int) const { return zero4(); }
+    SAID_DEVINL void store4(const RowCtx&, int m, int n, float4 a, float4) const {
         if (n >= N) return;
         const float4 bq = ldg4(bias + n);
         float2 o;

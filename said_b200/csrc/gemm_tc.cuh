@@ -298,19 +298,26 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
         const int q = warp & 3, half = warp >> 2;
         const int lr = lane >> 2, lq = lane & 3;           // after the transpose: rows lr + 8 i, float4 column lq
         const uint32_t stg = epi_base + (uint32_t)warp * (32 * 16 * 4);
+        const bool has_res = ep.tc_has_res() && !(d.dbg & 4);
+        float4 pf[EPI_PF][4];
+#pragma unroll
+        for (int jj = 0; jj < EPI_PF; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) pf[jj][ii] = zero4();
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = tile0 + i;
             const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
             const int buf = i & 1;
             const int mrow0 = mt * BM + q * 32 + lr;       // + 8 ii
-            float4 pf[EPI_PF][4];
+            typename EP::RowCtx rc[4];
 #pragma unroll
-            for (int jj = 0; jj < EPI_PF; ++jj) {
-                const int j = 2 * jj + half;
+            for (int ii = 0; ii < 4; ++ii) rc[ii] = ep.tc_row(mrow0 + 8 * ii, d.M);
+            if (has_res) {                                 // CTA-uniform; the loads themselves are unconditional
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {
-                    const int m = mrow0 + 8 * ii;
-                    pf[jj][ii] = (j < NCH && m < d.M && !(d.dbg & 4)) ? ep.prefetch4(m, nt * BN + j * 16 + lq * 4) : zero4();
+                for (int jj = 0; jj < EPI_PF; ++jj) {
+                    const int j = 2 * jj + half;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) pf[jj][ii] = ep.tc_prefetch4(rc[ii], nt * BN + (j < NCH ? j : 0) * 16 + lq * 4);
                 }
             }
             mbar_wait(accf_bar(buf), (uint32_t)(i >> 1) & 1u);
@@ -338,14 +345,13 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                         float4 acc;
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "r"(a));
                         const int m = mrow0 + 8 * ii;
-                        if (m < d.M && !(d.dbg & 4)) ep.store4(m, n, acc, pf[jj % EPI_PF][ii]);
+                        if (m < d.M && !(d.dbg & 4)) ep.store4(rc[ii], m, n, acc, pf[jj % EPI_PF][ii]);
                     }
                     __syncwarp();
                     const int jn = j + 2 * EPI_PF;
+                    if (has_res && jn < NCH) {             // warp-uniform
 #pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const int m = mrow0 + 8 * ii;
-                        if (jn < NCH && m < d.M && !(d.dbg & 4)) pf[jj % EPI_PF][ii] = ep.prefetch4(m, nt * BN + jn * 16 + lq * 4);
+                        for (int ii = 0; ii < 4; ++ii) pf[jj % EPI_PF][ii] = ep.tc_prefetch4(rc[ii], nt * BN + jn * 16 + lq * 4);
                     }
                 }
             }
@@ -632,19 +638,26 @@ gemm_tca_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
         const int q = warp & 3, half = warp >> 2;
         const int lr = lane >> 2, lq = lane & 3;           // after the transpose: rows lr + 8 i, float4 column lq
         const uint32_t stg = epi_base + (uint32_t)warp * (32 * 16 * 4);
+        const bool has_res = ep.tc_has_res() && !(d.dbg & 4);
+        float4 pf[EPI_PF][4];
+#pragma unroll
+        for (int jj = 0; jj < EPI_PF; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) pf[jj][ii] = zero4();
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = blockIdx.x + i * gridDim.x;
             const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
             const int buf = i & 1;
             const int mrow0 = mt * BM + q * 32 + lr;       // + 8 ii
-            float4 pf[EPI_PF][4];
+            typename EP::RowCtx rc[4];
 #pragma unroll
-            for (int jj = 0; jj < EPI_PF; ++jj) {
-                const int j = 2 * jj + half;
+            for (int ii = 0; ii < 4; ++ii) rc[ii] = ep.tc_row(mrow0 + 8 * ii, d.M);
+            if (has_res) {                                 // CTA-uniform; the loads themselves are unconditional
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {
-                    const int m = mrow0 + 8 * ii;
-                    pf[jj][ii] = (j < NCH && m < d.M && !(d.dbg & 4)) ? ep.prefetch4(m, nt * BN + j * 16 + lq * 4) : zero4();
+                for (int jj = 0; jj < EPI_PF; ++jj) {
+                    const int j = 2 * jj + half;
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) pf[jj][ii] = ep.tc_prefetch4(rc[ii], nt * BN + (j < NCH ? j : 0) * 16 + lq * 4);
                 }
             }
             mbar_wait(accf_bar(buf), (uint32_t)(i >> 1) & 1u);
@@ -672,14 +685,13 @@ gemm_tca_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                         float4 acc;
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "r"(a));
                         const int m = mrow0 + 8 * ii;
-                        if (m < d.M && !(d.dbg & 4)) ep.store4(m, n, acc, pf[jj % EPI_PF][ii]);
+                        if (m < d.M && !(d.dbg & 4)) ep.store4(rc[ii], m, n, acc, pf[jj % EPI_PF][ii]);
                     }
                     __syncwarp();
                     const int jn = j + 2 * EPI_PF;
+                    if (has_res && jn < NCH) {             // warp-uniform
 #pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const int m = mrow0 + 8 * ii;
-                        if (jn < NCH && m < d.M && !(d.dbg & 4)) pf[jj % EPI_PF][ii] = ep.prefetch4(m, nt * BN + jn * 16 + lq * 4);
+                        for (int ii = 0; ii < 4; ++ii) pf[jj % EPI_PF][ii] = ep.tc_prefetch4(rc[ii], nt * BN + jn * 16 + lq * 4);
                     }
                 }
             }
