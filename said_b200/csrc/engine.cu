@@ -993,7 +993,19 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         const int mh = h_nb * T;
         const bool shared_front = h_nb < Bp;
         CKI(gn(h, h_nb, h_nb, 6, 1e-6f, W.gn_g, W.gn_b, sc_st, sh_st, C, 0));
-        {   // q,k,v = LN1(GN(h)) W   (no bias)
+        // Tensor-core path: LN outputs that feed a GEMM wider than one output tile are materialised once (gnbuf is
+        // free inside the transformer block) so the GEMM's producers run the plain copy path
+        auto ln_rows = [&](const float* src, int m, const float* ps, const float* pb, const float* g, const float* b, float* dst) -> int {
+            cur_tag = TAG_GN;
+            ln192_rows_kernel<<<(unsigned)(((long long)m * 16 + 255) / 256), 256, 0, st>>>(src, m, T, ps, pb, g, b, 1e-5f, dst);
+            LAUNCH_CHECK();
+            return 0;
+        };
+        if (mat) {   // q,k,v = LN1(GN(h)) W   (no bias)
+            CKI(ln_rows(h, mh, sc_st, sh_st, W.ln1_g, W.ln1_b, gnb));
+            EpiStd ep = mk_epi(qkv.p, 3 * C, 3 * C);
+            CKI(gemm(st, mh, 3 * C, C, mk_plain(gnb, C, mh), W.wqkv, 3 * C, ep));
+        } else {
             ALoadLN al{h, mh, T, sc_st, sh_st, W.ln1_g, W.ln1_b, 1e-5f};
             EpiStd ep = mk_epi(qkv.p, 3 * C, 3 * C);
             CKI(gemm(st, mh, 3 * C, C, al, W.wqkv, 3 * C, ep));
@@ -1040,7 +1052,11 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             ep.ldr = C;
             CKI(gemm(st, Mc, C, C, mk_plain(ao.p + r0, C, Mc), W.wo2, C, ep));
         }
-        {   // GEGLU
+        if (mat) {   // GEGLU over the materialised LN3(x2)
+            CKI(ln_rows(x2, M, nullptr, nullptr, W.ln3_g, W.ln3_b, gnb));
+            EpiGeglu ep{ffb.p, FF, 2 * FF, W.bff1};
+            CKI(gemm(st, M, 2 * FF, C, mk_plain(gnb, C, M), W.wff1, 2 * FF, ep));
+        } else {
             ALoadLN al{x2, M, T, nullptr, nullptr, W.ln3_g, W.ln3_b, 1e-5f};
             EpiGeglu ep{ffb.p, FF, 2 * FF, W.bff1};
             CKI(gemm(st, M, 2 * FF, C, al, W.wff1, 2 * FF, ep));

@@ -490,10 +490,13 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                         }
                     }
                     const uint32_t lbase = a_lo(sl_x);
+                    float4 xs[LROWS];          // all shared loads first: the volatile asm statements keep program order
+#pragma unroll
+                    for (int i = 0; i < LROWS; ++i)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(xs[i].x), "=f"(xs[i].y), "=f"(xs[i].z), "=f"(xs[i].w) : "r"(abase + off[i]));
 #pragma unroll
                     for (int i = 0; i < LROWS; ++i) {
-                        float4 x;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(abase + off[i]));
+                        float4 x = xs[i];
                         float4 h;
                         if (!ident) {
                             x = al.xform(ctx[i], kc * BK + c * 4, x);

@@ -199,6 +199,55 @@ gn_fused_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, fl
     }
 }
 
+// LayerNorm(192) of every row, optionally preceded by a per-(sample, channel) affine (the SpatialTransformer's
+// GroupNorm folded in), materialised:  y = LN(x * ps + pb) * gamma + beta   (attention.py:170-191 norm1 / norm3).
+// The tcgen05 GEMMs whose output is wider than one tile (q/k/v: 3 tiles, GEGLU: 8 tiles) would otherwise redo this
+// transform in their operand producers once per output tile -- the producers, not the tensor pipe, bounded them.
+// 16 lanes per row (3 float4 each), two rows per warp; two-pass mean / variance in registers like ALoadLNT.
+__global__ void __launch_bounds__(256)
+ln192_rows_kernel(const float* __restrict__ x, int M, int T, const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ y) {
+    constexpr int C = 192;
+    const int row = (blockIdx.x * 256 + threadIdx.x) >> 4, l = threadIdx.x & 15;
+    const bool ok = row < M;
+    const int r = ok ? row : M - 1;
+    const float* xr = x + (long long)r * C;
+    float4 v[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[j] = ldg4(xr + (l + 16 * j) * 4);
+    if (pre_scale != nullptr) {
+        const int b = r / T;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 a = ldg4(pre_scale + (long long)b * C + (l + 16 * j) * 4), d = ldg4(pre_shift + (long long)b * C + (l + 16 * j) * 4);
+            v[j].x = v[j].x * a.x + d.x; v[j].y = v[j].y * a.y + d.y; v[j].z = v[j].z * a.z + d.z; v[j].w = v[j].w * a.w + d.w;
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float a = v[j].x - mean, b2 = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+        q += (a * a + b2 * b2) + (d * d + e * e);
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / C) + eps);
+    if (!ok) return;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int k = (l + 16 * j) * 4;
+        const float4 g = ldg4(gamma + k), bb = ldg4(beta + k);
+        st4(y + (long long)row * C + k, make_float4((v[j].x - mean) * rstd * g.x + bb.x, (v[j].y - mean) * rstd * g.y + bb.y,
+                                                    (v[j].z - mean) * rstd * g.z + bb.z, (v[j].w - mean) * rstd * g.w + bb.w));
+    }
+}
+
 // Row-wise LayerNorm (+ optional residual add before it):  y = LN(x [+ r]) * gamma + beta.
 // One warp per row; C % 128 == 0 not required, C % 4 == 0 and C <= 1024.
 // Used by the Wav2Vec2 post-LN encoder layers (TF modeling_wav2vec2.py:592-609).
