@@ -177,80 +177,67 @@ self_attention_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_of
 // projected once per clip ("K/V hoist") into kv: row (clip*T + t), K at column kv_off, V at
 // kv_off + 192, row stride kv_ld.  Unconditional samples (context = null embedding on every frame,
 // diffusion.py:397-400) see identical keys and values, so their output is the constant v_null.
-// One thread per (row, head); q rows for the conditional samples only: q[(b - n_uncond)*T + t].  For the
-// unconditional rows the kernel directly writes the block's next residual state (see below).
+// q rows exist for the conditional samples only: q[(b - n_uncond)*T + t].  For the unconditional rows the kernel
+// directly writes the block's next residual state (see below).
 // ------------------------------------------------------------------------------------------------
+// Eight lanes per (row, head): lane j owns dims 4j..4j+3, so every global access of a warp is one contiguous 512-byte
+// run (4 adjacent heads of a row) and all seven loads of a lane are independent; the three dot products are reduced
+// over the 8 lanes with shuffles.
 __global__ void __launch_bounds__(256)
 cross_attention3_kernel(const float* __restrict__ q, const float* __restrict__ kv, int kv_ld, int kv_off,
                         const float* __restrict__ c_null, const float* __restrict__ x_res, float* __restrict__ x_out,
                         int res_rows, int n_uncond, int Bp, int T, float scale, float* __restrict__ out) {
     constexpr int C = 192, HD = 32, H = 6;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)Bp * T * H) return;
-    const int h = (int)(idx % H);
-    const long long row = idx / H;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx = gid >> 3;                       // (row, head)
+    const int j = (int)(gid & 7);
+    const bool live = idx < (long long)Bp * T * H;        // dead lanes still take part in the shuffles
+    const long long ci = live ? idx : 0;
+    const int h = (int)(ci % H);
+    const long long row = ci / H;
     const int b = (int)(row / T), t = (int)(row - (long long)b * T);
-    float* o = out + row * C + h * HD;
-    if (b < n_uncond) {
-        // null-condition branch: attention output is the constant v_null for every query, so the whole
-        // "to_out(attn2) + x" step collapses to  x_out = x_res + c_null  with c_null = W_o v_null + b_o
-        const float* xr = x_res + (row % res_rows) * C + h * HD;   // x_res may hold only the shared (conditional) samples
-        float* xo = x_out + row * C + h * HD;
-#pragma unroll
-        for (int d = 0; d < HD; d += 4) {
-            const float4 a = ldg4(xr + d), c4 = ldg4(c_null + h * HD + d);
-            st4(xo + d, make_float4(a.x + c4.x, a.y + c4.y, a.z + c4.z, a.w + c4.w));
-        }
-        return;
+    const int col = h * HD + j * 4;
+    // null-condition branch: attention output is the constant v_null for every query, so the whole
+    // "to_out(attn2) + x" step collapses to  x_out = x_res + c_null  with c_null = W_o v_null + b_o.
+    // (No early return before the shuffles: they use the full-warp mask.)
+    const bool uncond = b < n_uncond;
+    const long long crow = uncond ? 0 : (long long)(b - n_uncond) * T + t;
+    float4 qv = zero4(), k0 = zero4(), k1 = zero4(), k2 = zero4(), v0 = zero4(), v1 = zero4(), v2 = zero4();
+    const bool has0 = t > 0, has2 = t < T - 1;
+    if (live && uncond) {
+        const float4 a = ldg4(x_res + (row % res_rows) * C + col), c4 = ldg4(c_null + col);   // x_res may hold only the shared samples
+        st4(x_out + row * C + col, make_float4(a.x + c4.x, a.y + c4.y, a.z + c4.z, a.w + c4.w));
+    } else if (live) {
+        const float* kr = kv + crow * kv_ld + kv_off + col;
+        qv = ldg4(q + crow * C + col);
+        k1 = ldg4(kr);
+        v1 = ldg4(kr + C);
+        if (has0) { k0 = ldg4(kr - kv_ld); v0 = ldg4(kr - kv_ld + C); }
+        if (has2) { k2 = ldg4(kr + kv_ld); v2 = ldg4(kr + kv_ld + C); }
     }
-    const long long crow = (long long)(b - n_uncond) * T + t;
-    float qv[HD];
+    float s0 = (qv.x * k0.x + qv.y * k0.y) + (qv.z * k0.z + qv.w * k0.w);
+    float s1 = (qv.x * k1.x + qv.y * k1.y) + (qv.z * k1.z + qv.w * k1.w);
+    float s2 = (qv.x * k2.x + qv.y * k2.y) + (qv.z * k2.z + qv.w * k2.w);
 #pragma unroll
-    for (int d = 0; d < HD; d += 4) {
-        const float4 x = ldg4(q + crow * C + h * HD + d);
-        qv[d] = x.x; qv[d + 1] = x.y; qv[d + 2] = x.z; qv[d + 3] = x.w;
+    for (int o = 1; o < 8; o <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    float s[3];
-#pragma unroll
-    for (int tap = 0; tap < 3; ++tap) {
-        const int tt = t + tap - 1;
-        float acc = 0.f;
-        if (tt >= 0 && tt < T) {
-            const float* kr = kv + (crow + tap - 1) * kv_ld + kv_off + h * HD;
-#pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 x = ldg4(kr + d);
-                acc = fmaf(qv[d], x.x, acc); acc = fmaf(qv[d + 1], x.y, acc);
-                acc = fmaf(qv[d + 2], x.z, acc); acc = fmaf(qv[d + 3], x.w, acc);
-            }
-            s[tap] = acc * scale;
-        } else {
-            s[tap] = -INFINITY;
-        }
-    }
-    const float m = fmaxf(s[0], fmaxf(s[1], s[2]));
-    float p[3], l = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 3; ++tap) { p[tap] = expf(s[tap] - m); l += p[tap]; }
-    const float inv = 1.0f / l;
-    float acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 3; ++tap) {
-        const int tt = t + tap - 1;
-        if (tt < 0 || tt >= T) continue;
-        const float w = p[tap] * inv;
-        const float* vr = kv + (crow + tap - 1) * kv_ld + kv_off + C + h * HD;
-#pragma unroll
-        for (int d = 0; d < HD; d += 4) {
-            const float4 x = ldg4(vr + d);
-            acc[d] = fmaf(w, x.x, acc[d]); acc[d + 1] = fmaf(w, x.y, acc[d + 1]);
-            acc[d + 2] = fmaf(w, x.z, acc[d + 2]); acc[d + 3] = fmaf(w, x.w, acc[d + 3]);
-        }
-    }
-#pragma unroll
-    for (int d = 0; d < HD; d += 4) st4(o + d, make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]));
+    if (!live || uncond) return;
+    s0 = has0 ? s0 * scale : -INFINITY;
+    s1 = s1 * scale;
+    s2 = has2 ? s2 * scale : -INFINITY;
+    const float m = fmaxf(s0, fmaxf(s1, s2));
+    const float p0 = expf(s0 - m), p1 = expf(s1 - m), p2 = expf(s2 - m);
+    const float inv = 1.0f / ((p0 + p1) + p2);
+    const float w0 = p0 * inv, w1 = p1 * inv, w2 = p2 * inv;
+    float4 acc;
+    acc.x = fmaf(w2, v2.x, fmaf(w1, v1.x, w0 * v0.x));
+    acc.y = fmaf(w2, v2.y, fmaf(w1, v1.y, w0 * v0.y));
+    acc.z = fmaf(w2, v2.z, fmaf(w1, v1.z, w0 * v0.z));
+    acc.w = fmaf(w2, v2.w, fmaf(w1, v1.w, w0 * v0.w));
+    st4(out + row * C + col, acc);
 }
 
 }  // namespace said

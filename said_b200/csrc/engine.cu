@@ -1038,7 +1038,7 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             CKI(gemm(st, Mc, C, C, al, W.wq2, C, ep));
         }
         {
-            const long long tot = (long long)M * HEADS;
+            const long long tot = (long long)M * HEADS * 8;   // 8 lanes per (row, head)
             cur_tag = TAG_XATTN;
             cross_attention3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q2.p, kv.p, 8 * C, i * 2 * C, cnull.p + i * C, x1, x2,
                                                                                   mh, n_uncond, Bp, T, att_scale, ao.p);
