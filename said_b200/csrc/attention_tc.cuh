@@ -22,8 +22,12 @@ namespace tc {
 static_assert(BK == 32 && ROW_BYTES == 128, "attention tiles assume 128-byte SWIZZLE_128B rows");
 constexpr int ATC_HD = 32;
 constexpr int ATC_MAXKEYS = 304;          // K and V^T hi/lo for the whole head must fit one SM's shared memory
-constexpr int ATC_SM_THREADS = 256;        // warps 0-7: staging / softmax / epilogue, two threads per query row
-constexpr int ATC_THREADS = ATC_SM_THREADS + 32;   // warp 8: MMA issuer
+constexpr int ATC_PARTS = 4;               // threads per query row: each owns 32 / ATC_PARTS columns of every 32-key chunk
+constexpr int ATC_CP = 32 / ATC_PARTS;     // (the softmax is instruction-latency bound: 16 warps hide what 8 could not)
+constexpr int ATC_SM_THREADS = 128 * ATC_PARTS;    // warps 0-15: staging / softmax / epilogue
+constexpr int ATC_MMA_WARP = ATC_SM_THREADS / 32;  // warp 16: MMA issuer
+constexpr int ATC_THREADS = ATC_SM_THREADS + 32;
+static_assert(ATC_CP == 8, "the softmax uses 8-column TMEM loads");
 constexpr int ATC_S_COL = 0;               // TMEM columns [0, Tk): scores
 constexpr int ATC_O_COL = 320;             // TMEM columns [320, 352): output accumulator
 
@@ -56,7 +60,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
     const uint32_t v_hi = (kv_end + 1023u) & ~1023u, v_lo = v_hi + (uint32_t)nch * 4096u;
     const uint32_t buf0 = v_lo + (uint32_t)nch * 4096u;          // operand buffer b: hi at bufb, lo at bufb + 16 KB
     const uint32_t buf1 = buf0 + 32768u;                         // buffer 1 also holds the Q tile for the S job
-    const uint32_t xch = buf1 + 32768u;                          // float[2][256]
+    const uint32_t xch = buf1 + 32768u;                          // float[2][ATC_SM_THREADS]
     const uint32_t bars = xch + 2u * ATC_SM_THREADS * 4u;
     const uint32_t bar_s_ready = bars, bar_s_done = bars + 8u;
     auto bar_p_ready = [&](int b) { return bars + 16u + 8u * b; };
@@ -77,7 +81,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
         fence_mbar_init();
     }
     __syncwarp();
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (warp == ATC_MMA_WARP) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -85,14 +89,15 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     const int n_qtiles = (T + 127) / 128;
 
-    if (warp < 8) {
+    if (warp < ATC_MMA_WARP) {
         // ---------------- stage K (rows = keys) and V^T (rows = dims), TF32 hi/lo ----------------
         // All global loads of a batch are issued before the first shared-memory store (the volatile stores would
         // otherwise serialise one load round trip per iteration: staging was ~1/3 of the CTA's lifetime).
-        float4 qreg[4];                                    // raw Q rows of the next query tile (prefetched)
+        constexpr int QR = 128 * 8 / ATC_SM_THREADS;       // float4 of a Q tile per thread
+        float4 qreg[QR];                                   // raw Q rows of the next query tile (prefetched)
         auto load_q = [&](int qt) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < QR; ++u) {
                 const int i = tid + u * ATC_SM_THREADS, r = i >> 3, c = i & 7;
                 qreg[u] = (qt * 128 + r < T) ? ldg4(gbase + (long long)(qt * 128 + r) * ld + q_off + c * 4) : zero4();
             }
@@ -140,14 +145,14 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(v_lo + off), "f"(ll.x), "f"(ll.y), "f"(ll.z), "f"(ll.w) : "memory");
             }
         }
-        const int row = tid & 127, half = tid >> 7;       // two threads per query row: column halves of every 32-key chunk
+        const int row = tid & 127, part = tid >> 7;       // ATC_PARTS threads per query row: column slices of every 32-key chunk
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const float sl2 = scale * 1.4426950408889634f;    // softmax in base 2: exp(x) = 2^(x log2 e)
         uint32_t s_jobs = 0, p_use[2] = {0u, 0u};
         for (int qt = 0; qt < n_qtiles; ++qt) {
             // ---------------- Q tile (into operand buffer 1) from the prefetched registers ----------------
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < QR; ++u) {
                 const int i = tid + u * ATC_SM_THREADS, r = i >> 3, c = i & 7;
                 const float4 x = qreg[u];
                 const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
@@ -162,53 +167,62 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
             mbar_wait(bar_s_done, s_jobs & 1u);
             ++s_jobs;
             tc_fence_after();
-            // ---------------- row max over the valid keys (each thread: every other 16-column group) ----------------
+            // ---------------- row max over the valid keys (each thread: its 8-column slice of every chunk) ----------------
             float mx = -INFINITY;
-            for (int j0 = half * 16; j0 < Tk; j0 += 64) {
-                float v[16], w[16];
-                const bool two = j0 + 32 < Tk;             // warp-uniform
-                tmem_ld16_issue(trow + ATC_S_COL + j0, v);
-                if (two) tmem_ld16_issue(trow + ATC_S_COL + j0 + 32, w);
-                tmem_ld_wait16(v);
-                if (two) tmem_ld_wait16(w);
+            for (int c0 = 0; c0 < nch; c0 += 4) {          // up to four TMEM loads in flight
+                float v[4][8];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    if (j0 + e < T) mx = fmaxf(mx, v[e]);
-                    if (two && j0 + 32 + e < T) mx = fmaxf(mx, w[e]);
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + u < nch) tmem_ld8_issue(trow + ATC_S_COL + (c0 + u) * 32 + part * ATC_CP, v[u]);   // warp-uniform
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + u < nch) tmem_ld_wait8(v[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (c0 + u < nch - 1) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[u][e]);
+                    } else if (c0 + u == nch - 1) {        // only the last chunk can hold padding keys
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if ((c0 + u) * 32 + part * ATC_CP + e < T) mx = fmaxf(mx, v[u][e]);
+                    }
                 }
             }
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)tid * 4u), "f"(mx) : "memory");
             named_bar_sync(1, ATC_SM_THREADS);
-            {
+#pragma unroll
+            for (int o = 1; o < ATC_PARTS; ++o) {
                 float other;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + (uint32_t)(tid ^ 128) * 4u));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + (uint32_t)((tid + 128 * o) & (ATC_SM_THREADS - 1)) * 4u));
                 mx = fmaxf(mx, other);
             }
             const float msl2 = mx * sl2;
             // ---------------- P chunks (ping-pong buffers) and O += P V ----------------
-            float lsum = 0.f;
+            float ls0 = 0.f, ls1 = 0.f;
             for (int ch = 0; ch < nch; ++ch) {
                 const int pb = ch & 1;
-                float p[16];
-                const int j0 = ch * 32 + half * 16;
-                if (j0 < Tk) {                             // warp-uniform
-                    float v[16];
-                    tmem_ld16(trow + ATC_S_COL + j0, v);
+                float p[8];
+                {
+                    float v[8];
+                    tmem_ld8_issue(trow + ATC_S_COL + ch * 32 + part * ATC_CP, v);
+                    tmem_ld_wait8(v);
+                    if (ch < nch - 1) {                    // warp-uniform: full chunks need no key mask
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        p[e] = (j0 + e < T) ? ex2_approx(v[e] * sl2 - msl2) : 0.f;
-                        lsum += p[e];
+                        for (int e = 0; e < 8; ++e) p[e] = ex2_approx(v[e] * sl2 - msl2);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) p[e] = (ch * 32 + part * ATC_CP + e < T) ? ex2_approx(v[e] * sl2 - msl2) : 0.f;
                     }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) p[e] = 0.f;
+                    ls0 += (p[0] + p[1]) + (p[2] + p[3]);
+                    ls1 += (p[4] + p[5]) + (p[6] + p[7]);
                 }
                 // the job that last read this buffer (chunk ch - 2, or the S job for buffer 1) must have completed
                 if (ch >= 2) mbar_wait(bar_p_done(pb), (p_use[pb] - 1u) & 1u);
                 const uint32_t pbase = (pb ? buf1 : buf0) + (uint32_t)row * 128u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t off = pbase + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4);
+                for (int c = 0; c < ATC_CP / 4; ++c) {
+                    const uint32_t off = pbase + (uint32_t)(((part * (ATC_CP / 4) + c) ^ (row & 7)) << 4);
                     float4 hh, ll;
                     tf32_split4(make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]), hh, ll);
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
@@ -219,26 +233,29 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 mbar_arrive(bar_p_ready(pb));             // job: O += P_ch V_ch
                 ++p_use[pb];
             }
+            float lsum = ls0 + ls1;
             // ---------------- wait for the last job on each buffer, then O / rowsum -> global ----------------
             mbar_wait(bar_p_done(0), (p_use[0] - 1u) & 1u);
             if (nch >= 2) mbar_wait(bar_p_done(1), (p_use[1] - 1u) & 1u);
             tc_fence_after();
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(ATC_SM_THREADS + tid) * 4u), "f"(lsum) : "memory");
             named_bar_sync(1, ATC_SM_THREADS);
-            {
+#pragma unroll
+            for (int o = 1; o < ATC_PARTS; ++o) {
                 float other;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + (uint32_t)(ATC_SM_THREADS + (tid ^ 128)) * 4u));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + (uint32_t)(ATC_SM_THREADS + ((tid + 128 * o) & (ATC_SM_THREADS - 1))) * 4u));
                 lsum += other;
             }
             {
-                float v[16];
-                tmem_ld16(trow + ATC_O_COL + half * 16, v);
+                float v[8];
+                tmem_ld8_issue(trow + ATC_O_COL + part * ATC_CP, v);
+                tmem_ld_wait8(v);
                 const int q = qt * 128 + row;
                 if (q < T) {
                     const float inv = 1.0f / lsum;
-                    float* orow = out + ((long long)b * T + q) * ldo + h * ATC_HD + half * 16;
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4) st4(orow + e, make_float4(v[e] * inv, v[e + 1] * inv, v[e + 2] * inv, v[e + 3] * inv));
+                    float* orow = out + ((long long)b * T + q) * ldo + h * ATC_HD + part * ATC_CP;
+                    st4(orow, make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv));
+                    st4(orow + 4, make_float4(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv));
                 }
             }
             tc_fence_before();                            // TMEM reads done before the next tile's MMAs overwrite S / O
@@ -291,7 +308,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == ATC_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

@@ -143,6 +143,19 @@ SAID_DEVINL void tmem_ld_wait16(float (&v)[16]) {
                  : "memory");
 }
 
+SAID_DEVINL void tmem_ld8_issue(uint32_t taddr, float (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+SAID_DEVINL void tmem_ld_wait8(float (&v)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
+                 :
+                 : "memory");
+}
+
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, rows of ROW_BYTES, hardware swizzle
 // matching the row width (SWIZZLE_64B for 64-byte rows, SWIZZLE_128B for 128-byte rows), 8-row groups
 // 8 * ROW_BYTES apart.
