@@ -29,13 +29,13 @@ constexpr int ATC_MMA_WARP = ATC_SM_THREADS / 32;  // warp 16: MMA issuer
 constexpr int ATC_THREADS = ATC_SM_THREADS + 32;
 static_assert(ATC_CP == 8, "the softmax uses 8-column TMEM loads");
 constexpr int ATC_S_COL = 0;               // TMEM columns [0, Tk): scores
-constexpr int ATC_O_COL = 320;             // TMEM columns [320, 352): output accumulator
+constexpr int ATC_O_COL = 320;             // TMEM columns [320, 384): output accumulators (P V_hi terms | P_hi V_lo term)
 
 inline size_t attention_tc_smem_bytes(int T) {
     const int Tk = (T + 15) / 16 * 16;
     const int nch = (T + 31) / 32;
     return (size_t)2 * Tk * 128            // K hi/lo
-           + (size_t)2 * nch * 32 * 128    // V^T hi/lo, one 32(d) x 32(keys) tile per key chunk
+           + (size_t)2 * nch * 32 * 128    // V^T [hi | lo], one 64(d hi, d lo) x 32(keys) tile per key chunk
            + (size_t)2 * 2 * 128 * 128     // two operand buffers (hi/lo): P chunk ping-pong; buffer 1 doubles as the Q tile
            + 2 * ATC_SM_THREADS * 4        // row max / row sum exchange
            + 1024 + 64;
@@ -57,8 +57,9 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t k_hi = base, k_lo = k_hi + (uint32_t)Tk * 128u;
     const uint32_t kv_end = k_lo + (uint32_t)Tk * 128u;
-    const uint32_t v_hi = (kv_end + 1023u) & ~1023u, v_lo = v_hi + (uint32_t)nch * 4096u;
-    const uint32_t buf0 = v_lo + (uint32_t)nch * 4096u;          // operand buffer b: hi at bufb, lo at bufb + 16 KB
+    // V^T: per 32-key chunk one 64-row operand [hi dims 0..31 | lo dims 0..31] (8 KB), so P_hi * [V_hi | V_lo] is ONE N = 64 MMA
+    const uint32_t v_hi = (kv_end + 1023u) & ~1023u, v_lo = v_hi + 4096u;
+    const uint32_t buf0 = v_hi + (uint32_t)nch * 8192u;          // operand buffer b: hi at bufb, lo at bufb + 16 KB
     const uint32_t buf1 = buf0 + 32768u;                         // buffer 1 also holds the Q tile for the S job
     const uint32_t xch = buf1 + 32768u;                          // float[2][ATC_SM_THREADS]
     const uint32_t bars = xch + 2u * ATC_SM_THREADS * 4u;
@@ -138,7 +139,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int dd = c4 * 4 + e;
-                const uint32_t off = (uint32_t)chunk * 4096u + (uint32_t)dd * 128u + (uint32_t)((kq ^ (dd & 7)) << 4);
+                const uint32_t off = (uint32_t)chunk * 8192u + (uint32_t)dd * 128u + (uint32_t)((kq ^ (dd & 7)) << 4);
                 float4 hh, ll;
                 tf32_split4(make_float4(xv[e][0], xv[e][1], xv[e][2], xv[e][3]), hh, ll);
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(v_hi + off), "f"(hh.x), "f"(hh.y), "f"(hh.z), "f"(hh.w) : "memory");
@@ -247,9 +248,13 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 lsum += other;
             }
             {
-                float v[8];
+                float v[8], w[8];
                 tmem_ld8_issue(trow + ATC_O_COL + part * ATC_CP, v);
+                tmem_ld8_issue(trow + ATC_O_COL + ATC_HD + part * ATC_CP, w);
                 tmem_ld_wait8(v);
+                tmem_ld_wait8(w);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += w[e];
                 const int q = qt * 128 + row;
                 if (q < T) {
                     const float inv = 1.0f / lsum;
@@ -264,7 +269,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
         // ---------------- MMA issuer ----------------
         uint32_t s_jobs = 0, p_cnt[2] = {0u, 0u};
         const int n1 = Tk > 256 ? 256 : Tk, n2 = Tk - n1;
-        const uint32_t id1 = make_idesc_tf32(128, n1), id2 = make_idesc_tf32(128, n2 > 0 ? n2 : 16), idv = make_idesc_tf32(128, ATC_HD);
+        const uint32_t id1 = make_idesc_tf32(128, n1), id2 = make_idesc_tf32(128, n2 > 0 ? n2 : 16), idv = make_idesc_tf32(128, ATC_HD), idv2 = make_idesc_tf32(128, 2 * ATC_HD);
         const uint64_t dqh = make_desc(buf1), dql = make_desc(buf1 + 16384u);
         const uint64_t dkh = make_desc(k_hi), dkl = make_desc(k_lo);
         const uint64_t dkh2 = make_desc(k_hi + 256u * 128u), dkl2 = make_desc(k_lo + 256u * 128u);
@@ -293,13 +298,14 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 tc_fence_after();
                 const uint32_t pa = pb ? buf1 : buf0;
                 const uint64_t dph = make_desc(pa), dpl = make_desc(pa + 16384u);
-                const uint64_t dvh = make_desc(v_hi + (uint32_t)ch * 4096u), dvl = make_desc(v_lo + (uint32_t)ch * 4096u);
+                // O[:, 0:32] += P_hi V_hi + P_lo V_hi,  O[:, 32:64] += P_hi V_lo  (summed in the epilogue): two MMAs per
+                // k-step instead of three -- these N = 32 MMAs are bound by the issuing thread, not by the tensor pipe
+                const uint64_t dvh = make_desc(v_hi + (uint32_t)ch * 8192u);
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     const uint64_t adv = (uint64_t)(k4 * 2);
-                    mma_tf32(tmem_base + ATC_O_COL, dph + adv, dvh + adv, idv, (ch | k4) != 0 ? 1u : 0u);
+                    mma_tf32(tmem_base + ATC_O_COL, dph + adv, dvh + adv, idv2, (ch | k4) != 0 ? 1u : 0u);
                     mma_tf32(tmem_base + ATC_O_COL, dpl + adv, dvh + adv, idv, 1u);
-                    mma_tf32(tmem_base + ATC_O_COL, dph + adv, dvl + adv, idv, 1u);
                 }
                 mma_commit(bar_p_done(pb));
             }
