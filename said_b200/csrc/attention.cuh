@@ -39,6 +39,8 @@ self_attention_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_of
     float* Vs = Kt + (size_t)HD * ATT_KSTR;         // [KB][HD]
     float* Qt = Vs + (size_t)ATT_KB * HD;           // [HD][64]
     float* Ps = Qt + (size_t)HD * ATT_QTILE;        // [8 warps][KB][PSTR]
+    pdl_wait();
+    pdl_trigger();
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q0 = blockIdx.x * ATT_QTILE, h = blockIdx.y, b = blockIdx.z;
@@ -188,6 +190,8 @@ cross_attention3_kernel(const float* __restrict__ q, const float* __restrict__ k
                         const float* __restrict__ c_null, const float* __restrict__ x_res, float* __restrict__ x_out,
                         int res_rows, int n_uncond, int Bp, int T, float scale, float* __restrict__ out) {
     constexpr int C = 192, HD = 32, H = 6;
+    pdl_wait();
+    pdl_trigger();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long idx = gid >> 3;                       // (row, head)
     const int j = (int)(gid & 7);

@@ -88,6 +88,8 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();      // barrier init and the TMEM allocation above overlap the previous kernel's tail
+    pdl_trigger();
     const int n_qtiles = (T + 127) / 128;
 
     if (warp < ATC_MMA_WARP) {

@@ -15,6 +15,42 @@ SAID_DEVINL float4 ldg4_l2pf(const float* p) {
     asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has completed
+// and its memory operations are visible, so everything a kernel does BEFORE it (barrier init, TMEM allocation, constant
+// weight prefetch) overlaps the predecessor's tail.  Every kernel of the step loop waits before it touches an activation
+// buffer (read or write), which makes the ordering transitive; pdl_trigger() after the wait lets the next kernel in.
+// Both are no-ops for a kernel launched without the attribute.
+// MEASURED (profiles/r1_pdl.md): inside the per-step CUDA graph PDL is a net loss on this path (batch 64: 4.08 vs 4.03 ms
+// per step; single clip: 0.95 vs 0.82 ms, 1.29 ms with the trigger before the wait), so it is OFF unless SAID_PDL=1.
+SAID_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SAID_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Launch with an optional PDL attribute and an optional cluster width (x dimension).
+template <class... KA, class... A>
+inline cudaError_t launch_ex(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, int cluster_x, A&&... args) {
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    unsigned n = 0;
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster_x;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
 SAID_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 SAID_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 SAID_DEVINL float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }

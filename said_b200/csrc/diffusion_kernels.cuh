@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(256)
 ddim_step_kernel(StepParams p) {
     __shared__ double red[4][8];
     __shared__ float s_ratio;
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.x, tid = threadIdx.x;
     const int step = *p.step_ptr;
     const float* row = p.table + (long long)step * 8;
@@ -188,6 +190,10 @@ __global__ void finalize_kernel(const float* __restrict__ latents, float latent_
 }
 
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
-__global__ void add_int_kernel(int* p, int v) { *p += v; }
+__global__ void add_int_kernel(int* p, int v) {
+    pdl_wait();
+    pdl_trigger();
+    *p += v;
+}
 
 }  // namespace said

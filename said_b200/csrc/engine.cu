@@ -98,6 +98,7 @@ struct EncLayerW {
 struct said_engine {
     int device = 0;
     int num_sms = 0;
+    bool pdl = getenv("SAID_PDL") != nullptr;   // programmatic dependent launch for the step-loop kernels: measured slower, opt-in (common.cuh)
     bool gn_fused = getenv("SAID_GN_TWO_PASS") == nullptr;   // cluster GroupNorm (one launch); the env switch keeps the two-kernel version reachable for A/B timing
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -154,14 +155,14 @@ struct said_engine {
             }
         } else if (w.bn == 128) {
             if constexpr (std::is_same<AL, ALoadPlain>::value && std::is_same<EP, EpiStd>::value)   // encoder conv stack (N = 512)
-                e = precision == 1 ? tc::launch_gemm_tc<128, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
-                                   : tc::launch_gemm_tc<128, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
+                e = precision == 1 ? tc::launch_gemm_tc<128, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
+                                   : tc::launch_gemm_tc<128, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
         } else if (w.bn == 192) {
-            e = precision == 1 ? tc::launch_gemm_tc<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
-                               : tc::launch_gemm_tc<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
+            e = precision == 1 ? tc::launch_gemm_tc<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
+                               : tc::launch_gemm_tc<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
         } else if (w.bn == 32) {
-            e = precision == 1 ? tc::launch_gemm_tc<32, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
-                               : tc::launch_gemm_tc<32, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
+            e = precision == 1 ? tc::launch_gemm_tc<32, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
+                               : tc::launch_gemm_tc<32, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
         }
         if (e != cudaSuccess) return fail(std::string("tcgen05 gemm launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
@@ -178,7 +179,7 @@ struct said_engine {
             if (it != tcmap.end() && it->second.K == K && it->second.N == N)
                 return gemm_tc_dispatch(st, M, N, K, to_tc_loader(al), it->second, ep);
         }
-        cudaError_t e = launch_gemm(st, M, N, K, al, Wt, ldw, ep, batch, wz_mod, w_zstride);
+        cudaError_t e = launch_gemm(st, M, N, K, al, Wt, ldw, ep, batch, wz_mod, w_zstride, pdl);
         if (e != cudaSuccess) return fail(std::string("gemm launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
     }
@@ -907,31 +908,20 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
             const int cl = nb * GN_SPLIT >= num_sms ? GN_SPLIT : 8;
             const int rows = (T + cl - 1) / cl;
             if (gn_fused && (rows + 7) / 8 <= GNF_MAXR) {
-                cudaLaunchConfig_t cfg;
-                memset(&cfg, 0, sizeof(cfg));
-                cfg.gridDim = dim3(cl, nb);
-                cfg.blockDim = dim3(GNF_THREADS);
-                cfg.stream = st;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = cl;
-                at[0].val.clusterDim.y = 1;
-                at[0].val.clusterDim.z = 1;
-                cfg.attrs = at;
-                cfg.numAttrs = 1;
                 cur_tag = TAG_GN;
-                CK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, src, src_nb, T, cpg, eps_, g, b, osc, osh, ld, off, act_out, act_ld, act_off));
+                CK(launch_ex(gn_fused_kernel, dim3(cl, nb), dim3(GNF_THREADS), 0, st, pdl, cl, src, src_nb, T, cpg, eps_, g, b, osc, osh, ld, off,
+                             act_out, act_ld, act_off));
                 LAUNCH_CHECK();
                 return 0;
             }
         }
         const int nsp = nb * GN_SPLIT >= num_sms ? GN_SPLIT : GN_SPLIT_MAX;   // few samples: more CTAs each
         cur_tag = TAG_GN;
-        gn_partial_kernel<<<dim3(nsp, nb), GN_THREADS, 0, st>>>(src, src_nb, T, gn_partial);
+        CK(launch_ex(gn_partial_kernel, dim3(nsp, nb), dim3(GN_THREADS), 0, st, pdl, 1, src, src_nb, T, gn_partial));
         LAUNCH_CHECK();
         cur_tag = TAG_GN;
-        gn_finish_kernel<<<dim3(act_out ? nsp : 1, nb), GN_THREADS, 0, st>>>(src, src_nb, T, cpg, eps_, gn_partial, nsp, g, b, osc, osh,
-                                                                             ld, off, act_out, act_ld, act_off);
+        CK(launch_ex(gn_finish_kernel, dim3(act_out ? nsp : 1, nb), dim3(GN_THREADS), 0, st, pdl, 1, src, src_nb, T, cpg, eps_,
+                     (const double*)gn_partial, nsp, g, b, osc, osh, ld, off, act_out, act_ld, act_off));
         LAUNCH_CHECK();
         return 0;
     };
@@ -997,7 +987,7 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         // free inside the transformer block) so the GEMM's producers run the plain copy path
         auto ln_rows = [&](const float* src, int m, const float* ps, const float* pb, const float* g, const float* b, float* dst) -> int {
             cur_tag = TAG_GN;
-            ln192_rows_kernel<<<(unsigned)(((long long)m * 16 + 255) / 256), 256, 0, st>>>(src, m, T, ps, pb, g, b, 1e-5f, dst);
+            CK(launch_ex(ln192_rows_kernel, dim3((unsigned)(((long long)m * 16 + 255) / 256)), dim3(256), 0, st, pdl, 1, src, m, T, ps, pb, g, b, 1e-5f, dst));
             LAUNCH_CHECK();
             return 0;
         };
@@ -1012,11 +1002,11 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         }
         cur_tag = TAG_ATTN;
         if (mat && T <= tc::ATC_MAXKEYS) {
-            tc::self_attention_tc_kernel<<<dim3(HEADS, h_nb), tc::ATC_THREADS, tc::attention_tc_smem_bytes(T), st>>>(
-                qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
+            CK(launch_ex(tc::self_attention_tc_kernel, dim3(HEADS, h_nb), dim3(tc::ATC_THREADS), tc::attention_tc_smem_bytes(T), st, pdl, 1,
+                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C));
         } else {
-            self_attention_kernel<32><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, h_nb), ATT_THREADS,
-                                        attention_smem_bytes<32>(), st>>>(qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C);
+            CK(launch_ex(self_attention_kernel<32>, dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, h_nb), dim3(ATT_THREADS),
+                         attention_smem_bytes<32>(), st, pdl, 1, (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C));
         }
         LAUNCH_CHECK();
         {   // x1 = to_out(attn) + GN(h)
@@ -1040,8 +1030,9 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         {
             const long long tot = (long long)M * HEADS * 8;   // 8 lanes per (row, head)
             cur_tag = TAG_XATTN;
-            cross_attention3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q2.p, kv.p, 8 * C, i * 2 * C, cnull.p + i * C, x1, x2,
-                                                                                  mh, n_uncond, Bp, T, att_scale, ao.p);
+            CK(launch_ex(cross_attention3_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, pdl, 1, (const float*)q2.p,
+                         (const float*)kv.p, 8 * C, i * 2 * C, (const float*)(cnull.p + i * C), (const float*)x1, x2, mh, n_uncond, Bp, T,
+                         att_scale, ao.p));
             LAUNCH_CHECK();
         }
         if (Mc > 0) {   // x2 = to_out(attn2) + x1 on the conditional rows (the kernel above wrote the unconditional ones)
@@ -1180,9 +1171,9 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         auto one_step = [&]() -> int {
             CKI(forward(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
             cur_tag = TAG_STEP;
-            ddim_step_kernel<<<dim3(B, DDIM_SPLIT), 256, 0, st>>>(sp);
+            CK(launch_ex(ddim_step_kernel, dim3(B, DDIM_SPLIT), dim3(256), 0, st, pdl, 1, sp));
             LAUNCH_CHECK();
-            add_int_kernel<<<1, 1, 0, st>>>(step_ctr, 1);
+            CK(launch_ex(add_int_kernel, dim3(1), dim3(1), 0, st, pdl, 1, step_ctr, 1));
             LAUNCH_CHECK();
             return 0;
         };

@@ -522,6 +522,8 @@ gemm_simt_kernel(GemmDims d, AL al, const float* __restrict__ Wt, EP ep) {
     constexpr int NB = (B_SLOTS + GEMM_THREADS - 1) / GEMM_THREADS;
     __shared__ __align__(16) float As[BKT][ASTR];
     __shared__ __align__(16) float Bs[BKT][BN];
+    pdl_wait();
+    pdl_trigger();
 
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * BM;
@@ -650,20 +652,19 @@ struct RebindLanes<LPR, ALoadLNT<L0>> {
 // single clip still spreads over the SMs).
 template <class AL, class EP>
 inline cudaError_t launch_gemm(cudaStream_t st, int M, int N, int K, const AL& al, const float* Wt, int ldw,
-                               const EP& ep, int batch = 1, int wz_mod = 1, long long w_zstride = 0) {
+                               const EP& ep, int batch = 1, int wz_mod = 1, long long w_zstride = 0, bool pdl = false) {
     if (M <= 0 || batch <= 0) return cudaSuccess;
     GemmDims d{M, N, K, ldw, wz_mod, w_zstride};
     const long long big_ctas = (long long)((M + 127) / 128) * ((N + 63) / 64) * batch;
     if (big_ctas >= 120 || K % 32 != 0) {
         using R = RebindLanes<4, AL>;
         dim3 grid((M + 127) / 128, (N + 63) / 64, batch);
-        gemm_simt_kernel<128, 64, 8, 4, 16, typename R::type, EP><<<grid, GEMM_THREADS, 0, st>>>(d, R::conv(al), Wt, ep);
+        return launch_ex(gemm_simt_kernel<128, 64, 8, 4, 16, typename R::type, EP>, grid, dim3(GEMM_THREADS), 0, st, pdl, 1, d, R::conv(al), Wt, ep);
     } else {
         using R = RebindLanes<8, AL>;
         dim3 grid((M + 31) / 32, (N + 31) / 32, batch);
-        gemm_simt_kernel<32, 32, 2, 2, 32, typename R::type, EP><<<grid, GEMM_THREADS, 0, st>>>(d, R::conv(al), Wt, ep);
+        return launch_ex(gemm_simt_kernel<32, 32, 2, 2, 32, typename R::type, EP>, grid, dim3(GEMM_THREADS), 0, st, pdl, 1, d, R::conv(al), Wt, ep);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace said

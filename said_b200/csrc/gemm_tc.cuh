@@ -297,6 +297,10 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // PDL: everything above overlapped the previous kernel's tail.  The weight-copy warp does not wait at all (weights
+    // are constants), so the B ring is already full when the activations become available.
+    if (warp != EPI_WARPS + 1) pdl_wait();
+    pdl_trigger();
 
     if (warp < EPI_WARPS) {
         // ===================== epilogue =====================
@@ -892,7 +896,7 @@ inline void pack_weights_tc(const float* Wt, int K, int N, int ldw, int BN, int 
 
 template <int BN, int NSPLIT, class AL, class EP>
 inline cudaError_t launch_gemm_tc(cudaStream_t st, int num_sms, int M, int N, int K, const AL& al, const float* Wp,
-                                  int w_block_floats, const EP& ep, int dbg = 0) {
+                                  int w_block_floats, const EP& ep, int dbg = 0, bool pdl = false) {
     using Cfg = TcCfg<BN, NSPLIT>;
     static bool configured = false;
     auto kern = gemm_tc_kernel<BN, NSPLIT, AL, EP>;
@@ -904,8 +908,7 @@ inline cudaError_t launch_gemm_tc(cudaStream_t st, int num_sms, int M, int N, in
     TcDims d{M, N, K, w_block_floats, dbg};
     const int total_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    kern<<<grid, THREADS2, Cfg::SMEM_BYTES, st>>>(d, al, Wp, ep);
-    return cudaGetLastError();
+    return launch_ex(kern, dim3(grid), dim3(THREADS2), Cfg::SMEM_BYTES, st, pdl, 1, d, al, Wp, ep);
 }
 
 }  // namespace tc

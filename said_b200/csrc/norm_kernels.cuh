@@ -25,6 +25,8 @@ gn_partial_kernel(const float* __restrict__ x, int src_samples, int T, double* _
     constexpr int C = 192;
     __shared__ double s_sum[4][C];
     __shared__ double s_sq[4][C];
+    pdl_wait();
+    pdl_trigger();
     const int sp = blockIdx.x, b = blockIdx.y;
     const int c = threadIdx.x % C, ph = threadIdx.x / C;
     const int nsp = gridDim.x;
@@ -61,6 +63,8 @@ gn_finish_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, f
     constexpr int C = 192;
     __shared__ double s_sum[C], s_sq[C];
     __shared__ float s_mean[32], s_rstd[32];
+    pdl_wait();
+    pdl_trigger();
     const int sp = blockIdx.x, b = blockIdx.y;
     const int c = threadIdx.x % C, ph = threadIdx.x / C;
     if (threadIdx.x < C) {
@@ -123,6 +127,8 @@ gn_fused_kernel(const float* __restrict__ x, int src_samples, int T, int cpg, fl
     __shared__ double s_part[2][32];     // this CTA's per-group sum / sum of squares (read by the whole cluster)
     __shared__ float s_mean[32], s_rstd[32];
     cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    pdl_wait();
+    pdl_trigger();
     const int nsp = (int)cluster.num_blocks(), sp = (int)cluster.block_rank(), b = blockIdx.y;
     const int q = threadIdx.x % Q, ph = threadIdx.x / Q;
     const int rows = (T + nsp - 1) / nsp;
@@ -208,6 +214,8 @@ __global__ void __launch_bounds__(256)
 ln192_rows_kernel(const float* __restrict__ x, int M, int T, const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ y) {
     constexpr int C = 192;
+    pdl_wait();
+    pdl_trigger();
     const int row = (blockIdx.x * 256 + threadIdx.x) >> 4, l = threadIdx.x & 15;
     const bool ok = row < M;
     const int r = ok ? row : M - 1;
