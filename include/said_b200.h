@@ -83,6 +83,9 @@ typedef struct said_denoise_args {
     float* result_dev;              /* (B,T,C): clamp(latents/latent_scale, 0, 1) */
     float* latents_out_dev;         /* (B,T,C) or NULL: final latents before the clamp */
     int use_graph;                  /* replay one captured CUDA graph per step */
+    int scheduler;                  /* 0 DDIMScheduler.step; 1 DDPMScheduler.step (ancestral sampling, reference diffusion.py:55,404:
+                                       table slots 2..4 then hold pred_original_sample_coeff, current_sample_coeff, sqrt(variance)
+                                       and eta_noise_dev the per-step variance noise) */
 } said_denoise_args;
 SAID_API int said_denoise(said_engine* e, const said_denoise_args* args, void* stream);
 
@@ -97,7 +100,7 @@ SAID_API int said_denoiser_forward(said_engine* e, const float* x_dev, const flo
 /* Unit entry points used by the parity tests (each is one kernel of the path). */
 SAID_API int said_op_ddim_step(said_engine* e, const float* pred_dev, float* latents_dev, int B, int n, int do_cfg,
                       float guidance_scale, float guidance_rescale, int prediction_type, const float* row8_host,
-                      const float* eta_noise_dev, void* stream);
+                      const float* eta_noise_dev, int scheduler, void* stream);
 SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, int heads, int head_dim,
                            float* out_dev, void* stream);
 

@@ -103,6 +103,51 @@ def ddim_step(
     return prev
 
 
+def ddpm_step(
+    model_output: torch.Tensor,
+    t: int,
+    sample: torch.Tensor,
+    alphas_cumprod: torch.Tensor,
+    num_inference_steps: int,
+    prediction_type: str = "epsilon",
+    variance_noise: Optional[torch.Tensor] = None,
+    num_train_timesteps: int = 1000,
+    clip_sample: bool = True,
+    clip_sample_range: float = 1.0,
+) -> torch.Tensor:
+    """One ``DDPMScheduler.step(...).prev_sample`` (diffusers 0.19 ``scheduling_ddpm.py``, ``variance_type="fixed_small"``):
+    the scheduler the reference gets when constructed with ``noise_scheduler=DDPMScheduler`` (``said/model/diffusion.py:55``).
+    Third-party arithmetic restated from the published source: parity unpinned, like ``ddim_step``."""
+    t = int(t)
+    t_prev = t - num_train_timesteps // num_inference_steps
+    ac = alphas_cumprod.to(sample.dtype) if sample.dtype == torch.float64 else alphas_cumprod
+    a = ac[t]
+    a_prev = ac[t_prev] if t_prev >= 0 else torch.tensor(1.0, dtype=ac.dtype)
+    b = 1 - a
+    b_prev = 1 - a_prev
+    cur_a = a / a_prev
+    cur_b = 1 - cur_a
+    if prediction_type == "epsilon":
+        x0 = (sample - b**0.5 * model_output) / a**0.5
+    elif prediction_type == "sample":
+        x0 = model_output
+    elif prediction_type == "v_prediction":
+        x0 = (a**0.5) * sample - (b**0.5) * model_output
+    else:
+        raise ValueError(prediction_type)
+    if clip_sample:
+        x0 = x0.clamp(-clip_sample_range, clip_sample_range)
+    c0 = (a_prev**0.5 * cur_b) / b
+    c1 = cur_a**0.5 * b_prev / b
+    prev = c0 * x0 + c1 * sample
+    if t > 0:
+        if variance_noise is None:
+            variance_noise = torch.randn(model_output.shape, dtype=model_output.dtype)
+        variance = torch.clamp((1 - a_prev) / (1 - a) * cur_b, min=1e-20)
+        prev = prev + (variance**0.5) * variance_noise
+    return prev
+
+
 def ddim_add_noise(x: torch.Tensor, noise: torch.Tensor, t, alphas_cumprod: torch.Tensor) -> torch.Tensor:
     ac = alphas_cumprod.to(dtype=x.dtype)
     t = torch.as_tensor(t, dtype=torch.long).reshape(-1)
@@ -360,6 +405,7 @@ def inference(
     teacher_latents: Optional[List[torch.Tensor]] = None,
     return_preclamp: bool = False,
     step_limit: Optional[int] = None,
+    scheduler: str = "ddim",
 ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """``SAID.inference`` restated.  ``noise`` replaces the single ``torch.randn`` draw of
     ``diffusion.py:364`` (generation) or ``:270`` (editing) so that the CUDA path can be fed the very same
@@ -409,10 +455,14 @@ def inference(
             pred = c + guidance_scale * (c - u)
             if guidance_rescale > 0.0:
                 pred = rescale_noise_cfg(pred, c, guidance_rescale)
-        latents = ddim_step(
-            pred, int(t), latents, ac, num_inference_steps, prediction_type, eta,
-            variance_noise=None if eta_noise is None else eta_noise[idx].to(dt),
-        )
+        if scheduler == "ddpm":   # eta_noise then holds DDPMScheduler's per-step variance noise (row unused at t = 0)
+            latents = ddpm_step(pred, int(t), latents, ac, num_inference_steps, prediction_type,
+                                variance_noise=None if eta_noise is None else eta_noise[idx].to(dt))
+        else:
+            latents = ddim_step(
+                pred, int(t), latents, ac, num_inference_steps, prediction_type, eta,
+                variance_noise=None if eta_noise is None else eta_noise[idx].to(dt),
+            )
         if init_samples is not None and mask is not None:
             noisy = init_latents
             nxt = t_start + idx + 1

@@ -65,6 +65,7 @@ class DenoiseArgs(ctypes.Structure):
         ("result_dev", ctypes.c_void_p),
         ("latents_out_dev", ctypes.c_void_p),
         ("use_graph", ctypes.c_int),
+        ("scheduler", ctypes.c_int),
     ]
 
 
@@ -101,7 +102,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_prepare_context.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.said_denoise.argtypes = [vp, ctypes.POINTER(DenoiseArgs), vp]
     lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp]
-    lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, vp]
+    lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, ci, vp]
     lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
     lib.said_op_self_attention_tc.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.said_launch_count.argtypes = [vp]
@@ -231,6 +232,7 @@ class Engine:
         intermediates: Optional[torch.Tensor] = None,
         latents_out: Optional[torch.Tensor] = None,
         use_graph: bool = True,
+        scheduler: int = 0,
     ) -> torch.Tensor:
         init_src = _check_dev(init_src, self.device, "initial latents")
         B, T, C = init_src.shape
@@ -255,7 +257,7 @@ class Engine:
             edit_noise_dev=_ptr(opt["edit_noise"]), edit_sqrt_a=float(edit_coefs[0]), edit_sqrt_b=float(edit_coefs[1]),
             mask_dev=_ptr(opt["mask"]), eta_noise_dev=_ptr(opt["eta_noise"]),
             intermediates_dev=_ptr(intermediates), result_dev=result.data_ptr(),
-            latents_out_dev=_ptr(latents_out), use_graph=int(bool(use_graph)),
+            latents_out_dev=_ptr(latents_out), use_graph=int(bool(use_graph)), scheduler=int(scheduler),
         )
         with torch.cuda.device(self.device):
             self._call(self.lib.said_denoise(self._h, ctypes.byref(a), self._stream()))
@@ -285,7 +287,7 @@ class Engine:
         return (out, tap_buf) if taps else out
 
     # ------------------------------------------------------------------ unit ops (tests)
-    def op_ddim_step(self, pred, latents, do_cfg, guidance_scale, guidance_rescale, prediction_type, row8, eta_noise=None):
+    def op_ddim_step(self, pred, latents, do_cfg, guidance_scale, guidance_rescale, prediction_type, row8, eta_noise=None, scheduler=0):
         pred = _check_dev(pred, self.device, "pred")
         latents = _check_dev(latents, self.device, "latents").clone()
         B = latents.shape[0]
@@ -295,7 +297,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self._call(self.lib.said_op_ddim_step(self._h, pred.data_ptr(), latents.data_ptr(), B, n, int(do_cfg),
                                                   float(guidance_scale), float(guidance_rescale), int(prediction_type),
-                                                  row.ctypes.data, _ptr(en), self._stream()))
+                                                  row.ctypes.data, _ptr(en), int(scheduler), self._stream()))
             torch.cuda.synchronize(self.device)
         return latents
 

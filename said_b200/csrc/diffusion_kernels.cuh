@@ -85,6 +85,7 @@ struct StepParams {
     float* intermediates;       // (n_steps, B, n) or null: latents / latent_scale before the step
     float latent_scale;
     float* result;              // (B, n): clamp(latents / latent_scale, 0, 1), written on the last step
+    int scheduler;              // 0: DDIMScheduler.step, 1: DDPMScheduler.step (ancestral; table row holds c0, c1, std)
 };
 
 constexpr int DDIM_SPLIT = 8;
@@ -156,7 +157,9 @@ ddim_step_kernel(StepParams p) {
             eps = __fadd_rn(__fmul_rn(sa, e), __fmul_rn(sb, x));
         }
         if (clip >= 0.f) x0 = fminf(fmaxf(x0, -clip), clip);
-        float prev = __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(dir, eps));
+        // DDIM: sqrt(a_prev) x0 + dir eps.  DDPM (scheduling_ddpm.py step): pred_original_sample_coeff x0 + current_sample_coeff x,
+        // the two coefficients arriving in the same table slots; the variance noise term below is shared (sigma = std, 0 at t = 0).
+        float prev = p.scheduler == 1 ? __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(dir, x)) : __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(dir, eps));
         if (p.eta_noise) prev = __fadd_rn(prev, __fmul_rn(sigma, p.eta_noise[soff + i]));
         if (p.mask) {
             const long long bi = (long long)b * p.n + i;

@@ -1117,6 +1117,7 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
 int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
     if (!ready) return fail("weights not committed");
     if (a.B <= 0 || a.T <= 0 || a.n_steps < 0) return fail("denoise: bad sizes");
+    if (a.scheduler != 0 && a.scheduler != 1) return fail("denoise: scheduler must be 0 (DDIM) or 1 (DDPM)");
     if (ctx_B != a.B || ctx_T != a.T || ctx_uncond != (a.do_cfg ? 1 : 0))
         return fail("denoise: said_prepare_context was not called for this (B, T, cfg)");
     const int B = a.B, T = a.T, Bp = a.do_cfg ? 2 * B : B;
@@ -1160,6 +1161,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         sp.step_ptr = step_ctr;
         sp.n_steps = a.n_steps;
         sp.eta_noise = a.eta_noise_dev;
+        sp.scheduler = a.scheduler;
         sp.init_latents = init_lat.p;
         sp.edit_noise = a.edit_noise_dev;
         sp.mask = a.mask_dev;
@@ -1311,8 +1313,9 @@ int said_denoiser_forward(said_engine* e, const float* x_dev, const float* times
 
 int said_op_ddim_step(said_engine* e, const float* pred_dev, float* latents_dev, int B, int n, int do_cfg,
                       float guidance_scale, float guidance_rescale, int prediction_type, const float* row8_host,
-                      const float* eta_noise_dev, void* stream) {
+                      const float* eta_noise_dev, int scheduler, void* stream) {
     if (!e) return fail("null engine");
+    if (scheduler != 0 && scheduler != 1) return fail("said_op_ddim_step: scheduler must be 0 (DDIM) or 1 (DDPM)");
     CK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
     CK(e->step_tab.ensure(8));
@@ -1333,6 +1336,7 @@ int said_op_ddim_step(said_engine* e, const float* pred_dev, float* latents_dev,
     sp.table = e->step_tab.p;
     sp.step_ptr = e->step_ctr;
     sp.n_steps = 2;   // never "last": no result write
+    sp.scheduler = scheduler;
     sp.eta_noise = eta_noise_dev;
     sp.latent_scale = 1.0f;
     ddim_step_kernel<<<dim3(B, DDIM_SPLIT), 256, 0, st>>>(sp);

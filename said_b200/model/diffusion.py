@@ -171,6 +171,7 @@ class SAID(ABC, nn.Module):
         self._engines: Dict[int, Engine] = {}
         self._engine_keys: Dict[int, tuple] = {}
         self.use_cuda_graph = True
+        self.dedup_audio = True           # a batch that repeats one clip (script/test_inference.py:167) is encoded once
         # contraction precision of the denoiser GEMMs: "tf32x3" (tcgen05, 3xTF32 split: fp32-level accuracy),
         # "tf32" (tcgen05, single pass) or "fp32" (FFMA); GEMMs below tc_min_rows rows stay on the FFMA kernel
         self.precision = "tf32x3"
@@ -313,6 +314,14 @@ class SAID(ABC, nn.Module):
             eta_noise = torch.stack(
                 [torch.randn(batch_size, window_size, in_channels, device=device) for _ in range(n_loop)]
             )
+        elif self._scheduler_is_ddpm() and n_loop > 0:
+            # DDPMScheduler.step draws randn(model_output.shape) in every iteration whose timestep is > 0
+            self.noise_scheduler.set_timesteps(num_inference_steps, device=device)
+            loop_ts = [int(t) for t in self.noise_scheduler.timesteps.detach().cpu().numpy()][num_inference_steps - n_loop:]
+            eta_noise = torch.stack(
+                [torch.randn(batch_size, window_size, in_channels, device=device) if t > 0
+                 else torch.zeros(batch_size, window_size, in_channels, device=device) for t in loop_ts]
+            )
         return self._run(
             waveform_processed, noise, init_samples, mask, num_inference_steps, strength, guidance_scale,
             guidance_rescale, eta, window_size, save_intermediate, show_process, eta_noise,
@@ -325,6 +334,10 @@ class SAID(ABC, nn.Module):
 
     def _scheduler_has_eta(self) -> bool:
         return "eta" in set(inspect.signature(self.noise_scheduler.step).parameters.keys())
+
+    def _scheduler_is_ddpm(self) -> bool:
+        """``DDPMScheduler`` (this package's or diffusers'): ancestral step, scheduler code 1 of the step kernel."""
+        return type(self.noise_scheduler).__name__ == "DDPMScheduler"
 
     def _run(
         self,
@@ -348,10 +361,11 @@ class SAID(ABC, nn.Module):
         device = waveform_processed.device
         eng = self._engine(device)
         ns = self.noise_scheduler
-        if not hasattr(ns, "alphas_cumprod") or not hasattr(ns, "final_alpha_cumprod"):
+        is_ddpm = self._scheduler_is_ddpm()
+        if not hasattr(ns, "alphas_cumprod") or not (is_ddpm or hasattr(ns, "final_alpha_cumprod")):
             raise NotImplementedError(
-                f"{type(ns).__name__}: the fused step kernel implements DDIMScheduler.step "
-                "(what script/inference.py and script/test_inference.py construct); other schedulers are not implemented"
+                f"{type(ns).__name__}: the fused step kernel implements DDIMScheduler.step (what script/inference.py and "
+                "script/test_inference.py construct) and DDPMScheduler.step; other schedulers are not implemented"
             )
         batch_size, in_channels = waveform_processed.shape[0], self.denoiser.in_channels
         do_cfg = guidance_scale > 1.0
@@ -385,14 +399,25 @@ class SAID(ABC, nn.Module):
         if use_mask:
             blend_next = [timesteps[t_start + i + 1] if t_start + i + 1 < num_inference_steps else None for i in range(n_loop)]
         has_eta = self._scheduler_has_eta()
-        table = sched.ddim_step_table(ns, loop_ts, eta if has_eta else 0.0, blend_next)
-        if eta_noise is not None and not (eta > 0 and has_eta):
-            eta_noise = None
-        if eta > 0 and has_eta and n_loop > 0 and eta_noise is None:
-            raise ValueError("eta > 0 needs the per-step variance noise")
+        if is_ddpm:
+            table = sched.ddpm_step_table(ns, loop_ts, blend_next)
+            if n_loop > 0 and any(t > 0 for t in loop_ts) and eta_noise is None:
+                raise ValueError("DDPMScheduler needs the per-step variance noise")
+        else:
+            table = sched.ddim_step_table(ns, loop_ts, eta if has_eta else 0.0, blend_next)
+            if eta_noise is not None and not (eta > 0 and has_eta):
+                eta_noise = None
+            if eta > 0 and has_eta and n_loop > 0 and eta_noise is None:
+                raise ValueError("eta > 0 needs the per-step variance noise")
 
         # audio encoder once per clip, then the K/V hoist
-        emb = eng.encode_audio(waveform_processed.to(torch.float32), window_size)
+        w32 = waveform_processed.to(torch.float32)
+        if self.dedup_audio and batch_size > 1 and bool((w32 == w32[:1]).all()):
+            # script/test_inference.py:167-168 repeats ONE clip over the batch (different noise per row): encode it once.
+            # (one tiny device reduction + a host read before the loop starts)
+            emb = eng.encode_audio(w32[:1].contiguous(), window_size).expand(batch_size, -1, -1).contiguous()
+        else:
+            emb = eng.encode_audio(w32, window_size)
         eng.prepare_context(emb, do_cfg)
 
         inter = None
@@ -406,6 +431,7 @@ class SAID(ABC, nn.Module):
             float(self.latent_scale), float(self.latent_scale) * float(ns.init_noise_sigma),
             edit_noise=edit_noise, edit_coefs=edit_coefs, mask=mask if use_mask else None,
             eta_noise=eta_noise, intermediates=inter, latents_out=latents_out, use_graph=self.use_cuda_graph,
+            scheduler=1 if is_ddpm else 0,
         )
         if show_process:
             from tqdm import tqdm

@@ -277,3 +277,133 @@ class DDIMScheduler(SchedulerMixin):
 
     def __len__(self) -> int:
         return self.config.num_train_timesteps
+
+
+# ======================================================================================================
+# DDPMScheduler (ancestral sampling).  The reference's constructor takes ``noise_scheduler: Type[SchedulerMixin]``
+# (``said/model/diffusion.py:55``) and calls only ``set_timesteps / scale_model_input / step / add_noise /
+# get_velocity`` on it; ``DDPMScheduler.step`` has no ``eta`` argument, so the ``inspect.signature`` test of
+# ``diffusion.py:404-405`` leaves ``extra_step_kwargs`` empty.  Restated from diffusers v0.19.3
+# ``src/diffusers/schedulers/scheduling_ddpm.py`` (same caveat as above: the package is absent, parity unpinned).
+# ======================================================================================================
+def ddpm_step_table(scheduler, timesteps: Sequence[int], blend_next: Optional[Sequence[Optional[int]]] = None) -> np.ndarray:
+    """Per-step scalars of ``DDPMScheduler.step`` for the fused CUDA step kernel (scheduler code 1), float32 with the
+    operation order of diffusers' 0-d tensor arithmetic.
+
+    Row ``k`` = ``[sqrt_a, sqrt_b, c0, c1, std, clip, blend_sa, blend_sb]`` with ``a = abar[t]``, ``ap = abar[t_prev]``
+    (1 below 0), ``cur_a = a / ap``, ``cur_b = 1 - cur_a``, ``c0 = sqrt(ap) * cur_b / (1 - a)`` (pred_original_sample_coeff),
+    ``c1 = sqrt(cur_a) * (1 - ap) / (1 - a)`` (current_sample_coeff), ``std = sqrt(clamp((1-ap)/(1-a) * cur_b, 1e-20))`` for
+    ``t > 0`` and 0 at ``t = 0`` (no variance noise is drawn there)."""
+    n = len(timesteps)
+    rows = np.zeros((n, 8), dtype=np.float32)
+    if n == 0:
+        return rows
+    if scheduler.config.variance_type != "fixed_small":
+        raise NotImplementedError("DDPM variance_type other than 'fixed_small' is not supported on the CUDA path")
+    ac = scheduler.alphas_cumprod.detach().to("cpu", torch.float32)
+    cfg = scheduler.config
+    one = torch.tensor(1.0, dtype=torch.float32)
+    clip = float(getattr(cfg, "clip_sample_range", 1.0)) if cfg.clip_sample else -1.0
+    ratio = cfg.num_train_timesteps // int(scheduler.num_inference_steps)
+    ts = torch.as_tensor(np.asarray(timesteps, dtype=np.int64))
+    tp = ts - ratio
+    a = ac[ts]
+    ap = torch.where(tp >= 0, ac[tp.clamp(min=0)], one)
+    b = 1 - a
+    bp = 1 - ap
+    cur_a = a / ap
+    cur_b = 1 - cur_a
+    c0 = (ap**0.5 * cur_b) / b
+    c1 = cur_a**0.5 * bp / b
+    var = torch.clamp((1 - ap) / (1 - a) * cur_b, min=1e-20)
+    std = torch.where(ts > 0, var**0.5, torch.zeros_like(var))
+    rows[:, 0] = (a**0.5).numpy()
+    rows[:, 1] = (b**0.5).numpy()
+    rows[:, 2] = c0.numpy()
+    rows[:, 3] = c1.numpy()
+    rows[:, 4] = std.numpy()
+    rows[:, 5] = clip
+    rows[:, 6], rows[:, 7] = 1.0, 0.0
+    if blend_next is not None:
+        idx = [k for k in range(n) if blend_next[k] is not None]
+        if idx:
+            an = ac[torch.as_tensor([int(blend_next[k]) for k in idx], dtype=torch.long)]
+            rows[idx, 6] = (an**0.5).numpy()
+            rows[idx, 7] = ((1 - an) ** 0.5).numpy()
+    return rows
+
+
+class DDPMScheduler(DDIMScheduler):
+    """diffusers-0.19 ``DDPMScheduler`` restricted to what SAiD can instantiate: ``squaredcos_cap_v2`` / linear betas,
+    ``variance_type="fixed_small"``, ``clip_sample=True``, leading timestep grid.  Shares the alpha table, the grid,
+    ``add_noise`` and ``get_velocity`` with :class:`DDIMScheduler`; ``step`` is the ancestral update."""
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", trained_betas=None, variance_type: str = "fixed_small",
+                 clip_sample: bool = True, prediction_type: str = "epsilon", thresholding: bool = False,
+                 dynamic_thresholding_ratio: float = 0.995, clip_sample_range: float = 1.0, sample_max_value: float = 1.0,
+                 timestep_spacing: str = "leading", steps_offset: int = 0):
+        super().__init__(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                         beta_schedule=beta_schedule, trained_betas=trained_betas, clip_sample=clip_sample,
+                         steps_offset=steps_offset, prediction_type=prediction_type, thresholding=thresholding,
+                         clip_sample_range=clip_sample_range, timestep_spacing=timestep_spacing)
+        if variance_type not in ("fixed_small", "fixed_small_log", "fixed_large", "fixed_large_log"):
+            raise NotImplementedError(f"variance_type {variance_type} (learned variances) is not used by SAiD")
+        self.config.variance_type = variance_type
+        self.one = torch.tensor(1.0)
+
+    def step_table(self, timesteps: List[int], eta: float = 0.0) -> np.ndarray:
+        return ddpm_step_table(self, timesteps)
+
+    def _get_variance(self, t: int) -> torch.Tensor:
+        tp = self.prev_timestep(t)
+        a = self.alphas_cumprod[t]
+        ap = self.alphas_cumprod[tp] if tp >= 0 else self.one
+        cur_b = 1 - a / ap
+        variance = (1 - ap) / (1 - a) * cur_b
+        variance = torch.clamp(variance, min=1e-20)
+        vt = self.config.variance_type
+        if vt == "fixed_small_log":
+            variance = torch.exp(0.5 * torch.log(variance))
+        elif vt == "fixed_large":
+            variance = cur_b
+        elif vt == "fixed_large_log":
+            variance = torch.log(cur_b)
+        return variance
+
+    def step(self, model_output: torch.Tensor, timestep: int, sample: torch.Tensor, generator=None,  # noqa: D102
+             variance_noise: Optional[torch.Tensor] = None, return_dict: bool = True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' first")
+        t = int(timestep)
+        tp = self.prev_timestep(t)
+        a = self.alphas_cumprod[t]
+        ap = self.alphas_cumprod[tp] if tp >= 0 else self.one
+        b = 1 - a
+        bp = 1 - ap
+        cur_a = a / ap
+        cur_b = 1 - cur_a
+        p = self.config.prediction_type
+        if p == "epsilon":
+            x0 = (sample - b**0.5 * model_output) / a**0.5
+        elif p == "sample":
+            x0 = model_output
+        else:
+            x0 = (a**0.5) * sample - (b**0.5) * model_output
+        if self.config.clip_sample:
+            x0 = x0.clamp(-self.config.clip_sample_range, self.config.clip_sample_range)
+        c0 = (ap**0.5 * cur_b) / b
+        c1 = cur_a**0.5 * bp / b
+        prev = c0 * x0 + c1 * sample
+        if t > 0:
+            if variance_noise is None:
+                variance_noise = torch.randn(model_output.shape, generator=generator, device=model_output.device,
+                                             dtype=model_output.dtype)
+            if self.config.variance_type == "fixed_small_log":
+                variance = self._get_variance(t) * variance_noise
+            else:
+                variance = (self._get_variance(t) ** 0.5) * variance_noise
+            prev = prev + variance
+        if not return_dict:
+            return (prev,)
+        return SchedulerOutput(prev_sample=prev, pred_original_sample=x0)

@@ -168,3 +168,47 @@ def test_compat_imports_resolve():
             assert names == BlendVOCADataset.default_blendshape_classes
     finally:
         sys.path.remove(os.path.join(ROOT, "compat"))
+
+
+def test_ddpm_scheduler_step_table_and_oracle():
+    """DDPMScheduler: the restated step, the oracle's restatement and the float32 coefficient table
+    handed to the CUDA kernel are the same arithmetic bit for bit; analytic anchors at the last step (t = 0:
+    a_prev = 1, so c0 = 1, c1 = 0, no noise: prev == clipped x0)."""
+    from oracle import said_oracle as O
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 7, 32, generator=g)
+    e = torch.randn(2, 7, 32, generator=g)
+    z = torch.randn(2, 7, 32, generator=g)
+    for pt in ("epsilon", "sample", "v_prediction"):
+        sch = S.DDPMScheduler(1000, beta_schedule="squaredcos_cap_v2", prediction_type=pt)
+        assert "eta" not in __import__("inspect").signature(sch.step).parameters     # diffusion.py:404-405 depends on this
+        sch.set_timesteps(50)
+        assert [int(t) for t in sch.timesteps[:3]] == [980, 960, 940] and int(sch.timesteps[-1]) == 0
+        for t in (980, 500, 20, 0):
+            want = sch.step(e, t, x, variance_noise=z).prev_sample
+            ora = O.ddpm_step(e, t, x, sch.alphas_cumprod, 50, pt, variance_noise=z)
+            assert torch.equal(want, ora), (pt, t)
+            row = torch.from_numpy(S.ddpm_step_table(sch, [t])[0])
+            sa, sb, c0, c1, std, clip = row[0], row[1], row[2], row[3], row[4], row[5]
+            if pt == "epsilon":
+                x0 = (x - sb * e) / sa
+            elif pt == "sample":
+                x0 = e
+            else:
+                x0 = sa * x - sb * e
+            x0 = x0.clamp(-clip, clip)
+            got = c0 * x0 + c1 * x
+            if t > 0:
+                got = got + std * z
+            assert torch.equal(got, want), (pt, t, float((got - want).abs().max()))
+            if t == 0:
+                assert float(c0) == 1.0 and float(c1) == 0.0 and float(std) == 0.0
+                assert torch.equal(want, x0)
+    # variance anchor: fixed_small = (1 - a_prev) / (1 - a) * (1 - a / a_prev), computed independently in float64
+    sch = S.DDPMScheduler(1000, beta_schedule="squaredcos_cap_v2")
+    sch.set_timesteps(1000)
+    ac = sch.alphas_cumprod.double()
+    t = 500
+    v64 = (1 - ac[t - 1]) / (1 - ac[t]) * (1 - ac[t] / ac[t - 1])
+    assert abs(float(S.ddpm_step_table(sch, [t])[0][4]) - float(v64**0.5)) < 1e-6
