@@ -145,7 +145,7 @@ def cpu_clips_per_s(t_enc: float, t_iter: float) -> float:
     return 1.0 / (t_enc + NUM_STEPS * t_iter)
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -176,7 +176,8 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def workload_config(args, world):
@@ -191,7 +192,18 @@ def workload_config(args, world):
 
 
 # --------------------------------------------------------------------------------------------------
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints
+    "NCCL version ..." there when NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run
+    and the JSON line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out = protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -206,7 +218,7 @@ def main():
     args = ap.parse_args()
 
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
         return
 
     import torch.distributed as dist
@@ -363,7 +375,8 @@ def main():
                           f"({ti * 1000:.1f} ms each), extrapolated to the full loop",
             }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -57,6 +57,11 @@ SAID_API int said_get_config(const said_engine* e, int* in_channels, int* ctx_di
  * said/model/wav2vec2.py:14-82): processed waveform (B, T_a) -> features (B, T, ctx_dim). */
 SAID_API int said_encode_audio(said_engine* e, const float* wave_dev, int B, int T_a, int T, float* emb_out_dev, void* stream);
 
+/* Device-side SAID.process_audio (reference said/model/diffusion.py:188-207 -> HF Wav2Vec2FeatureExtractor):
+ * per-utterance (x - mean) / sqrt(var + 1e-7) with the population variance, for B equal-length raw clips that are already
+ * on the device.  wave_dev (B, T_a) -> out_dev (B, T_a); in place allowed.   */
+SAID_API int said_normalize_audio(said_engine* e, const float* wave_dev, int B, int T_a, float* out_dev, void* stream);
+
 /* Hoist of everything the step loop needs from the audio features: cross-attention keys/values of all
  * four transformer blocks (reference said/model/ldm/attention.py:90-91 evaluates them on every step)
  * and, when with_uncond != 0, the constant value vector of the null-condition branch

@@ -311,17 +311,25 @@ def folded_pos_conv_weight(sd: SD, p: str) -> torch.Tensor:
     return g * v / v.norm(p=2, dim=(0, 1), keepdim=True)
 
 
-def wav2vec2_forward(sd: SD, input_values: torch.Tensor, num_frames: Optional[int], prefix: str = "audio_encoder.", heads: int = 12, taps: Optional[dict] = None) -> torch.Tensor:
+def wav2vec2_forward(sd: SD, input_values: torch.Tensor, num_frames: Optional[int], prefix: str = "audio_encoder.", heads: Optional[int] = None, taps: Optional[dict] = None, stable_layer_norm: bool = False) -> torch.Tensor:
     """``ModifiedWav2Vec2Model.forward(...).last_hidden_state`` (``said/model/wav2vec2.py:14-82``) in eval
     mode without attention mask: conv feature encoder -> linear interpolation to ``num_frames``
-    (``align_corners=True``) -> LN + projection -> grouped positional conv -> 12 post-LN layers."""
+    (``align_corners=True``) -> LN + projection -> grouped positional conv -> post-LN layers (wav2vec2-base family) or,
+    with ``stable_layer_norm`` (wav2vec2-large family: ``do_stable_layer_norm=True``, TF modeling_wav2vec2.py:612-655,
+    730-803), pre-LN layers and one LayerNorm after the last layer.  A feature extractor whose state dict holds a
+    LayerNorm per conv layer is the ``feat_extract_norm="layer"`` variant (conv bias + LayerNorm over channels + GELU,
+    TF :275-299).  ``heads`` defaults to hidden / 64."""
     g = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     x = input_values[:, None]
     n_conv = sum(1 for k in g if k.startswith("feature_extractor.conv_layers.") and k.endswith("conv.weight"))
     for i in range(n_conv):
         w = g[f"feature_extractor.conv_layers.{i}.conv.weight"]
-        x = F.conv1d(x, w, None, stride=CONV_STRIDES[i])
-        if i == 0:
+        layer_mode = "feature_extractor.conv_layers.1.layer_norm.weight" in g
+        x = F.conv1d(x, w, g.get(f"feature_extractor.conv_layers.{i}.conv.bias"), stride=CONV_STRIDES[i])
+        if layer_mode:
+            x = F.layer_norm(x.transpose(-2, -1), (w.shape[0],), g[f"feature_extractor.conv_layers.{i}.layer_norm.weight"],
+                             g[f"feature_extractor.conv_layers.{i}.layer_norm.bias"], 1e-5).transpose(-2, -1)
+        elif i == 0:
             x = F.group_norm(x, w.shape[0], g["feature_extractor.conv_layers.0.layer_norm.weight"], g["feature_extractor.conv_layers.0.layer_norm.bias"], 1e-5)
         x = F.gelu(x)
         if taps is not None:
@@ -341,21 +349,38 @@ def wav2vec2_forward(sd: SD, input_values: torch.Tensor, num_frames: Optional[in
     if k % 2 == 0:
         pos = pos[:, :, :-1]
     x = x + F.gelu(pos).transpose(1, 2)
-    x = F.layer_norm(x, (hdim,), g["encoder.layer_norm.weight"], g["encoder.layer_norm.bias"], 1e-5)
+    if not stable_layer_norm:
+        x = F.layer_norm(x, (hdim,), g["encoder.layer_norm.weight"], g["encoder.layer_norm.bias"], 1e-5)
     if taps is not None:
         taps["encoder_in"] = x
     n_layers = sum(1 for kk in g if kk.endswith("final_layer_norm.weight"))
+    if heads is None:
+        heads = hdim // 64
     d = hdim // heads
     B, T, _ = x.shape
-    for l in range(n_layers):
-        p = f"encoder.layers.{l}."
-        q = F.linear(x, g[p + "attention.q_proj.weight"], g[p + "attention.q_proj.bias"]) * (d**-0.5)
-        kk = F.linear(x, g[p + "attention.k_proj.weight"], g[p + "attention.k_proj.bias"])
-        v = F.linear(x, g[p + "attention.v_proj.weight"], g[p + "attention.v_proj.bias"])
-        sh = lambda t: t.reshape(B, T, heads, d).transpose(1, 2)  # noqa: E731
+    sh = lambda t: t.reshape(B, T, heads, d).transpose(1, 2)  # noqa: E731
+
+    def attention(p: str, h: torch.Tensor) -> torch.Tensor:
+        q = F.linear(h, g[p + "attention.q_proj.weight"], g[p + "attention.q_proj.bias"]) * (d**-0.5)
+        kk = F.linear(h, g[p + "attention.k_proj.weight"], g[p + "attention.k_proj.bias"])
+        v = F.linear(h, g[p + "attention.v_proj.weight"], g[p + "attention.v_proj.bias"])
         att = torch.softmax(sh(q) @ sh(kk).transpose(-1, -2), dim=-1) @ sh(v)
         att = att.transpose(1, 2).reshape(B, T, hdim)
-        att = F.linear(att, g[p + "attention.out_proj.weight"], g[p + "attention.out_proj.bias"])
+        return F.linear(att, g[p + "attention.out_proj.weight"], g[p + "attention.out_proj.bias"])
+
+    if stable_layer_norm:
+        for l in range(n_layers):
+            p = f"encoder.layers.{l}."
+            x = x + attention(p, F.layer_norm(x, (hdim,), g[p + "layer_norm.weight"], g[p + "layer_norm.bias"], 1e-5))
+            h = F.layer_norm(x, (hdim,), g[p + "final_layer_norm.weight"], g[p + "final_layer_norm.bias"], 1e-5)
+            ff = F.gelu(F.linear(h, g[p + "feed_forward.intermediate_dense.weight"], g[p + "feed_forward.intermediate_dense.bias"]))
+            x = x + F.linear(ff, g[p + "feed_forward.output_dense.weight"], g[p + "feed_forward.output_dense.bias"])
+            if taps is not None:
+                taps[f"layer{l}"] = x
+        return F.layer_norm(x, (hdim,), g["encoder.layer_norm.weight"], g["encoder.layer_norm.bias"], 1e-5)
+    for l in range(n_layers):
+        p = f"encoder.layers.{l}."
+        att = attention(p, x)
         x = F.layer_norm(x + att, (hdim,), g[p + "layer_norm.weight"], g[p + "layer_norm.bias"], 1e-5)
         ff = F.gelu(F.linear(x, g[p + "feed_forward.intermediate_dense.weight"], g[p + "feed_forward.intermediate_dense.bias"]))
         ff = F.linear(ff, g[p + "feed_forward.output_dense.weight"], g[p + "feed_forward.output_dense.bias"])

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "said_weights_ready",
     "said_get_config",
     "said_encode_audio",
+    "said_normalize_audio",
     "said_prepare_context",
     "said_denoise",
     "said_denoiser_forward",
@@ -99,6 +100,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_weights_ready.argtypes = [vp]
     lib.said_get_config.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.said_encode_audio.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.said_normalize_audio.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.said_prepare_context.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.said_denoise.argtypes = [vp, ctypes.POINTER(DenoiseArgs), vp]
     lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp]
@@ -205,6 +207,14 @@ class Engine:
         out = torch.empty((B, num_frames, self.config()["ctx_dim"]), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._call(self.lib.said_encode_audio(self._h, wave.data_ptr(), B, T_a, num_frames, out.data_ptr(), self._stream()))
+        return out
+
+    def normalize_audio(self, wave: torch.Tensor) -> torch.Tensor:
+        wave = _check_dev(wave, self.device, "waveform")
+        B, T_a = wave.shape
+        out = torch.empty_like(wave)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_normalize_audio(self._h, wave.data_ptr(), B, T_a, out.data_ptr(), self._stream()))
         return out
 
     def prepare_context(self, emb: torch.Tensor, with_uncond: bool) -> None:

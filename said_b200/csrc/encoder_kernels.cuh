@@ -14,6 +14,83 @@ constexpr int C0_K = 10;
 constexpr int C0_S = 5;
 constexpr int C0_TILE = 128;   // frames per smem tile
 
+// Per-utterance zero-mean / unit-variance normalisation on the device: y = (x - mean) / sqrt(var + 1e-7), population
+// variance (HF Wav2Vec2FeatureExtractor.zero_mean_unit_var_norm, reached from said/model/diffusion.py:188-207; the
+// reference does this in numpy on the host and returns a CPU tensor).  One CTA per clip, two passes in fp64 (the second
+// pass and the write re-read the clip from L2).
+__global__ void __launch_bounds__(1024)
+normalize_audio_kernel(const float* __restrict__ x, int T_a, float* __restrict__ y) {
+    __shared__ double red[32];
+    __shared__ double s_mean, s_rstd;
+    const float* xb = x + (long long)blockIdx.x * T_a;
+    float* yb = y + (long long)blockIdx.x * T_a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double s = 0.0;
+    for (int i = tid; i < T_a; i += blockDim.x) s += (double)__ldg(xb + i);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        s_mean = t / T_a;
+    }
+    __syncthreads();
+    const double mean = s_mean;
+    double q = 0.0;
+    for (int i = tid; i < T_a; i += blockDim.x) { const double d = (double)__ldg(xb + i) - mean; q += d * d; }
+    q = warp_sum(q);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        s_rstd = 1.0 / sqrt(t / T_a + 1e-7);
+    }
+    __syncthreads();
+    const float m32 = (float)mean, r32 = (float)s_rstd;
+    for (int i = tid; i < T_a; i += blockDim.x) yb[i] = (__ldg(xb + i) - m32) * r32;
+}
+
+// feat_extract_norm == "layer" (wav2vec2-large family, TF modeling_wav2vec2.py:275-299): conv0 = Conv1d(1 -> 512, k=10,
+// s=5, bias) -> LayerNorm over the 512 channels of each frame -> GELU.  One warp per frame (16 channels per lane, the
+// frame's 10 input samples broadcast from one load), output channel-last at row (b * out_stride + f).
+__global__ void __launch_bounds__(256)
+conv0_layernorm_gelu_kernel(const float* __restrict__ wave, int T_a, int L0, int B, const float* __restrict__ w /*(10,512)*/,
+                            const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            float eps, float* __restrict__ out, int out_stride) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (long long)B * L0) return;
+    const int b = (int)(gw / L0), f = (int)(gw - (long long)b * L0);
+    const float* x = wave + (long long)b * T_a + (long long)f * C0_S;
+    float xs[C0_K];
+#pragma unroll
+    for (int k = 0; k < C0_K; ++k) xs[k] = __ldg(x + k);
+    float y[16];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int c = lane + 32 * j;
+        float a = __ldg(bias + c);
+#pragma unroll
+        for (int k = 0; k < C0_K; ++k) a = fmaf(__ldg(w + k * C0_CH + c), xs[k], a);
+        y[j] = a;
+        s += a;
+    }
+    const float mean = warp_sum(s) * (1.0f / C0_CH);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const float d = y[j] - mean; q += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C0_CH) + eps);
+    float* o = out + ((long long)b * out_stride + f) * C0_CH;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int c = lane + 32 * j;
+        o[c] = gelu_erf((y[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c));
+    }
+}
+
 // grid (nchunk, B); partial: (B, nchunk, 2, 512) doubles
 __global__ void __launch_bounds__(C0_CH)
 conv0_stats_kernel(const float* __restrict__ wave, int T_a, int L0, const float* __restrict__ w /*(10,512)*/,

@@ -207,6 +207,9 @@ struct said_engine {
 
     // ---- packed encoder weights ----
     float *c0_w = nullptr, *c0_g = nullptr, *c0_b = nullptr;
+    // wav2vec2-large family (feat_extract_norm="layer", conv_bias, do_stable_layer_norm): per-conv bias + LayerNorm, pre-LN layers
+    bool enc_fe_layer_norm = false, enc_stable_ln = false;
+    float *c0_bias = nullptr, *conv_bias_p[8] = {nullptr}, *conv_ln_g[8] = {nullptr}, *conv_ln_b[8] = {nullptr};
     float *conv_w[8] = {nullptr};
     float *fp_ln_g = nullptr, *fp_ln_b = nullptr, *fp_w = nullptr, *fp_b = nullptr;
     float *pos_w = nullptr, *pos_b = nullptr, *enc_ln_g = nullptr, *enc_ln_b = nullptr;
@@ -496,11 +499,28 @@ int said_engine::commit_encoder() {
             for (int k = 0; k < C0_K; ++k) w[(size_t)k * C0_CH + c] = t->data[(size_t)c * C0_K + k];
         CKI(upload(w, &c0_w));
     }
-    if (find(P + "feature_extractor.conv_layers.0.conv.bias")) return fail("audio encoder: conv_bias=True is not supported");
-    if (find(P + "feature_extractor.conv_layers.1.layer_norm.weight"))
-        return fail("audio encoder: feat_extract_norm='layer' is not supported (wav2vec2-base family only)");
+    // feat_extract_norm: "group" (base: GroupNorm on layer 0 only, no conv bias) or "layer" (large: bias + LayerNorm over
+    // channels after every conv).  The state dict tells them apart; do_stable_layer_norm does not show in the names and
+    // arrives as the pseudo tensor "audio_encoder.config.do_stable_layer_norm" (set by the Python layer from the config).
+    enc_fe_layer_norm = find(P + "feature_extractor.conv_layers.1.layer_norm.weight") != nullptr;
+    const bool has_conv_bias = find(P + "feature_extractor.conv_layers.0.conv.bias") != nullptr;
+    if (enc_fe_layer_norm != has_conv_bias)
+        return fail("audio encoder: supported feature extractors are (group norm, no conv bias) and (layer norm, conv bias)");
+    {
+        const HostTensor* sl = find(P + "config.do_stable_layer_norm");
+        enc_stable_ln = sl && sl->numel() == 1 && sl->data[0] != 0.f;
+    }
     CKI(upload_raw(P + "feature_extractor.conv_layers.0.layer_norm.weight", {C0_CH}, &c0_g));
     CKI(upload_raw(P + "feature_extractor.conv_layers.0.layer_norm.bias", {C0_CH}, &c0_b));
+    if (enc_fe_layer_norm) {
+        CKI(upload_raw(P + "feature_extractor.conv_layers.0.conv.bias", {C0_CH}, &c0_bias));
+        for (int i = 1; i < 7; ++i) {
+            const std::string q = P + "feature_extractor.conv_layers." + std::to_string(i) + ".";
+            CKI(upload_raw(q + "conv.bias", {C0_CH}, &conv_bias_p[i]));
+            CKI(upload_raw(q + "layer_norm.weight", {C0_CH}, &conv_ln_g[i]));
+            CKI(upload_raw(q + "layer_norm.bias", {C0_CH}, &conv_ln_b[i]));
+        }
+    }
     for (int i = 1; i < 7; ++i) {
         conv_k[i] = ks[i];
         CKI(need(P + "feature_extractor.conv_layers." + std::to_string(i) + ".conv.weight", {C0_CH, C0_CH, ks[i]}, &t));
@@ -708,11 +728,18 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         if (conv_s[i] != 2) return fail("audio encoder: conv strides other than (5,2,2,2,2,2,2) are not supported");
     CK(e_a.ensure((size_t)(B * S[0] + 4) * CD));
     CK(e_b.ensure((size_t)(B * S[1] + 4) * CD));
-    conv0_stats_kernel<<<dim3(nchunk, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, fpc, c0_partial);
-    LAUNCH_CHECK();
-    conv0_apply_kernel<<<dim3((L[0] + C0_TILE - 1) / C0_TILE, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, c0_partial, nchunk,
-                                                                                   c0_g, c0_b, 1e-5f, e_a.p, S[0]);
-    LAUNCH_CHECK();
+    if (enc_fe_layer_norm) {
+        const long long warps = (long long)B * L[0];
+        conv0_layernorm_gelu_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(wave, T_a, L[0], B, c0_w, c0_bias, c0_g, c0_b, 1e-5f,
+                                                                                          e_a.p, S[0]);
+        LAUNCH_CHECK();
+    } else {
+        conv0_stats_kernel<<<dim3(nchunk, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, fpc, c0_partial);
+        LAUNCH_CHECK();
+        conv0_apply_kernel<<<dim3((L[0] + C0_TILE - 1) / C0_TILE, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, c0_partial, nchunk,
+                                                                                       c0_g, c0_b, 1e-5f, e_a.p, S[0]);
+        LAUNCH_CHECK();
+    }
     // ---- conv1..6 (stride 2, GELU): one flat overlapping-row GEMM per layer
     float* src = e_a.p;
     float* dst = e_b.p;
@@ -720,8 +747,16 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         const int rows = B * S[i];
         ALoadPlain al = mk_plain(src, (long long)conv_s[i] * CD, rows);
         EpiStd ep = mk_epi(dst, CD, CD);
-        ep.act = 1;
-        CKI(gemm(st, rows, CD, conv_k[i] * CD, al, conv_w[i], CD, ep));
+        if (enc_fe_layer_norm) {   // conv + bias, then LayerNorm(512) + GELU over every (also padding) row, in place
+            ep.bias = conv_bias_p[i];
+            CKI(gemm(st, rows, CD, conv_k[i] * CD, al, conv_w[i], CD, ep));
+            layernorm_rows_kernel<8><<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(dst, nullptr, rows, CD, 1e-5f, conv_ln_g[i],
+                                                                                                  conv_ln_b[i], dst, 1);
+            LAUNCH_CHECK();
+        } else {
+            ep.act = 1;
+            CKI(gemm(st, rows, CD, conv_k[i] * CD, al, conv_w[i], CD, ep));
+        }
         std::swap(src, dst);
     }
     // src now holds (B, S_last, CD), valid frames [0, Lf) of each clip
@@ -760,12 +795,64 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         ep.zs1 = cg;
         ep.bias_zs = cg;
         CKI(gemm(st, T, cg, pos_k * cg, al, pos_w, cg, ep, B * pos_g, pos_g, (long long)pos_k * cg * cg));
-        layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(e_c.p, nullptr, M, H, 1e-5f, enc_ln_g, enc_ln_b, e_d.p);
-        LAUNCH_CHECK();
+        if (!enc_stable_ln) {   // post-LN encoder: LayerNorm right after the positional embedding (TF :690-693)
+            layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(e_c.p, nullptr, M, H, 1e-5f, enc_ln_g, enc_ln_b, e_d.p);
+            LAUNCH_CHECK();
+        }
     }
-    // ---- transformer layers; x lives in e_d
     CK(cudaFuncSetAttribute(self_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)attention_smem_bytes<64>()));
+    if (enc_stable_ln) {
+        // ---- Wav2Vec2EncoderStableLayerNorm (TF modeling_wav2vec2.py:730-803, 612-655): pre-LN layers over h = e_c,
+        //      h += attn(LN1(h)); h += ffn(LN2(h)); one LayerNorm after the last layer.  The residual adds run in place
+        //      (epilogue reads and writes the same element).
+        float* h = e_c.p;
+        for (int l = 0; l < enc_layers; ++l) {
+            const EncLayerW& W = enc[l];
+            layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(h, nullptr, M, H, 1e-5f, W.ln1_g, W.ln1_b, e_d.p);
+            LAUNCH_CHECK();
+            {
+                EpiStd ep = mk_epi(e_qkv.p, 3 * H, 3 * H);
+                ep.bias = W.bqkv;
+                CKI(gemm(st, M, 3 * H, H, mk_plain(e_d.p, H, M), W.wqkv, 3 * H, ep));
+            }
+            self_attention_kernel<64><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, enc_heads, B), ATT_THREADS,
+                                        attention_smem_bytes<64>(), st>>>(e_qkv.p, 3 * H, 0, H, 2 * H, T, 0.125f, e_d.p, H);
+            LAUNCH_CHECK();
+            {
+                EpiStd ep = mk_epi(h, H, H);
+                ep.bias = W.bo;
+                ep.res = h;
+                ep.ldr = H;
+                CKI(gemm(st, M, H, H, mk_plain(e_d.p, H, M), W.wo, H, ep));
+            }
+            layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(h, nullptr, M, H, 1e-5f, W.ln2_g, W.ln2_b, e_d.p);
+            LAUNCH_CHECK();
+            {
+                EpiStd ep = mk_epi(e_ff.p, enc_ffn, enc_ffn);
+                ep.bias = W.bff1;
+                ep.act = 1;
+                CKI(gemm(st, M, enc_ffn, H, mk_plain(e_d.p, H, M), W.wff1, enc_ffn, ep));
+            }
+            {
+                EpiStd ep = mk_epi(h, H, H);
+                ep.bias = W.bff2;
+                ep.res = h;
+                ep.ldr = H;
+                CKI(gemm(st, M, H, enc_ffn, mk_plain(e_ff.p, enc_ffn, M), W.wff2, H, ep));
+            }
+        }
+        float* dst_ln = proj_dim == 0 ? emb_out : e_d.p;
+        layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(h, nullptr, M, H, 1e-5f, enc_ln_g, enc_ln_b, dst_ln);
+        LAUNCH_CHECK();
+        if (proj_dim != 0) {   // audio_proj_layer (diffusion.py:228-229)
+            EpiStd ep = mk_epi(emb_out, proj_dim, proj_dim);
+            ep.bias = b_aproj;
+            CKI(gemm(st, M, proj_dim, H, mk_plain(e_d.p, H, M), w_aproj, proj_dim, ep));
+        }
+        return 0;
+    }
+    // ---- transformer layers; x lives in e_d
     const bool last_direct = proj_dim == 0;
     for (int l = 0; l < enc_layers; ++l) {
         const EncLayerW& W = enc[l];
@@ -1270,6 +1357,16 @@ int said_get_config(const said_engine* e, int* in_channels, int* ctx_dim, int* e
     if (in_channels) *in_channels = e->in_ch;
     if (ctx_dim) *ctx_dim = e->ctx_dim;
     if (enc_hidden) *enc_hidden = e->enc_hidden;
+    return 0;
+}
+
+int said_normalize_audio(said_engine* e, const float* wave_dev, int B, int T_a, float* out_dev, void* stream) {
+    if (!e) return fail("null engine");
+    if (B <= 0 || T_a <= 0 || !wave_dev || !out_dev) return fail("said_normalize_audio: bad arguments");
+    CK(cudaSetDevice(e->device));
+    normalize_audio_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(wave_dev, T_a, out_dev);
+    ++e->launches;
+    CK(cudaGetLastError());
     return 0;
 }
 

@@ -262,7 +262,7 @@ ln192_rows_kernel(const float* __restrict__ x, int M, int T, const float* __rest
 template <int MAXV>   // float4 per lane, C <= 128*MAXV
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ r, int M, int C, float eps,
-                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y) {
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int act = 0 /*1: GELU after*/) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= M) return;
     const float* xr = x + (long long)warp * C;
@@ -301,6 +301,7 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ r, 
             o.y = (v[j].y - mean) * rstd * g.y + bb.y;
             o.z = (v[j].z - mean) * rstd * g.z + bb.z;
             o.w = (v[j].w - mean) * rstd * g.w + bb.w;
+            if (act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
             st4(y + (long long)warp * C + k, o);
         }
     }

@@ -211,6 +211,8 @@ class SAID(ABC, nn.Module):
             tensors["time_freqs"] = torch.exp(
                 -np.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half
             )  # ldm/util.py:75-78, evaluated with the same torch ops as the reference
+            # the one encoder switch that does not show in the state-dict names
+            tensors["audio_encoder.config.do_stable_layer_norm"] = torch.tensor([1.0 if self._audio_dims.stable_layer_norm else 0.0])
             eng.load_weights(tensors)
             self._engine_keys[idx] = key
         eng.set_precision(self.precision, self.tc_min_rows, self.encoder_precision)
@@ -243,6 +245,14 @@ class SAID(ABC, nn.Module):
         returns (Batch_size, T_a) float32 on the CPU."""
         out = self.audio_processor(waveform, sampling_rate=self.sampling_rate, return_tensors="pt")["input_values"]
         return out
+
+    def process_audio_device(self, waveform: torch.Tensor) -> torch.FloatTensor:
+        """``process_audio`` for equal-length raw clips that already live on the GPU: (B, T_a) -> (B, T_a) on the same
+        device, per-utterance zero mean / unit variance in one kernel (no host round trip; the reference's
+        ``process_audio`` normalises in numpy and returns a CPU tensor, ``diffusion.py:188-207``)."""
+        if waveform.dim() == 1:
+            waveform = waveform[None]
+        return self._engine(waveform.device).normalize_audio(waveform.float())
 
     def _conv_out_frames(self, n: int) -> int:
         for k, s in zip(self._audio_dims.conv_kernel, self._audio_dims.conv_stride):

@@ -167,12 +167,10 @@ class Wav2Vec2Dims:
     def check_supported(self) -> None:
         """Fail loudly on configurations the sm_100a kernels do not implement."""
         bad = []
-        if self.feat_extract_norm != "group":
-            bad.append("feat_extract_norm != 'group'")
-        if self.stable_layer_norm:
-            bad.append("do_stable_layer_norm=True")
-        if self.conv_bias:
-            bad.append("conv_bias=True")
+        if self.feat_extract_norm not in ("group", "layer"):
+            bad.append("feat_extract_norm not in ('group', 'layer')")
+        if (self.feat_extract_norm == "layer") != self.conv_bias:
+            bad.append("feat_extract_norm='layer' without conv_bias=True (or the reverse)")
         if self.add_adapter:
             bad.append("add_adapter=True")
         if len(set(self.conv_dim)) != 1:
@@ -181,7 +179,7 @@ class Wav2Vec2Dims:
             bad.append("head_dim != 64")
         if bad:
             raise NotImplementedError(
-                "said_b200 audio encoder supports the wav2vec2-base family only; unsupported: "
+                "said_b200 audio encoder supports the wav2vec2-base and wav2vec2-large families; unsupported: "
                 + ", ".join(bad)
             )
 
@@ -193,7 +191,9 @@ def audio_encoder_spec(d: Wav2Vec2Dims) -> Spec:
     cin = 1
     for i, (co, k) in enumerate(zip(d.conv_dim, d.conv_kernel)):
         spec.append((f"feature_extractor.conv_layers.{i}.conv.weight", (co, cin, k)))
-        if i == 0:
+        if d.conv_bias:
+            spec.append((f"feature_extractor.conv_layers.{i}.conv.bias", (co,)))
+        if i == 0 or d.feat_extract_norm == "layer":
             spec.append((f"feature_extractor.conv_layers.{i}.layer_norm.weight", (co,)))
             spec.append((f"feature_extractor.conv_layers.{i}.layer_norm.bias", (co,)))
         cin = co

@@ -447,3 +447,43 @@ def test_repeated_clip_is_encoded_once(gpu_model):
     print("dedup", maxdiff(a, b), la, lb)
     assert maxdiff(a, b) < 1e-4
     assert not torch.equal(a[0], a[1])      # different noise per row: different results
+
+
+def test_large_family_encoder_golden(golden_dir, large_family):
+    """wav2vec2-large family on the CUDA path (per-conv bias + LayerNorm + GELU feature extractor, pre-LN transformer layers,
+    final LayerNorm) against the output of the reference's own ModifiedWav2Vec2Model.  Reference fp32-vs-fp64 floor for this
+    configuration: 1.7e-5; tolerance 1e-4."""
+    from said_b200.model.diffusion import SAID_UNet1D
+
+    cfg, sd = large_family
+    gd = load(golden_dir, "audio_encoder_large_family_1s.npz")
+    m = SAID_UNet1D(audio_config=cfg)
+    m.load_state_dict(sd, strict=False)
+    m.to(DEV).eval()
+    with torch.no_grad():
+        emb = m.get_audio_embedding(torch.from_numpy(gd["wave"]).to(DEV), 60)
+    e32, e64 = maxdiff(emb, gd["emb"]), maxdiff(emb, gd["emb64"])
+    print("large-family encoder", e32, e64)
+    assert emb.shape == (1, 60, 256)
+    assert e32 < 1e-4 and e64 < 1e-4
+    # and a batch, through the full inference path (encoder -> K/V hoist -> 4 steps): finite, in range, per-clip independent
+    wave = torch.from_numpy(gd["wave"]).repeat(3, 1)
+    wave[1] = wave[1].flip(0)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        out = m.inference(wave.to(DEV), num_inference_steps=4, guidance_scale=2.0).result
+    assert out.shape == (3, 60, 32) and bool(torch.isfinite(out).all())
+
+
+def test_process_audio_device_matches_host(gpu_model):
+    """Device-side per-utterance normalisation (8(f) rank 1) == the host feature extractor's, to fp32 rounding."""
+    from said_b200.synth import synthetic_waveform
+
+    m = gpu_model()
+    raw = np.stack([synthetic_waveform(i, 1.0) * (1.0 + i) + 0.05 * i for i in range(3)]).astype(np.float32)
+    want = m.process_audio(list(raw))
+    got = m.process_audio_device(torch.from_numpy(raw).to(DEV))
+    e = maxdiff(got, want)
+    print("process_audio_device", e)
+    assert got.device.type == "cuda" and got.shape == want.shape
+    assert e < 2e-6

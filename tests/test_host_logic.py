@@ -134,7 +134,29 @@ def test_unsupported_encoder_config_fails_loudly():
     from said_b200.model.diffusion import SAID_UNet1D
 
     with pytest.raises(NotImplementedError):
-        SAID_UNet1D(audio_config=SimpleNamespace(do_stable_layer_norm=True, feat_extract_norm="layer"))
+        SAID_UNet1D(audio_config=SimpleNamespace(add_adapter=True))
+    with pytest.raises(NotImplementedError):
+        SAID_UNet1D(audio_config=SimpleNamespace(feat_extract_norm="layer", conv_bias=False))
+
+
+def test_large_family_state_dict_layout(large_family):
+    """SAID_UNet1D(audio_config=<wav2vec2-large family>) exposes exactly transformers' parameter names for that
+    configuration (conv biases, one LayerNorm per conv layer) and loads them strictly."""
+    from said_b200.model.diffusion import SAID_UNet1D
+
+    cfg, sd = large_family
+    m = SAID_UNet1D(audio_config=cfg)
+    own = {k for k in m.state_dict() if k.startswith("audio_encoder.")}
+    alias = {"audio_encoder.encoder.pos_conv_embed.conv.parametrizations.weight.original0": "audio_encoder.encoder.pos_conv_embed.conv.weight_g",
+             "audio_encoder.encoder.pos_conv_embed.conv.parametrizations.weight.original1": "audio_encoder.encoder.pos_conv_embed.conv.weight_v"}
+    theirs = {alias.get(k, k) for k in sd}
+    assert own == theirs, (sorted(own - theirs)[:5], sorted(theirs - own)[:5])
+    assert "audio_encoder.feature_extractor.conv_layers.3.layer_norm.weight" in own
+    assert "audio_encoder.feature_extractor.conv_layers.0.conv.bias" in own
+    full = m.state_dict()
+    full.update({alias.get(k, k): v for k, v in sd.items()})
+    m.load_state_dict(full, strict=True)
+    assert m._audio_dims.stable_layer_norm and m.denoiser.model if hasattr(m.denoiser, "model") else True
 
 
 def test_compat_imports_resolve():

@@ -99,3 +99,19 @@ def test_floors_recorded(golden_dir):
     assert d["report"]["denoiser_oracle_vs_ref"] == 0.0
     assert d["report"]["cfg1_loop_oracle_vs_ref_same_emb"] == 0.0
     assert d["report"]["chain1000_v_prediction_oracle_vs_ref"] == 0.0
+
+
+def test_oracle_large_family_encoder_matches_reference(golden_dir, large_family):
+    """wav2vec2-large family (layer-norm feature extractor, conv bias, stable layer norm): the oracle
+    against the output of the reference's own ModifiedWav2Vec2Model (tests/golden/make_golden_large.py)."""
+    import numpy as np
+    import torch
+
+    from oracle import said_oracle as O
+
+    _, sd = large_family
+    gd = np.load(os.path.join(golden_dir, "audio_encoder_large_family_1s.npz"))
+    with torch.no_grad():
+        emb = O.wav2vec2_forward(sd, torch.from_numpy(gd["wave"]), 60, stable_layer_norm=True)
+    err = float((emb - torch.from_numpy(gd["emb"])).abs().max())
+    assert err < 1e-4, err
