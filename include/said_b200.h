@@ -44,8 +44,10 @@ SAID_API void said_destroy(said_engine* e);
  * "null_cond_emb", "audio_proj_layer.weight", ...; both weight-norm spellings of the positional conv
  * are accepted).  The data is copied.  "time_freqs" (96 floats: exp(-ln(1e4) k/96), reference
  * said/model/ldm/util.py:75-78) must also be supplied by the host so that it is bit-identical to the
- * value the reference computes with torch.  said_commit_weights() validates the set, infers the
- * configuration from the shapes, repacks into the kernels' layouts and uploads. */
+ * value the reference computes with torch.  "audio_encoder.config.do_stable_layer_norm" (one float, 0 or 1; absent = 0) is
+ * the one Wav2Vec2Config switch that cannot be read off the parameter names (wav2vec2-large family: pre-LN layers).
+ * said_commit_weights() validates the set, infers the rest of the configuration from the names and shapes (e.g. a LayerNorm
+ * per conv layer = feat_extract_norm "layer"), repacks into the kernels' layouts and uploads. */
 SAID_API int said_set_tensor(said_engine* e, const char* name, const float* host_data, const int64_t* shape, int ndim);
 SAID_API int said_commit_weights(said_engine* e);
 /* 1 if said_commit_weights has succeeded since the last said_set_tensor */
