@@ -272,8 +272,29 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     // blocked assignment: CTA c owns a contiguous run of tiles (n fastest), so the n-tiles of one row block are
     // processed back to back by the same CTA (row statistics computed once, activation rows hot in L1/L2)
     const int tq = total_tiles / (int)gridDim.x, tr = total_tiles % (int)gridDim.x;
-    const int my_tiles = tq + ((int)blockIdx.x < tr ? 1 : 0);
-    const int tile0 = (int)blockIdx.x * tq + min((int)blockIdx.x, tr);
+    // Tail balancing for single-column-tile GEMMs (N == BN): with T tiles on G CTAs the tr = T % G leftover tiles used to cost
+    // a whole extra round (300 tiles on 148 SMs: 3 rounds for 2.03; 150 tiles: 2 for 1.01).  Each leftover tile is instead cut
+    // along N into S slivers (S * tr <= G, sliver width a multiple of 16) handed to different CTAs as their LAST item: a sliver
+    // repeats the tile's operand production but only 1/S of its MMAs, weight traffic and epilogue.
+    int sl_S = 1;
+    if (n_tiles == 1 && BN == 192 && tq >= 1 && tr > 0 && !(d.dbg & 32)) {
+        const int cand[5] = {12, 6, 4, 3, 2};
+        for (int k = 0; k < 5; ++k)
+            if (cand[k] * tr <= (int)gridDim.x) { sl_S = cand[k]; break; }
+    }
+    const bool sliver_mode = sl_S > 1;
+    const int my_tiles = sliver_mode ? tq + ((int)blockIdx.x < tr * sl_S ? 1 : 0) : tq + ((int)blockIdx.x < tr ? 1 : 0);
+    const int tile0 = sliver_mode ? (int)blockIdx.x * tq : (int)blockIdx.x * tq + min((int)blockIdx.x, tr);
+    struct Item { int mt, nt, n0, nw; };
+    auto item = [&](int i) -> Item {       // i-th work item of this CTA (the same for every role)
+        if (sliver_mode && i >= tq) {
+            const int s = (int)blockIdx.x;
+            return Item{(int)gridDim.x * tq + s / sl_S, 0, (s % sl_S) * (BN / sl_S), BN / sl_S};
+        }
+        const int tile = tile0 + i;
+        const int mt = tile / n_tiles;
+        return Item{mt, tile - mt * n_tiles, 0, BN};
+    };
 
     if (tid == EPI_WARPS * 32) {
         for (int s = 0; s < AS; ++s) {
@@ -322,8 +343,10 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) pf[jj][ii] = zero4();
         for (int i = 0; i < my_tiles; ++i) {
-            const int tile = tile0 + i;
-            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+            const Item it_ = item(i);
+            const int mt = it_.mt, nt = it_.nt;
+            const int nch_i = it_.nw / 16;                 // 16-column chunks of this item (NCH, or fewer for a sliver)
+            const int ncol0 = nt * BN + it_.n0;            // first output column of this item
             const int buf = i & 1;
             const int mrow0 = mt * BM + q * 32 + lr;       // + 8 ii
             typename EP::RowCtx rc[4];
@@ -334,7 +357,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                 for (int jj = 0; jj < EPI_PF; ++jj) {
                     const int j = 2 * jj + half;
 #pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) pf[jj][ii] = ep.tc_prefetch4(rc[ii], nt * BN + (j < NCH ? j : 0) * 16 + lq * 4);
+                    for (int ii = 0; ii < 4; ++ii) pf[jj][ii] = ep.tc_prefetch4(rc[ii], ncol0 + (j < nch_i ? j : 0) * 16 + lq * 4);
                 }
             }
             mbar_wait(accf_bar(buf), (uint32_t)(i >> 1) & 1u);
@@ -343,7 +366,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
 #pragma unroll
             for (int jj = 0; jj < MYCH; ++jj) {
                 const int j = 2 * jj + half;
-                if (j < NCH) {                             // warp-uniform
+                if (j < nch_i) {                           // warp-uniform
                     float v[16];
                     tmem_ld16(taddr + j * 16, v);
                     // lane = row `lane`: write 4 float4 with the float4-column XOR-swizzled by (row >> 1) & 3
@@ -354,7 +377,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                                      "f"(v[4 * c4 + 2]), "f"(v[4 * c4 + 3]) : "memory");
                     }
                     __syncwarp();
-                    const int n = nt * BN + j * 16 + lq * 4;
+                    const int n = ncol0 + j * 16 + lq * 4;
 #pragma unroll
                     for (int ii = 0; ii < 4; ++ii) {
                         const int r = lr + 8 * ii;
@@ -366,9 +389,9 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                     }
                     __syncwarp();
                     const int jn = j + 2 * EPI_PF;
-                    if (has_res && jn < NCH) {             // warp-uniform
+                    if (has_res && jn < nch_i) {           // warp-uniform
 #pragma unroll
-                        for (int ii = 0; ii < 4; ++ii) pf[jj % EPI_PF][ii] = ep.tc_prefetch4(rc[ii], nt * BN + jn * 16 + lq * 4);
+                        for (int ii = 0; ii < 4; ++ii) pf[jj % EPI_PF][ii] = ep.tc_prefetch4(rc[ii], ncol0 + jn * 16 + lq * 4);
                     }
                 }
             }
@@ -378,11 +401,13 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     } else if (warp == EPI_WARPS) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(BM, BN);
             int sa = 0, sb = 0, sl = 0;
             uint32_t pa = 0, pb = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int buf = i & 1;
+                const Item it_ = item(i);
+                const uint32_t idesc = make_idesc_tf32(BM, it_.nw);          // a sliver multiplies by rows [n0, n0 + nw) of the weight tile
+                const uint32_t boff = (uint32_t)it_.n0 * ROW_BYTES;          // (n0 is a multiple of 16 rows: whole 1024-byte swizzle atoms)
                 mbar_wait(acce_bar(buf), ((uint32_t)(i >> 1) & 1u) ^ 1u);   // accumulator drained (first use: free)
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_STRIDE);
@@ -391,9 +416,9 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
                     mbar_wait(fullb_bar(sb), pb);
                     tc_fence_after();
                     const uint64_t da = make_desc(a_hi(sa));
-                    const uint64_t db = make_desc(b_hi(sb));
+                    const uint64_t db = make_desc(b_hi(sb) + boff);
                     const uint64_t dal = make_desc(a_lo(sl));
-                    const uint64_t dbl = make_desc(b_hi(sb) + Cfg::B_TILE_BYTES);
+                    const uint64_t dbl = make_desc(b_hi(sb) + Cfg::B_TILE_BYTES + boff);
 #pragma unroll
                     for (int k4 = 0; k4 < ((d.dbg & 8) ? 0 : BK / 8); ++k4) {
                         const uint64_t adv = (uint64_t)(k4 * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units along K (inside one swizzle row)
@@ -420,16 +445,22 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
             int sb = 0;
             uint32_t pb = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                const int tile = tile0 + i;
-                const int nt = tile % n_tiles;
-                const float* wsrc = Wp + (size_t)nt * nk * d.w_block_floats;
+                const Item it_ = item(i);
+                const float* wsrc = Wp + (size_t)it_.nt * nk * d.w_block_floats;
                 for (int kc = 0; kc < nk; ++kc) {
                     mbar_wait(emptyb_bar(sb), pb ^ 1u);
                     if (d.dbg & 2) {
                         mbar_arrive(fullb_bar(sb));
-                    } else {
+                    } else if (it_.nw == BN) {
                         mbar_arrive_expect_tx(fullb_bar(sb), bytes);
                         bulk_g2s(b_hi(sb), wsrc + (size_t)kc * d.w_block_floats, bytes, fullb_bar(sb));
+                    } else {   // sliver: only its rows of the hi and (3xTF32) lo tiles
+                        const uint32_t part = (uint32_t)it_.nw * ROW_BYTES, roff = (uint32_t)it_.n0 * ROW_BYTES;
+                        const float* blk = wsrc + (size_t)kc * d.w_block_floats;
+                        mbar_arrive_expect_tx(fullb_bar(sb), part * Cfg::NPARTS);
+                        bulk_g2s(b_hi(sb) + roff, blk + roff / 4, part, fullb_bar(sb));
+                        if (Cfg::NPARTS == 2)
+                            bulk_g2s(b_hi(sb) + Cfg::B_TILE_BYTES + roff, blk + (Cfg::B_TILE_BYTES + roff) / 4, part, fullb_bar(sb));
                     }
                     if (++sb == BS) { sb = 0; pb ^= 1u; }
                 }
@@ -453,7 +484,7 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
         typename AL::ICtx ic[LROWS];
         auto issue_one = [&]() {                 // the stage must be free (MMAs of item ii - AS complete)
             if (kc_i == 0) {
-                const int m0 = ((tile0 + ti_i) / n_tiles) * BM;
+                const int m0 = item(ti_i).mt * BM;
 #pragma unroll
                 for (int i = 0; i < LROWS; ++i) ic[i] = al.iprep(m0 + rb + LROW_STEP * i);
             }
@@ -476,8 +507,8 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
         int sj = 0;                              // hi stage (and its phase) of item it - ALS, whose MMAs free lo stage sl_x
         uint32_t pj = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
-            const int m0 = ((tile0 + ti) / n_tiles) * BM;
-            const bool new_rows = ti == 0 || (tile0 + ti) / n_tiles != (tile0 + ti - 1) / n_tiles;
+            const int m0 = item(ti).mt * BM;
+            const bool new_rows = ti == 0 || item(ti).mt != item(ti - 1).mt;
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 // keep the ring full without blocking: a stage is free once the MMAs that read it have completed
                 while (ii < total_items && ii - it < AS && mbar_test_wait(emptya_bar(sa_i), pa_i ^ 1u)) issue_one();

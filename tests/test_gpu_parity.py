@@ -487,3 +487,25 @@ def test_process_audio_device_matches_host(gpu_model):
     print("process_audio_device", e)
     assert got.device.type == "cuda" and got.shape == want.shape
     assert e < 2e-6
+
+
+def test_gemm_tail_slivers_match_fp32(gpu_model):
+    """150 row tiles on 148 SMs: the two leftover tiles of every N = 192 GEMM are cut into 16-column slivers spread over
+    24 CTAs (gemm_tc.cuh "tail balancing").  One UNet forward of 320 samples x 60 frames (19 200 rows) in tf32x3 against
+    the fp32 FFMA kernels of the same engine; tolerance 2e-4 (the precision-mode test's bound for block activations)."""
+    m = gpu_model()
+    eng = m._engine(torch.device(DEV))
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(320, 60, 32, generator=g).to(DEV)
+    ctx = torch.randn(320, 60, 768, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (320,), generator=g)
+    outs = {}
+    for mode in ("tf32x3", "fp32"):
+        eng.set_precision(mode, 2048, "fp32")
+        try:
+            outs[mode] = eng.denoiser_forward(x, t, ctx).cpu()
+        finally:
+            eng.set_precision(m.precision, m.tc_min_rows, m.encoder_precision)
+    e = maxdiff(outs["tf32x3"], outs["fp32"])
+    print("tail slivers tf32x3 vs fp32", e)
+    assert e < 2e-4
