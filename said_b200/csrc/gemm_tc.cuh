@@ -272,12 +272,12 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     // blocked assignment: CTA c owns a contiguous run of tiles (n fastest), so the n-tiles of one row block are
     // processed back to back by the same CTA (row statistics computed once, activation rows hot in L1/L2)
     const int tq = total_tiles / (int)gridDim.x, tr = total_tiles % (int)gridDim.x;
-    // Tail balancing for single-column-tile GEMMs (N == BN): with T tiles on G CTAs the tr = T % G leftover tiles used to cost
+    // Tail balancing: with T tiles on G CTAs the tr = T % G leftover tiles used to cost
     // a whole extra round (300 tiles on 148 SMs: 3 rounds for 2.03; 150 tiles: 2 for 1.01).  Each leftover tile is instead cut
     // along N into S slivers (S * tr <= G, sliver width a multiple of 16) handed to different CTAs as their LAST item: a sliver
     // repeats the tile's operand production but only 1/S of its MMAs, weight traffic and epilogue.
     int sl_S = 1;
-    if (n_tiles == 1 && BN == 192 && tq >= 1 && tr > 0 && !(d.dbg & 32)) {
+    if (BN == 192 && tq >= 1 && tr > 0 && !(d.dbg & 32)) {
         const int cand[5] = {12, 6, 4, 3, 2};
         for (int k = 0; k < 5; ++k)
             if (cand[k] * tr <= (int)gridDim.x) { sl_S = cand[k]; break; }
@@ -289,7 +289,8 @@ gemm_tc_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     auto item = [&](int i) -> Item {       // i-th work item of this CTA (the same for every role)
         if (sliver_mode && i >= tq) {
             const int s = (int)blockIdx.x;
-            return Item{(int)gridDim.x * tq + s / sl_S, 0, (s % sl_S) * (BN / sl_S), BN / sl_S};
+            const int tile = (int)gridDim.x * tq + s / sl_S, mt = tile / n_tiles;
+            return Item{mt, tile - mt * n_tiles, (s % sl_S) * (BN / sl_S), BN / sl_S};
         }
         const int tile = tile0 + i;
         const int mt = tile / n_tiles;
