@@ -2,17 +2,19 @@
 //
 //   out = softmax(q k^T * scale) v          (CrossAttention.forward with context=None, ldm/attention.py:86-128)
 //
-// One CTA per (head, sample).  The head's K (rows = keys) and V^T (rows = head dims) are staged once in shared
-// memory as TF32 hi/lo pairs in the UMMA K-major SWIZZLE_128B layout (a key's 32 dims, or 32 keys of one dim,
-// are exactly one 128-byte swizzle row).  Then, per tile of 128 queries:
+// One CTA per (head, sample).  The head's K (rows = keys) and [V_hi | V_lo]^T (rows = head dims, hi then lo) are staged once
+// in shared memory as TF32 hi/lo in the UMMA K-major SWIZZLE_128B layout (a key's 32 dims, or 32 keys of one dim, are
+// exactly one 128-byte swizzle row); all global loads of a staging batch are issued before the first shared store.
+// Then, per tile of 128 queries (the next tile's Q rows are prefetched into registers):
 //   1. Q hi/lo -> smem;  S(128 x Tk) = Q K^T with 3xTF32 (hi*hi + lo*hi + hi*lo) into TMEM (N = 256 + rest)
-//   2. each of 128 threads owns one query row (= TMEM lane): row max over the valid keys, then per chunk of
-//      32 keys p = exp(s*scale - max), row sum, TF32 hi/lo of p -> smem (A operand)
-//   3. O(128 x 32) += P_chunk V_chunk, again 3xTF32, accumulated in TMEM
-//   4. O / rowsum -> global
-// The softmax threads and the single MMA-issuing thread hand work back and forth through two mbarriers
-// (operands ready / MMAs complete); tensor work and softmax of one CTA do not overlap (one CTA per SM fills
-// the shared memory), the chip-level parallelism comes from the 6 x samples CTAs.
+//   2. four threads per query row (= TMEM lane; 16 softmax warps): row max over the valid keys, then per chunk of
+//      32 keys p = exp(s*scale - max), row sum, TF32 hi/lo of p -> smem (A operand); only the last chunk masks keys
+//   3. O[:, 0:32] += P_hi V_hi + P_lo V_hi and O[:, 32:64] += P_hi V_lo as TWO MMAs per k-step (P_hi x [V_hi | V_lo] is one
+//      N = 64 MMA): these small MMAs are bound by the single issuing thread, not by the tensor pipe
+//   4. (O[:, 0:32] + O[:, 32:64]) / rowsum -> global
+// The softmax threads and the single MMA-issuing thread hand work back and forth through mbarriers (operands ready /
+// MMAs complete, ping-pong P buffers); one CTA per SM fills the shared memory, the chip-level parallelism comes from the
+// 6 x samples CTAs.
 #pragma once
 #include "gemm_tc.cuh"
 

@@ -3,23 +3,26 @@
 //   out[m, n] = epilogue( sum_k  load(m, k) * W[n, k] )
 //
 // Same loaders / epilogues as gemm_simt.cuh (normalisation + activation folded into the A operand,
-// bias / residual / GEGLU folded into the epilogue), but the contraction runs on the tensor cores:
+// bias / residual / GEGLU folded into the epilogue), but the contraction runs on the tensor cores.
+// Persistent, one CTA per SM, 576 threads, warp-specialised (details at gemm_tc_kernel below):
 //
-//   * A (activations): 4 loader warps read fp32 from global (coalesced 16-byte chunks), apply the
-//     loader transform, split every value into TF32 hi + TF32 lo  (x = hi + lo + O(2^-22 x)) and write
-//     both into shared memory in the UMMA canonical K-major SWIZZLE_128B layout (32 fp32 = 128 B per row,
-//     16-byte chunk index XOR row%8), followed by fence.proxy.async + mbarrier arrive.
+//   * A (activations): 8 producer warps cp.async 16-byte chunks of fp32 straight into a 5-deep ring of "hi" stages in
+//     the UMMA canonical K-major SWIZZLE_128B layout (32 fp32 = 128 B per row, 16-byte chunk index XOR row%8); the raw
+//     fp32 IS the TF32 hi operand (the tensor core ignores the low 13 mantissa bits).  In place they apply the loader
+//     transform (if any) and write the TF32 lo part (x - hi, 3 ALU instructions per value: tf32_split4) into a separate
+//     2-deep lo ring, then fence.proxy.async + mbarrier arrive.  Four chunks of global loads stay in flight.
 //   * B (weights): pre-split and pre-swizzled on the host into ready-to-use tile images, one contiguous
 //     block per (n-tile, k-chunk); a single cp.async.bulk (TMA engine, UBLKCP) per stage lands it and
 //     completes the stage's mbarrier transaction count.
-//   * MMA: one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) with the accumulator in
-//     TMEM.  NSPLIT == 3 issues hi*hi + lo*hi + hi*lo ("3xTF32": fp32-level accuracy, which is what keeps
+//   * MMA: one elected thread issues tcgen05.mma.kind::tf32 (M=128, N<=BN, K=8) into one of two TMEM accumulators.
+//     NSPLIT == 3 issues hi*hi + lo*hi + hi*lo ("3xTF32": fp32-level accuracy, which is what keeps
 //     the path inside the reference's fp32 tolerance); NSPLIT == 1 issues hi*hi only.
-//     tcgen05.commit releases the stage back to the producers and finally signals the epilogue.
-//   * Epilogue: the 4 loader warps read their 32 TMEM lanes (tcgen05.ld 32x32b.x16), apply the epilogue and
-//     store.
+//     tcgen05.commit releases the stages back to the producers and finally signals the epilogue.
+//   * Epilogue: 8 warps drain the other accumulator (tcgen05.ld 32x32b.x16), transpose through shared memory for
+//     sector-coalesced global I/O, apply the epilogue (residual prefetched two chunks ahead) and store.
+//   * Scheduling: contiguous runs of tiles per CTA; the T % G leftover tiles are cut along N into slivers for idle CTAs.
 //
-// One CTA = one 128 x BN output tile; STAGES-deep mbarrier pipeline over K in chunks of 32.
+// Measured history of the pipeline (what starved what, and the fixes): profiles/r1_gemm_pipeline.md.
 #pragma once
 #include <cstring>
 #include <vector>
