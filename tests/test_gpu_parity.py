@@ -509,3 +509,26 @@ def test_gemm_tail_slivers_match_fp32(gpu_model):
     e = maxdiff(outs["tf32x3"], outs["fp32"])
     print("tail slivers tf32x3 vs fp32", e)
     assert e < 2e-4
+
+
+def test_full_size_forward_tc_vs_fp32(gpu_model):
+    """BASELINE configs[2] shape: one UNet forward of 128 samples x 300 frames (38 400 rows = 300 / 900 / 2400 GEMM tiles on 148
+    SMs: every tail-sliver width the production run uses, the 3-tile attention, the 4-CTA-cluster GroupNorm) in tf32x3 against
+    the fp32 FFMA kernels of the same engine.  Tolerance 2e-4 (block-activation bound of the precision-mode test)."""
+    m = gpu_model()
+    eng = m._engine(torch.device(DEV))
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(128, 300, 32, generator=g).to(DEV)
+    ctx = torch.randn(128, 300, 768, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (128,), generator=g)
+    outs = {}
+    for mode in ("tf32x3", "fp32"):
+        eng.set_precision(mode, 2048, "fp32")
+        try:
+            outs[mode] = eng.denoiser_forward(x, t, ctx).cpu()
+        finally:
+            eng.set_precision(m.precision, m.tc_min_rows, m.encoder_precision)
+    e = maxdiff(outs["tf32x3"], outs["fp32"])
+    print("full-size forward tf32x3 vs fp32", e)
+    assert bool(torch.isfinite(outs["tf32x3"]).all())
+    assert e < 2e-4

@@ -234,3 +234,21 @@ def test_ddpm_scheduler_step_table_and_oracle():
     t = 500
     v64 = (1 - ac[t - 1]) / (1 - ac[t]) * (1 - ac[t] / ac[t - 1])
     assert abs(float(S.ddpm_step_table(sch, [t])[0][4]) - float(v64**0.5)) < 1e-6
+
+
+def test_batched_csv_is_byte_identical_to_reference_writer(tmp_path):
+    """save_blendshape_coeffs_batch (8(f) rank 1) writes, per clip, exactly the bytes of the reference's pandas writer."""
+    from said_b200.util.blendshape import DEFAULT_BLENDSHAPE_CLASSES as C
+    from said_b200.util.blendshape import save_blendshape_coeffs, save_blendshape_coeffs_batch
+
+    rng = np.random.default_rng(0)
+    x = rng.random((3, 50, 32)).astype(np.float32)
+    x[0, 0, :5] = [0.0, 1.0, 1e-5, 0.5, 1e-7]
+    x[1, 3, 2] = np.float32(1 / 3)
+    x[2] = np.clip(x[2] * 3 - 1, 0, 1)               # plenty of exact 0 / 1 entries, like a clamped result
+    save_blendshape_coeffs_batch(x, C, [str(tmp_path / f"b{i}.csv") for i in range(3)])
+    for i in range(3):
+        save_blendshape_coeffs(x[i], C, str(tmp_path / f"r{i}.csv"))
+        assert (tmp_path / f"b{i}.csv").read_bytes() == (tmp_path / f"r{i}.csv").read_bytes()
+    with pytest.raises(ValueError):
+        save_blendshape_coeffs_batch(x, C, ["only-one.csv"])
