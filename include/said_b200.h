@@ -118,7 +118,7 @@ SAID_API int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int
 SAID_API long long said_launch_count(const said_engine* e);
 
 /* Diagnostics: average milliseconds of the tcgen05 GEMM (N = 192, plain loader, M x K activations) over
- * `iters` launches on scratch buffers; dbg bits disable parts of the kernel (1 A loads, 2 weight copies,
+ * `iters` launches on scratch buffers; dbg bits disable parts of the kernel (2 weight copies,
  * 4 epilogue I/O, 8 MMAs) to attribute time.  Synchronises. */
 SAID_API int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int with_residual, int dbg, int iters, float* ms_out);
 

@@ -7,4 +7,4 @@ from said_b200._lib import Engine
 
 eng = Engine(torch.device("cuda:0"))
 for K in (1152, 192):
-    print(K, eng.op_gemm_tc_bench(38400, K, 3, True, 16, 1))
+    print(K, eng.op_gemm_tc_bench(38400, K, 3, True, 0, 1))
