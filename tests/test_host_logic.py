@@ -252,3 +252,57 @@ def test_batched_csv_is_byte_identical_to_reference_writer(tmp_path):
         assert (tmp_path / f"b{i}.csv").read_bytes() == (tmp_path / f"r{i}.csv").read_bytes()
     with pytest.raises(ValueError):
         save_blendshape_coeffs_batch(x, C, ["only-one.csv"])
+
+
+def _gemm_tc_items(M, N, G, BN=192, BM=128):
+    """Python replica of the work decomposition of tc::gemm_tc_kernel (said_b200/csrc/gemm_tc.cuh, "Tail balancing"):
+    returns, per CTA, its list of (row tile, column tile, first column, width)."""
+    n_tiles = (N + BN - 1) // BN
+    total = ((M + BM - 1) // BM) * n_tiles
+    G = min(G, total)
+    tq, tr = divmod(total, G)
+    S = 1
+    if BN == 192 and tq >= 1 and tr > 0:
+        for c in (12, 6, 4, 3, 2):
+            if c * tr <= G:
+                S = c
+                break
+    out = []
+    for cta in range(G):
+        items = []
+        if S > 1:
+            for i in range(tq):
+                t = cta * tq + i
+                items.append((t // n_tiles, t % n_tiles, 0, BN))
+            if cta < tr * S:
+                t = G * tq + cta // S
+                items.append((t // n_tiles, t % n_tiles, (cta % S) * (BN // S), BN // S))
+        else:
+            n = tq + (1 if cta < tr else 0)
+            t0 = cta * tq + min(cta, tr)
+            for i in range(n):
+                t = t0 + i
+                items.append((t // n_tiles, t % n_tiles, 0, BN))
+        out.append(items)
+    return out
+
+
+@pytest.mark.parametrize("M,N", [(38400, 192), (19200, 192), (38400, 576), (38400, 1536), (19200, 576), (37888, 192),
+                                 (128 * 149, 192), (128 * 221, 192), (128 * 295, 1536), (4800, 192), (600, 576)])
+def test_gemm_tile_and_sliver_decomposition_covers_output_once(M, N):
+    """Every (row tile, 16-column group) of the output is produced by exactly one work item, slivers are multiples of 16
+    columns, and no CTA gets more than ceil(tiles / CTAs) items (the point of cutting the leftover tiles)."""
+    G = 148
+    per_cta = _gemm_tc_items(M, N, G)
+    seen = {}
+    for items in per_cta:
+        for mt, nt, n0, nw in items:
+            assert nw % 16 == 0 and 16 <= nw <= 192 and n0 % 16 == 0 and n0 + nw <= 192
+            for c in range(n0 // 16, (n0 + nw) // 16):
+                key = (mt, nt, c)
+                assert key not in seen
+                seen[key] = True
+    rows, cols = (M + 127) // 128, (N + 191) // 192
+    assert len(seen) == rows * cols * 12
+    total = rows * cols
+    assert max(len(i) for i in per_cta) <= -(-total // min(G, total))
