@@ -116,6 +116,9 @@ SAID_API int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int
 
 /* Number of kernels this engine has launched (graph replays counted node by node). */
 SAID_API long long said_launch_count(const said_engine* e);
+/* Number of times said_denoise had to capture + instantiate its per-step CUDA graph (the instantiated graph is cached and
+ * replayed by later calls whose shapes, scalars, per-step user tensors and workspaces are unchanged). */
+SAID_API long long said_graph_captures(const said_engine* e);
 
 /* Diagnostics: average milliseconds of the tcgen05 GEMM (N = 192, plain loader, M x K activations) over
  * `iters` launches on scratch buffers; dbg bits disable parts of the kernel (2 weight copies,

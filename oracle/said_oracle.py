@@ -151,8 +151,8 @@ def ddpm_step(
 def ddim_add_noise(x: torch.Tensor, noise: torch.Tensor, t, alphas_cumprod: torch.Tensor) -> torch.Tensor:
     ac = alphas_cumprod.to(dtype=x.dtype)
     t = torch.as_tensor(t, dtype=torch.long).reshape(-1)
-    sa = (ac[t] ** 0.5).reshape(-1, *([1] * (x.dim() - 1)))
-    sb = ((1 - ac[t]) ** 0.5).reshape(-1, *([1] * (x.dim() - 1)))
+    sa = (ac[t] ** 0.5).reshape(-1, *([1] * (x.dim() - 1))).to(x.device)
+    sb = ((1 - ac[t]) ** 0.5).reshape(-1, *([1] * (x.dim() - 1))).to(x.device)
     return sa * x + sb * noise
 
 
@@ -172,9 +172,9 @@ def rescale_noise_cfg(noise_cfg: torch.Tensor, noise_pred_text: torch.Tensor, gu
 def timestep_embedding(timesteps: torch.Tensor, dim: int, dtype: torch.dtype) -> torch.Tensor:
     """``ldm/util.py:66-90``: ``[cos(t f) | sin(t f)]``, ``f_k = exp(-ln(1e4) k / half)``."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
     if dtype == torch.float64:
-        freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float64) / half)
+        freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float64) / half).to(timesteps.device)
         args = timesteps[:, None].to(torch.float64) * freqs[None]
     else:
         args = timesteps[:, None].float() * freqs[None]
@@ -198,11 +198,12 @@ def _resblock(sd: SD, p: str, x: torch.Tensor, emb: torch.Tensor) -> torch.Tenso
     return x + h
 
 
-def alignment_mask(batch: int, x_len: int, c_len: int, pad: int = 1) -> torch.Tensor:
-    """``BasicTransformerBlock._forward`` alignment bias (``attention.py:170-189``): True = masked."""
+def alignment_mask(batch: int, x_len: int, c_len: int, pad: int = 1, device=None) -> torch.Tensor:
+    """``BasicTransformerBlock._forward`` alignment bias (``attention.py:170-189``): True = masked.  Built on ``device`` with
+    one slice-assign per query frame, exactly like the reference (on a GPU that is x_len tiny kernel launches per block)."""
     ratio = c_len / x_len
     half = ratio / 2 + pad
-    mask = torch.ones(batch, x_len, c_len, dtype=torch.bool)
+    mask = torch.ones(batch, x_len, c_len, dtype=torch.bool, device=device)
     for i in range(x_len):
         mid = (i + 0.5) * ratio
         lo = max(round(mid - half), 0)
@@ -244,7 +245,7 @@ def _transformer(sd: SD, p: str, x: torch.Tensor, context: torch.Tensor, heads: 
     x = _attention(sd, tb + "attn1.", F.layer_norm(x, (c,), sd[tb + "norm1.weight"], sd[tb + "norm1.bias"], 1e-5), None, None, heads) + x
     if taps is not None:
         taps[p + "after_attn1"] = x
-    mask = alignment_mask(x.shape[0], x.shape[1], context.shape[1])
+    mask = alignment_mask(x.shape[0], x.shape[1], context.shape[1], device=x.device)
     x = _attention(sd, tb + "attn2.", F.layer_norm(x, (c,), sd[tb + "norm2.weight"], sd[tb + "norm2.bias"], 1e-5), context, mask, heads) + x
     if taps is not None:
         taps[p + "after_attn2"] = x
@@ -473,7 +474,7 @@ def inference(
         if save_intermediate:
             intermediates.append((latents / latent_scale).clone())
         x_in = torch.cat([latents] * 2) if do_cfg else latents
-        ts = torch.full((x_in.shape[0],), int(t), dtype=torch.long)
+        ts = torch.full((x_in.shape[0],), int(t), dtype=torch.long, device=x_in.device)
         pred = denoiser_forward(sd, x_in, ts, emb)
         if do_cfg:
             u, c = pred.chunk(2)

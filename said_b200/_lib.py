@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "said_op_self_attention",
     "said_op_self_attention_tc",
     "said_launch_count",
+    "said_graph_captures",
     "said_op_gemm_tc_bench",
     "said_set_precision",
     "said_profile_begin",
@@ -109,6 +110,8 @@ def load_library() -> ctypes.CDLL:
     lib.said_op_self_attention_tc.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.said_launch_count.argtypes = [vp]
     lib.said_launch_count.restype = ctypes.c_longlong
+    lib.said_graph_captures.argtypes = [vp]
+    lib.said_graph_captures.restype = ctypes.c_longlong
     lib.said_set_precision.argtypes = [vp, ci, ci, ci]
     lib.said_op_gemm_tc_bench.argtypes = [vp, ci, ci, ci, ci, ci, ci, ctypes.POINTER(cf)]
     lib.said_profile_begin.argtypes = [vp]
@@ -179,6 +182,10 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(self.lib.said_launch_count(self._h))
+
+    @property
+    def graph_captures(self) -> int:
+        return int(self.lib.said_graph_captures(self._h))
 
     PROFILE_FAMILIES = ("gemm_conv3", "gemm_layernorm", "gemm_plain", "self_attention", "cross_attention3",
                         "gn_stats", "cfg_ddim_step", "other")

@@ -55,6 +55,7 @@ struct HostTensor {
     int64_t numel() const { return (int64_t)data.size(); }
 };
 
+unsigned long long g_alloc_gen = 0;   // bumped whenever a workspace moves: cached step graphs bake workspace pointers
 struct DevBuf {
     float* p = nullptr;
     size_t cap = 0;   // floats
@@ -63,6 +64,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
+        ++g_alloc_gen;
         cudaError_t e = cudaMalloc((void**)&p, n * sizeof(float));
         if (e == cudaSuccess) cap = n;
         return e;
@@ -225,7 +227,25 @@ struct said_engine {
     size_t c0_partial_cap = 0;
     int* step_ctr = nullptr;
     int ctx_B = 0, ctx_T = 0, ctx_uncond = 0;
+    // The instantiated step graph is kept across denoise() calls and replayed as long as everything baked into its
+    // kernel nodes is unchanged (shapes, scalars, user tensors read per step, workspace addresses, precision).
+    struct GraphKey {
+        int B, T, do_cfg, n_steps, pred_type, scheduler, precision, tc_min_rows;
+        float gscale, grescale, latent_scale;
+        const void *eta_noise, *edit_noise, *mask, *intermediates;
+        unsigned long long alloc_gen;
+    };
+    GraphKey graph_key{};
+    long long graph_launches = 0;     // kernel nodes in the cached graph
+    long long graph_captures = 0;     // how many times a step graph was captured (tests: the cache works)
     cudaGraphExec_t graph_exec = nullptr;
+    void drop_graph() {
+        if (graph_exec) {
+            cudaGraphExecDestroy(graph_exec);
+            graph_exec = nullptr;
+        }
+    }
+    DevBuf result_buf;
 
     ~said_engine() {
         cudaSetDevice(device);
@@ -633,6 +653,7 @@ int said_engine::commit_encoder() {
 int said_engine::commit() {
     CK(cudaSetDevice(device));
     CK(cudaDeviceSynchronize());
+    drop_graph();                     // its nodes hold weight pointers
     for (float* p : arena) cudaFree(p);
     arena.clear();
     tcmap.clear();
@@ -1254,7 +1275,8 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         sp.mask = a.mask_dev;
         sp.intermediates = a.intermediates_dev;
         sp.latent_scale = a.latent_scale;
-        sp.result = a.result_dev;
+        CK(result_buf.ensure((size_t)tot));
+        sp.result = result_buf.p;       // engine-owned so that the cached graph does not depend on the caller's output tensor
         if (sp.mask && !sp.edit_noise) return fail("denoise: mask given without edit noise");
 
         auto one_step = [&]() -> int {
@@ -1267,29 +1289,42 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
             return 0;
         };
         if (a.use_graph && a.n_steps > 1) {
-            if (graph_exec) {
-                CK(cudaStreamSynchronize(st));
-                cudaGraphExecDestroy(graph_exec);
-                graph_exec = nullptr;
+            GraphKey key;
+            memset(&key, 0, sizeof(key));
+            key.B = B; key.T = T; key.do_cfg = a.do_cfg; key.n_steps = a.n_steps; key.pred_type = a.prediction_type;
+            key.scheduler = a.scheduler; key.precision = precision; key.tc_min_rows = tc_min_rows;
+            key.gscale = a.guidance_scale; key.grescale = a.guidance_rescale; key.latent_scale = a.latent_scale;
+            key.eta_noise = a.eta_noise_dev; key.edit_noise = a.edit_noise_dev; key.mask = a.mask_dev;
+            key.intermediates = a.intermediates_dev;
+            key.alloc_gen = g_alloc_gen;
+            if (!graph_exec || memcmp(&key, &graph_key, sizeof(key)) != 0) {
+                if (graph_exec) {
+                    CK(cudaStreamSynchronize(st));
+                    drop_graph();
+                }
+                const long long before = launches;
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const int rc = one_step();
+                cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (rc != 0) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return rc;
+                }
+                CK(ce);
+                graph_launches = launches - before;
+                launches = before;
+                CK(cudaGraphInstantiate(&graph_exec, graph, 0));
+                cudaGraphDestroy(graph);
+                graph_key = key;
+                ++graph_captures;
             }
-            const long long before = launches;
-            cudaGraph_t graph = nullptr;
-            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int rc = one_step();
-            cudaError_t ce = cudaStreamEndCapture(st, &graph);
-            if (rc != 0) {
-                if (graph) cudaGraphDestroy(graph);
-                return rc;
-            }
-            CK(ce);
-            const long long per_step = launches - before;
-            CK(cudaGraphInstantiate(&graph_exec, graph, 0));
-            cudaGraphDestroy(graph);
             for (int s = 0; s < a.n_steps; ++s) CK(cudaGraphLaunch(graph_exec, st));
-            launches = before + per_step * a.n_steps;
+            launches += graph_launches * a.n_steps;
         } else {
             for (int s = 0; s < a.n_steps; ++s) CKI(one_step());
         }
+        CK(cudaMemcpyAsync(a.result_dev, result_buf.p, (size_t)tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     if (a.latents_out_dev)
         CK(cudaMemcpyAsync(a.latents_out_dev, lat.p, (size_t)tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1479,6 +1514,7 @@ int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int B, int T
 }
 
 long long said_launch_count(const said_engine* e) { return e ? e->launches : 0; }
+long long said_graph_captures(const said_engine* e) { return e ? e->graph_captures : 0; }
 
 int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int with_residual, int dbg, int iters, float* ms_out) {
     // diagnostics: times the tcgen05 GEMM (N = 192, plain loader) on scratch buffers with parts of it disabled

@@ -25,6 +25,9 @@
 // Measured history of the pipeline (what starved what, and the fixes): profiles/r1_gemm_pipeline.md.
 #pragma once
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -872,16 +875,29 @@ gemm_tca_kernel(TcDims d, AL al, const float* __restrict__ Wp, EP ep) {
     }
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: one process may drive several GPUs (one engine
+// each), so "already configured" is remembered per (kernel, device), not per kernel.
+inline cudaError_t configure_once(const void* kern, int smem_bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({kern, dev})) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) done.insert({kern, dev});
+    return e;
+}
+
 template <int BN, int NSPLIT, class AL, class EP>
 inline cudaError_t launch_gemm_tca(cudaStream_t st, int num_sms, int M, int N, int K, const AL& al, const float* Wp,
                                    int w_block_floats, const EP& ep) {
     using Cfg = TcaCfg<BN, NSPLIT>;
-    static bool configured = false;
     auto kern = gemm_tca_kernel<BN, NSPLIT, AL, EP>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    {
+        cudaError_t e = configure_once((const void*)kern, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     TcDims d{M, N, K, w_block_floats, 0};
     const int total_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
@@ -933,12 +949,10 @@ template <int BN, int NSPLIT, class AL, class EP>
 inline cudaError_t launch_gemm_tc(cudaStream_t st, int num_sms, int M, int N, int K, const AL& al, const float* Wp,
                                   int w_block_floats, const EP& ep, int dbg = 0, bool pdl = false) {
     using Cfg = TcCfg<BN, NSPLIT>;
-    static bool configured = false;
     auto kern = gemm_tc_kernel<BN, NSPLIT, AL, EP>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    {
+        cudaError_t e = configure_once((const void*)kern, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     TcDims d{M, N, K, w_block_floats, dbg};
     const int total_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);

@@ -32,8 +32,9 @@ def draw_sharded_noise(shape, seed: int, device, lo: int, hi: int) -> torch.Tens
     return full[lo:hi].contiguous()
 
 
-def gather_clips(local: torch.Tensor, batch: int, group=None) -> torch.Tensor:
-    """All-gather ragged per-rank results ``(b_r, ...)`` into ``(batch, ...)`` on every rank."""
+def gather_clips(local: torch.Tensor, batch: int, group=None, dst: Optional[int] = None) -> Optional[torch.Tensor]:
+    """Gather ragged per-rank results ``(b_r, ...)`` into ``(batch, ...)``: on every rank (all-gather, ``dst=None``) or
+    on rank ``dst`` only (the other ranks return ``None``) -- a caller that writes the CSVs on one rank needs no more."""
     if not (dist.is_available() and dist.is_initialized()):
         return local
     world = dist.get_world_size(group)
@@ -44,8 +45,14 @@ def gather_clips(local: torch.Tensor, batch: int, group=None) -> torch.Tensor:
     max_b = max(hi - lo for lo, hi in sizes)
     pad = torch.zeros((max_b,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
+    if dst is None:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+    else:
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, bufs, dst=dst, group=group)
+        if rank != dst:
+            return None
     return torch.cat([bufs[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 

@@ -29,6 +29,12 @@ LARGE_FAMILY_CONFIG = dict(
     feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True,
     num_conv_pos_embeddings=128, num_conv_pos_embedding_groups=16, vocab_size=32,
 )
+# The real wav2vec2-large (facebook/wav2vec2-large-960h-lv60 architecture): 1024 / 16 heads / 24 layers / 4096, 315 M parameters.
+LARGE_FULL_CONFIG = dict(
+    hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+    feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True,
+    num_conv_pos_embeddings=128, num_conv_pos_embedding_groups=16, vocab_size=32,
+)
 
 
 def main():
@@ -42,7 +48,11 @@ def main():
     sys.modules["said.model"] = model
     ref = importlib.import_module("said.model.wav2vec2")
 
-    cfg = Wav2Vec2Config(**LARGE_FAMILY_CONFIG)
+    for conf, fname in ((LARGE_FAMILY_CONFIG, "audio_encoder_large_family_1s.npz"), (LARGE_FULL_CONFIG, "audio_encoder_large_full_1s.npz")):
+        make_one(ref, Wav2Vec2Config(**conf), fname)
+
+
+def make_one(ref, cfg, fname):
     torch.manual_seed(0)
     m = ref.ModifiedWav2Vec2Model(cfg).eval()
     sd = {"audio_encoder." + k: v.detach().clone() for k, v in m.state_dict().items()}
@@ -56,7 +66,7 @@ def main():
     print("oracle vs reference:", d_or, " fp32 vs fp64 floor:", d_64, " mean |emb|:", float(emb.abs().mean()))
     assert d_or < 1e-4
     np.savez_compressed(
-        os.path.join(HERE, "audio_encoder_large_family_1s.npz"), wave=wave.numpy(), emb=emb.numpy(),
+        os.path.join(HERE, fname), wave=wave.numpy(), emb=emb.numpy(),
         emb64=emb_o64.float().numpy(), weights_abs_sum=np.float64(sum(float(v.double().abs().sum()) for v in sd.values())),
         oracle_vs_ref=np.float64(d_or), fp32_vs_fp64=np.float64(d_64))
 

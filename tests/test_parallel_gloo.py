@@ -43,7 +43,11 @@ def _worker(rank, world, port, B, q):
     mask = (torch.rand(B, 60, 32, generator=g) > 0.5).float()
     a = sharded_inference(_Stub, wave, seed=11, runner=_runner)
     b = sharded_inference(_Stub, wave, seed=11, init_samples=init, mask=mask, runner=_runner)
+    lo, hi = shard_bounds(B, world, rank)
+    c = gather_clips(a[lo:hi].contiguous(), B, dst=0)       # gather on one rank only
+    assert (c is None) == (rank != 0)
     if rank == 0:
+        assert torch.equal(c, a)
         q.put((a, b))
     dist.barrier()
     dist.destroy_process_group()
