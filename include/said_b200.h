@@ -98,11 +98,17 @@ SAID_API int said_denoise(said_engine* e, const said_denoise_args* args, void* s
 
 /* One denoiser forward: SAID.forward / UNet1DConditionModel.forward (reference
  * said/model/diffusion.py:127-155, said/model/unet_1d_condition.py:51-77).
- * x_dev (Bp,T,C), timesteps_host (Bp) as float, ctx_dev (Bp,T,ctx_dim) -> out_dev (Bp,T,C).
+ * x_dev (Bp,T,C), timesteps_host (Bp) as float, ctx_dev (Bp,T_ctx,ctx_dim) -> out_dev (Bp,T,C).  T_ctx may differ from T: the
+ * cross-attention then uses the reference's general alignment window (said/model/ldm/attention.py:170-189).
  * taps_dev (optional, 10 x (Bp,T,192)): outputs of the ten UNet blocks in execution order (parity tests).
  * Synchronises the stream before returning. */
 SAID_API int said_denoiser_forward(said_engine* e, const float* x_dev, const float* timesteps_host, const float* ctx_dev,
-                          int Bp, int T, float* out_dev, float* taps_dev, void* stream);
+                          int Bp, int T, int T_ctx, float* out_dev, float* taps_dev, void* stream);
+
+/* Synchronises `stream` and returns (and clears) the engine's device-side status word: bit 0 = an activation reached fp16's
+ * range limit (|x| >= 65000) on the fp16x3 path, whose operands are fp16 hi/lo pairs -- the results of that call are invalid;
+ * rerun with precision mode 1 (3xTF32).  The Python layer calls this at the end of every inference() and raises. */
+SAID_API int said_check_status(said_engine* e, void* stream, int* status_out);
 
 /* Unit entry points used by the parity tests (each is one kernel of the path). */
 SAID_API int said_op_ddim_step(said_engine* e, const float* pred_dev, float* latents_dev, int B, int n, int do_cfg,
@@ -110,6 +116,13 @@ SAID_API int said_op_ddim_step(said_engine* e, const float* pred_dev, float* lat
                       const float* eta_noise_dev, int scheduler, void* stream);
 SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B, int T, int heads, int head_dim,
                            float* out_dev, void* stream);
+
+/* Unit entry point of the fp16x3 GEMM (gemm_h.cuh): out (M,N) = sum over taps of A[m + tap - (taps-1)/2, :] . Wt[tap*Cin:(tap+1)*Cin, :]
+ * + bias, rows outside [0, M) read as zero (Conv1d padding); a_dev (M,Cin) fp32 is converted to the fp16 hi/lo pair format on
+ * the device, wt_host (taps*Cin, N) is the K-major weight matrix, packed and uploaded by the call.  taps 1 or 3, Cin % 64 == 0,
+ * N = 32 or a multiple of 192.  Synchronises. */
+SAID_API int said_op_gemm_h(said_engine* e, const float* a_dev, int M, int Cin, int taps, const float* wt_host, int N,
+                            const float* bias_dev, float* out_dev, void* stream);
 
 /* The tcgen05 (3xTF32) self-attention kernel: head_dim 32, T <= 304 (longer sequences use the FFMA kernel). */
 SAID_API int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int B, int T, int heads, float* out_dev, void* stream);
@@ -128,7 +141,10 @@ SAID_API int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int
 /* Contraction precision of the denoiser's Linear / Conv1d layers:
  *   0  IEEE fp32 FFMA (CUDA cores);
  *   1  tcgen05 tensor cores, 3xTF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulate): fp32-level accuracy [default];
- *   2  tcgen05 tensor cores, single TF32 pass (what the reference gets from cuDNN for its convs on a GPU).
+ *   2  tcgen05 tensor cores, single TF32 pass (what the reference gets from cuDNN for its convs on a GPU);
+ *   3  tcgen05 tensor cores, fp16 hi/lo operand pairs, three passes (hi*hi + lo*hi + hi*lo, fp32 accumulate), operands
+ *      pre-split by their producers and loaded by TMA: the accuracy of mode 1 at twice its tensor-core rate; activations
+ *      must stay below fp16's range (65504), checked on the device (said_check_status).
  * GEMMs with fewer than tc_min_rows rows (<= 0: keep the current threshold) stay on the FFMA kernel, so results
  * are bit-reproducible across batch sizes only within one regime (mode 0 is reproducible across all sizes).
  * encoder_mode: the same choice for the Wav2Vec2 encoder's GEMMs (default 0: the encoder runs once per clip, and

@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = (
     "said_prepare_context",
     "said_denoise",
     "said_denoiser_forward",
+    "said_check_status",
+    "said_op_gemm_h",
     "said_op_ddim_step",
     "said_op_self_attention",
     "said_op_self_attention_tc",
@@ -104,7 +106,9 @@ def load_library() -> ctypes.CDLL:
     lib.said_normalize_audio.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.said_prepare_context.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.said_denoise.argtypes = [vp, ctypes.POINTER(DenoiseArgs), vp]
-    lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp]
+    lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, vp, vp]
+    lib.said_check_status.argtypes = [vp, vp, ctypes.POINTER(ci)]
+    lib.said_op_gemm_h.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, vp, vp]
     lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, ci, vp]
     lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
     lib.said_op_self_attention_tc.argtypes = [vp, vp, ci, ci, ci, vp, vp]
@@ -190,7 +194,7 @@ class Engine:
     PROFILE_FAMILIES = ("gemm_conv3", "gemm_layernorm", "gemm_plain", "self_attention", "cross_attention3",
                         "gn_stats", "cfg_ddim_step", "other")
 
-    PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+    PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "fp16x3": 3}
 
     def set_precision(self, mode: str, tc_min_rows: int = 0, encoder_mode: str = "fp32") -> None:
         if mode not in self.PRECISIONS or encoder_mode not in self.PRECISIONS:
@@ -286,11 +290,9 @@ class Engine:
         x = _check_dev(x, self.device, "noisy samples")
         ctx = _check_dev(ctx, self.device, "audio embedding")
         Bp, T, C = x.shape
-        if ctx.shape[0] != Bp or ctx.shape[1] != T:
-            raise ValueError(
-                f"audio embedding must be (batch={Bp}, frames={T}, dim); got {tuple(ctx.shape)} "
-                "(the aligned cross-attention kernel needs one feature frame per coefficient frame)"
-            )
+        if ctx.shape[0] != Bp:
+            raise ValueError(f"audio embedding must have batch {Bp}; got {tuple(ctx.shape)}")
+        T_ctx = int(ctx.shape[1])
         ts = np.ascontiguousarray(timesteps.detach().to("cpu").reshape(-1).numpy().astype(np.float32))
         if ts.shape[0] == 1 and Bp > 1:
             ts = np.repeat(ts, Bp)
@@ -299,9 +301,21 @@ class Engine:
         out = torch.empty_like(x)
         tap_buf = torch.empty((10, Bp, T, 192), dtype=torch.float32, device=self.device) if taps else None
         with torch.cuda.device(self.device):
-            self._call(self.lib.said_denoiser_forward(self._h, x.data_ptr(), ts.ctypes.data, ctx.data_ptr(), Bp, T,
+            self._call(self.lib.said_denoiser_forward(self._h, x.data_ptr(), ts.ctypes.data, ctx.data_ptr(), Bp, T, T_ctx,
                                                       out.data_ptr(), _ptr(tap_buf), self._stream()))
+        self.check_status()
         return (out, tap_buf) if taps else out
+
+    def check_status(self) -> None:
+        """Synchronise and raise if the device-side status word is set (fp16x3 path: an activation left fp16's range)."""
+        v = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_check_status(self._h, self._stream(), ctypes.byref(v)))
+        if v.value & 1:
+            raise SaidLibraryError(
+                "an activation reached fp16's range limit (|x| >= 65000) on the fp16x3 tensor-core path; the result of this call is "
+                "invalid -- rerun with model.precision = 'tf32x3' (3xTF32 operands have fp32's range)"
+            )
 
     # ------------------------------------------------------------------ unit ops (tests)
     def op_ddim_step(self, pred, latents, do_cfg, guidance_scale, guidance_rescale, prediction_type, row8, eta_noise=None, scheduler=0):
@@ -325,6 +339,19 @@ class Engine:
         out = torch.empty((B, T, heads * 32), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._call(self.lib.said_op_self_attention_tc(self._h, qkv.data_ptr(), B, T, heads, out.data_ptr(), self._stream()))
+        return out
+
+    def op_gemm_h(self, a: torch.Tensor, wt: torch.Tensor, taps: int = 1, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp16x3 GEMM unit op: a (M, Cin) on the device, wt (taps * Cin, N) K-major on the host -> (M, N)."""
+        a = _check_dev(a, self.device, "a")
+        M, Cin = a.shape
+        w = np.ascontiguousarray(wt.detach().to("cpu", torch.float32).numpy())
+        N = w.shape[1]
+        assert w.shape[0] == taps * Cin
+        b = None if bias is None else _check_dev(bias, self.device, "bias")
+        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_op_gemm_h(self._h, a.data_ptr(), M, Cin, taps, w.ctypes.data, N, _ptr(b), out.data_ptr(), self._stream()))
         return out
 
     def op_gemm_tc_bench(self, M: int, K: int, nsplit: int = 3, with_residual: bool = True, dbg: int = 0, iters: int = 10) -> float:

@@ -1,6 +1,7 @@
 // Attention kernels of the path (fp32, register-tiled, online softmax).
 #pragma once
 #include "common.cuh"
+#include "pair.cuh"
 
 namespace said {
 
@@ -33,7 +34,9 @@ constexpr size_t attention_smem_bytes() {
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
 self_attention_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int T, float scale,
-                      float* __restrict__ out, int ldo) {
+                      float* __restrict__ out, int ldo, int Tstr = 0 /*rows per sample in qkv / out (0: T)*/,
+                      __half* __restrict__ out_pair = nullptr /*write the pair tensor (ldo columns) instead of fp32*/,
+                      int* __restrict__ flag = nullptr) {
     extern __shared__ __align__(16) float smem[];
     float* Kt = smem;                               // [HD][KSTR]   keys of the current block, transposed
     float* Vs = Kt + (size_t)HD * ATT_KSTR;         // [KB][HD]
@@ -44,7 +47,8 @@ self_attention_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_of
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q0 = blockIdx.x * ATT_QTILE, h = blockIdx.y, b = blockIdx.z;
-    const float* base = qkv + (long long)b * T * ld;
+    if (Tstr == 0) Tstr = T;
+    const float* base = qkv + (long long)b * Tstr * ld;
     constexpr int V4 = HD / 4;
 
     for (int i = tid; i < ATT_QTILE * V4; i += ATT_THREADS) {
@@ -164,11 +168,17 @@ self_attention_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_of
         const int q = q0 + warp * 8 + 2 * qp + i;
         if (q >= T) continue;
         const float inv = 1.0f / (i == 0 ? l0 : l1);
-        float* orow = out + ((long long)b * T + q) * ldo + h * HD + dc * 4;
+        const long long orow_i = (long long)b * Tstr + q;
 #pragma unroll
-        for (int u = 0; u < DU; ++u)
-            st4(orow + 32 * u, make_float4(o[i][4 * u] * inv, o[i][4 * u + 1] * inv, o[i][4 * u + 2] * inv,
-                                           o[i][4 * u + 3] * inv));
+        for (int u = 0; u < DU; ++u) {
+            const float4 ov = make_float4(o[i][4 * u] * inv, o[i][4 * u + 1] * inv, o[i][4 * u + 2] * inv, o[i][4 * u + 3] * inv);
+            if (out_pair != nullptr) {
+                store_pair4(out_pair, orow_i, ldo, h * HD + dc * 4 + 32 * u, ov);
+                if (amax4(0.f, ov) > P16_LIMIT) atomicOr(flag, 1);
+            } else {
+                st4(out + orow_i * ldo + h * HD + dc * 4 + 32 * u, ov);
+            }
+        }
     }
 }
 

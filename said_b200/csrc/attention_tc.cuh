@@ -17,6 +17,7 @@
 // 6 x samples CTAs.
 #pragma once
 #include "gemm_tc.cuh"
+#include "pair.cuh"
 
 namespace said {
 namespace tc {
@@ -52,7 +53,9 @@ SAID_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int T, float scale,
-                         float* __restrict__ out, int ldo) {
+                         float* __restrict__ out, int ldo, int Tstr /*rows per sample in qkv / out*/,
+                         __half* __restrict__ out_pair /*non-null: write the pair tensor (ldo columns) instead of fp32*/,
+                         int* __restrict__ flag) {
     extern __shared__ uint8_t smem_raw[];
     const int Tk = (T + 15) / 16 * 16;
     const int nch = (T + 31) / 32;
@@ -72,7 +75,7 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = blockIdx.x, b = blockIdx.y;
-    const float* gbase = qkv + (long long)b * T * ld + h * ATC_HD;
+    const float* gbase = qkv + (long long)b * Tstr * ld + h * ATC_HD;
 
     if (tid == ATC_SM_THREADS) {
         mbar_init(bar_s_ready, ATC_SM_THREADS);
@@ -262,9 +265,18 @@ self_attention_tc_kernel(const float* __restrict__ qkv, int ld, int q_off, int k
                 const int q = qt * 128 + row;
                 if (q < T) {
                     const float inv = 1.0f / lsum;
-                    float* orow = out + ((long long)b * T + q) * ldo + h * ATC_HD + part * ATC_CP;
-                    st4(orow, make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv));
-                    st4(orow + 4, make_float4(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv));
+                    const float4 o0 = make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
+                    const float4 o1 = make_float4(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv);
+                    const long long orow_i = (long long)b * Tstr + q;
+                    if (out_pair != nullptr) {
+                        store_pair4(out_pair, orow_i, ldo, h * ATC_HD + part * ATC_CP, o0);
+                        store_pair4(out_pair, orow_i, ldo, h * ATC_HD + part * ATC_CP + 4, o1);
+                        if (amax4(amax4(0.f, o0), o1) > P16_LIMIT) atomicOr(flag, 1);
+                    } else {
+                        float* orow = out + orow_i * ldo + h * ATC_HD + part * ATC_CP;
+                        st4(orow, o0);
+                        st4(orow + 4, o1);
+                    }
                 }
             }
             tc_fence_before();                            // TMEM reads done before the next tile's MMAs overwrite S / O

@@ -25,8 +25,10 @@
 #include "diffusion_kernels.cuh"
 #include "encoder_kernels.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_h.cuh"
 #include "gemm_tc.cuh"
 #include "norm_kernels.cuh"
+#include "pair_kernels.cuh"
 
 using namespace said;
 
@@ -67,6 +69,13 @@ struct DevBuf {
         ++g_alloc_gen;
         cudaError_t e = cudaMalloc((void**)&p, n * sizeof(float));
         if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    // workspaces of the padded-row (fp16x3) path are zero-filled when (re)allocated: rows nobody writes stay finite
+    cudaError_t ensure_zero(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        cudaError_t e = ensure(n);
+        if (e == cudaSuccess) e = cudaMemset(p, 0, cap * sizeof(float));
         return e;
     }
     ~DevBuf() {
@@ -126,7 +135,11 @@ struct said_engine {
     // ---- tensor-core path: per GEMM weight, a pre-split / pre-swizzled tile image (gemm_tc.cuh)
     struct TcW { float* img; int K, N, bn; };
     std::map<const float*, TcW> tcmap;   // keyed by the SIMT "Wt" device pointer of the same weight
-    int precision = 1;                   // 0: fp32 FFMA, 1: 3xTF32 tcgen05 (fp32-level), 2: 1xTF32 tcgen05
+    int precision = 1;                   // 0: fp32 FFMA, 1: 3xTF32 tcgen05 (fp32-level), 2: 1xTF32 tcgen05, 3: fp16 hi/lo x3 tcgen05 via TMA
+    // ---- fp16x3 path (gemm_h.cuh): per GEMM weight, an fp16 hi/lo tile image pre-scaled by 2^exp
+    struct HW { uint8_t* img; int K, N, bn, exp; };
+    std::map<const float*, HW> hmap;     // keyed like tcmap
+    bool reg_h = false;                  // register_tc also builds the fp16 image (denoiser weights only)
     int register_tc(const float* key, const float* host_wt, int K, int N, int ldw) {
         const int bn = (N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : (N == 32 ? 32 : 0));
         if (bn == 0 || K % tc::BK != 0) return 0;
@@ -135,6 +148,95 @@ struct said_engine {
         float* d = nullptr;
         CKI(upload(img, &d));
         tcmap[key] = TcW{d, K, N, bn};
+        if (reg_h && K % hx::HBK == 0 && (bn == 192 || bn == 32)) {
+            std::vector<uint16_t> himg;
+            const int e = hx::pack_weights_h(host_wt, K, N, ldw, bn, himg);
+            uint8_t* hd = nullptr;
+            CK(cudaMalloc((void**)&hd, himg.size() * sizeof(uint16_t)));
+            arena.push_back(reinterpret_cast<float*>(hd));
+            CK(cudaMemcpy(hd, himg.data(), himg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            hmap[key] = HW{hd, K, N, bn, e};
+        }
+        return 0;
+    }
+    // One contraction on the fp16x3 path.  The K dimension is the concatenation of `segs`: columns [col0, col0 + ncols) of
+    // the pair tensor `src` (C columns, `rows` rows), rows shifted by row_shift (Conv1d taps).  Weight = the image of `wkey`.
+    struct HSrc { const __half* base; int C; long long rows; };
+    struct HSegSpec { HSrc src; int col0, ncols, row_shift; };
+    template <class EP>
+    int gemm_h(cudaStream_t st, int M, int N, std::initializer_list<HSegSpec> segs, const float* wkey, EP ep, int tag) {
+        auto it = hmap.find(wkey);
+        if (it == hmap.end()) return fail("fp16x3 gemm: weight image not registered");
+        const HW& w = it->second;
+        hx::HParams p;
+        memset(&p, 0, sizeof(p));
+        const __half* bases[3] = {nullptr, nullptr, nullptr};
+        int nmaps = 0, nk = 0, ns = 0;
+        for (const HSegSpec& sg : segs) {
+            if (ns >= hx::H_MAX_SEG) return fail("fp16x3 gemm: too many segments");
+            if (sg.ncols % hx::HBK != 0 || sg.col0 % 8 != 0) return fail("fp16x3 gemm: segment not a multiple of 64 columns");
+            int mi = -1;
+            for (int j = 0; j < nmaps; ++j)
+                if (bases[j] == sg.src.base) mi = j;
+            if (mi < 0) {
+                if (nmaps >= 3) return fail("fp16x3 gemm: too many source tensors");
+                if (!hx::make_pair_map(&p.maps[nmaps], sg.src.base, sg.src.C, sg.src.rows))
+                    return fail("cuTensorMapEncodeTiled failed (driver entry point unavailable or bad tensor geometry)");
+                bases[nmaps] = sg.src.base;
+                mi = nmaps++;
+            }
+            p.seg[ns++] = hx::HSeg{mi, sg.ncols / hx::HBK, sg.col0, sg.src.C, sg.row_shift};
+            nk += sg.ncols / hx::HBK;
+        }
+        if (nk * hx::HBK != w.K || N != w.N) return fail("fp16x3 gemm: shape does not match the registered weight");
+        p.M = M;
+        p.N = N;
+        p.nk = nk;
+        p.nseg = ns;
+        p.nmaps = nmaps;
+        p.w_block_bytes = 2 * w.bn * hx::HROW;
+        p.sliver = 1;
+        ep.acc_scale = std::ldexp(1.0f, -w.exp);
+        cur_tag = tag;
+        cudaError_t e = cudaErrorInvalidValue;
+        if (w.bn == 192) e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, ep, pdl);
+        else if (w.bn == 32) e = hx::launch_gemm_h<32>(st, num_sms, p, w.img, ep, pdl);
+        if (e != cudaSuccess) return fail(std::string("fp16x3 gemm launch failed: ") + cudaGetErrorString(e));
+        return after_launch(st);
+    }
+    // device-side status word: bit 0 = a pair-format producer saw |x| >= fp16 max (the fp16x3 path cannot represent it)
+    int* status_flag = nullptr;
+    // alignment band of the cross-attention (attention.py:177-189) for the current (frames, context frames)
+    int2* band_dev = nullptr;
+    int band_T = -1, band_Tc = -1, band_cap = 0;
+    int ensure_band(int T, int Tc, cudaStream_t st) {
+        if (T == band_T && Tc == band_Tc) return 0;
+        std::vector<int2> hb((size_t)T);
+        const double ratio = (double)Tc / (double)T;           // c_x_ratio
+        const double half = ratio / 2 + 1;                      // c_kh_size with pad = 1
+        for (int i = 0; i < T; ++i) {
+            const double mid = (i + 0.5) * ratio;
+            long lo = (long)std::nearbyint(mid - half), hi = (long)std::nearbyint(mid + half);   // Python round(): ties to even
+            if (lo < 0) lo = 0;
+            if (hi > Tc) hi = Tc;
+            if (hi - lo < 1 || hi - lo > XATT_MAXW)
+                return fail("cross-attention alignment window of " + std::to_string(hi - lo) + " context frames per query (context " +
+                            std::to_string(Tc) + " frames, sample " + std::to_string(T) + "): supported 1.." + std::to_string(XATT_MAXW));
+            hb[i] = make_int2((int)lo, (int)(hi - lo));
+        }
+        if (T > band_cap) {
+            if (band_dev) cudaFree(band_dev);
+            band_dev = nullptr;
+            band_cap = 0;
+            ++g_alloc_gen;
+            CK(cudaMalloc((void**)&band_dev, (size_t)T * sizeof(int2)));
+            band_cap = T;
+        }
+        CK(cudaMemcpyAsync(band_dev, hb.data(), (size_t)T * sizeof(int2), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                          // hb is a temporary
+        band_T = T;
+        band_Tc = Tc;
+        ++g_alloc_gen;                                          // the table content is baked into nothing, but keep graphs honest
         return 0;
     }
     // the tcgen05 kernel's loader threads share a row among ROW_CHUNKS lanes
@@ -146,25 +248,26 @@ struct said_engine {
     template <class AL, class EP>
     int gemm_tc_dispatch(cudaStream_t st, int M, int N, int K, const AL& al, const TcW& w, const EP& ep) {
         const int stride = 2 * w.bn * tc::BK;   // image holds hi + lo tiles
+        const bool x3 = precision == 1 || precision == 3;   // fp16x3 mode: the GEMMs that stay on these kernels run 3xTF32
         cudaError_t e = cudaErrorInvalidValue;
         if (a_in_tmem && w.bn != 128) {   // activations through TMEM (TS MMA): experimental, see gemm_tc.cuh
             if (w.bn == 192) {
-                e = precision == 1 ? tc::launch_gemm_tca<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
-                                   : tc::launch_gemm_tca<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
+                e = x3 ? tc::launch_gemm_tca<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
+                       : tc::launch_gemm_tca<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
             } else if (w.bn == 32) {
-                e = precision == 1 ? tc::launch_gemm_tca<32, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
-                                   : tc::launch_gemm_tca<32, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
+                e = x3 ? tc::launch_gemm_tca<32, 3>(st, num_sms, M, N, K, al, w.img, stride, ep)
+                       : tc::launch_gemm_tca<32, 1>(st, num_sms, M, N, K, al, w.img, stride, ep);
             }
         } else if (w.bn == 128) {
             if constexpr (std::is_same<AL, ALoadPlain>::value && std::is_same<EP, EpiStd>::value)   // encoder conv stack (N = 512)
-                e = precision == 1 ? tc::launch_gemm_tc<128, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
-                                   : tc::launch_gemm_tc<128, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
+                e = x3 ? tc::launch_gemm_tc<128, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
+                       : tc::launch_gemm_tc<128, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
         } else if (w.bn == 192) {
-            e = precision == 1 ? tc::launch_gemm_tc<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
-                               : tc::launch_gemm_tc<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
+            e = x3 ? tc::launch_gemm_tc<192, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
+                   : tc::launch_gemm_tc<192, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
         } else if (w.bn == 32) {
-            e = precision == 1 ? tc::launch_gemm_tc<32, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
-                               : tc::launch_gemm_tc<32, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
+            e = x3 ? tc::launch_gemm_tc<32, 3>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl)
+                   : tc::launch_gemm_tc<32, 1>(st, num_sms, M, N, K, al, w.img, stride, ep, 0, pdl);
         }
         if (e != cudaSuccess) return fail(std::string("tcgen05 gemm launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
@@ -221,6 +324,8 @@ struct said_engine {
     DevBuf cnull;
     DevBuf act[7], gnbuf, qkv, ao, q2, ffb, eps, ss, ss_st, emb_tab, tvals, step_tab, kv, vnull, lat, init_lat, vnull_tmp;
     DevBuf e_a, e_b, e_c, e_d, e_qkv, e_ff, e_xp, e_emb;
+    // pair-format (fp16 hi/lo) operands of the fp16x3 path, sized in floats (a pair element takes 4 bytes like an fp32 one)
+    DevBuf p_gn, p_raw, p_ln, p_ao, p_x2, p_ff;
     double* c0_partial = nullptr;
     double* gn_partial = nullptr;
     size_t gn_partial_cap = 0;
@@ -230,7 +335,7 @@ struct said_engine {
     // The instantiated step graph is kept across denoise() calls and replayed as long as everything baked into its
     // kernel nodes is unchanged (shapes, scalars, user tensors read per step, workspace addresses, precision).
     struct GraphKey {
-        int B, T, do_cfg, n_steps, pred_type, scheduler, precision, tc_min_rows;
+        int B, T, Tc, do_cfg, n_steps, pred_type, scheduler, precision, tc_min_rows;
         float gscale, grescale, latent_scale;
         const void *eta_noise, *edit_noise, *mask, *intermediates;
         unsigned long long alloc_gen;
@@ -255,6 +360,8 @@ struct said_engine {
         if (c0_partial) cudaFree(c0_partial);
         if (gn_partial) cudaFree(gn_partial);
         if (step_ctr) cudaFree(step_ctr);
+        if (status_flag) cudaFree(status_flag);
+        if (band_dev) cudaFree(band_dev);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -302,6 +409,9 @@ struct said_engine {
     int ensure_denoiser_ws(int Bp, int T);
     int forward(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T, const float* emb_table,
                 const int* step_ptr, float* eps_out, float* taps);
+    int forward_h(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T, const float* emb_table,
+                  const int* step_ptr, float* eps_out, float* taps);
+    bool use_h(int M) const { return precision == 3 && M >= tc_min_rows && in_ch == 32; }
     int denoise(const said_denoise_args& a, cudaStream_t user);
 };
 
@@ -386,6 +496,15 @@ int said_engine::commit_denoiser() {
         CKI(register_tc(r.w2, w2.data(), 3 * C, C, C));
         if (r.skip) CKI(register_tc(r.w2 + (size_t)3 * C * C, w2.data() + (size_t)3 * C * C, r.cin, C, C));
         CKI(upload(b2, &r.b2));
+        if (r.skip) {   // fp16x3 path: second conv + 1x1 skip as one K = 576 + 384 contraction; image keyed by the (unique) bias pointer
+            std::vector<uint16_t> himg;
+            const int e = hx::pack_weights_h(w2.data(), r.k2, C, C, 192, himg);
+            uint8_t* hd = nullptr;
+            CK(cudaMalloc((void**)&hd, himg.size() * sizeof(uint16_t)));
+            arena.push_back(reinterpret_cast<float*>(hd));
+            CK(cudaMemcpy(hd, himg.data(), himg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            hmap[r.b2] = HW{hd, r.k2, C, 192, e};
+        }
     }
     // ---- SpatialTransformers in execution order
     const char* tr_paths[4] = {"input_blocks.1.1", "middle_block.1", "output_blocks.0.1", "output_blocks.1.1"};
@@ -657,9 +776,13 @@ int said_engine::commit() {
     for (float* p : arena) cudaFree(p);
     arena.clear();
     tcmap.clear();
+    hmap.clear();
     ready = false;
     ctx_B = ctx_T = 0;
-    CKI(commit_denoiser());
+    reg_h = true;
+    const int rc_d = commit_denoiser();
+    reg_h = false;
+    CKI(rc_d);
     CKI(commit_encoder());
     const int enc_out = proj_dim > 0 ? proj_dim : enc_hidden;
     if (enc_out != ctx_dim)
@@ -681,6 +804,7 @@ EpiStd mk_epi(float* out, long long ldo, int N) {
     e.N = N;
     e.T = 1;
     e.zdiv = 1;
+    e.acc_scale = 1.0f;
     return e;
 }
 ALoadPlain mk_plain(const float* A, long long lda, int M) {
@@ -956,16 +1080,26 @@ int said_engine::prepare_context(const float* emb, int B, int T, int with_uncond
 // Denoiser forward
 // =====================================================================================================
 int said_engine::ensure_denoiser_ws(int Bp, int T) {
-    const size_t M = (size_t)Bp * T;
-    for (auto& a : act) CK(a.ensure(M * C));
-    CK(gnbuf.ensure(M * 2 * C));
-    CK(qkv.ensure(M * 3 * C));
-    CK(ao.ensure(M * C));
-    CK(q2.ensure(M * C));
-    CK(ffb.ensure(M * FF));
+    // sized for the padded row space of the fp16x3 path (one zero row between clips); the other paths use the first Bp*T rows
+    const size_t M = (size_t)Bp * (T + 1);
+    for (auto& a : act) CK(a.ensure_zero(M * C));
+    CK(gnbuf.ensure_zero(M * 2 * C));
+    CK(qkv.ensure_zero(M * 3 * C));
+    CK(ao.ensure_zero(M * C));
+    CK(q2.ensure_zero(M * C));
+    CK(ffb.ensure_zero(M * FF));
     CK(eps.ensure(M * in_ch));
     CK(ss.ensure((size_t)Bp * 2 * C * 2));
     CK(ss_st.ensure((size_t)Bp * C * 2));
+    if (precision == 3) {
+        CK(p_raw.ensure_zero(M * 2 * C));
+        CK(p_ln.ensure_zero(M * C));
+        CK(p_x2.ensure_zero(M * C));
+    }
+    if (!status_flag) {
+        CK(cudaMalloc((void**)&status_flag, sizeof(int)));
+        CK(cudaMemset(status_flag, 0, sizeof(int)));
+    }
     if (!step_ctr) CK(cudaMalloc((void**)&step_ctr, sizeof(int)));
     if ((size_t)Bp * GN_SPLIT_MAX * 2 * C > gn_partial_cap) {
         if (gn_partial) cudaFree(gn_partial);
@@ -1111,10 +1245,11 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         cur_tag = TAG_ATTN;
         if (mat && T <= tc::ATC_MAXKEYS) {
             CK(launch_ex(tc::self_attention_tc_kernel, dim3(HEADS, h_nb), dim3(tc::ATC_THREADS), tc::attention_tc_smem_bytes(T), st, pdl, 1,
-                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C));
+                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C, T, (__half*)nullptr, (int*)nullptr));
         } else {
             CK(launch_ex(self_attention_kernel<32>, dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, h_nb), dim3(ATT_THREADS),
-                         attention_smem_bytes<32>(), st, pdl, 1, (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C));
+                         attention_smem_bytes<32>(), st, pdl, 1, (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, ao.p, C, T,
+                         (__half*)nullptr, (int*)nullptr));
         }
         LAUNCH_CHECK();
         {   // x1 = to_out(attn) + GN(h)
@@ -1138,9 +1273,9 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         {
             const long long tot = (long long)M * HEADS * 8;   // 8 lanes per (row, head)
             cur_tag = TAG_XATTN;
-            CK(launch_ex(cross_attention3_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, pdl, 1, (const float*)q2.p,
-                         (const float*)kv.p, 8 * C, i * 2 * C, (const float*)(cnull.p + i * C), (const float*)x1, x2, mh, n_uncond, Bp, T,
-                         att_scale, ao.p));
+            CK(launch_ex(cross_attention_band_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, pdl, 1, (const float*)q2.p,
+                         (const float*)kv.p, 8 * C, i * 2 * C, (const int2*)band_dev, (const float*)(cnull.p + i * C), (const float*)x1, x2,
+                         mh, n_uncond, Bp, T, T, ctx_T, att_scale, ao.p, (__half*)nullptr, (int*)nullptr));
             LAUNCH_CHECK();
         }
         if (Mc > 0) {   // x2 = to_out(attn2) + x1 on the conditional rows (the kernel above wrote the unconditional ones)
@@ -1220,17 +1355,205 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
 }
 
 // =====================================================================================================
+// Denoiser forward, fp16x3 path: every contraction is a TMA-fed tcgen05 kind::f16 GEMM over pair-format operands
+// (gemm_h.cuh); GroupNorm / LayerNorm / attention kernels write their outputs directly in that format.
+// Row space: sample b, frame t -> row b * (T + 1) + t; row T of every sample is a zero row in the conv operands, so
+// Conv1d(k=3, pad=1) is three row-shifted TMA boxes and tiles may straddle clips.  Same arguments as forward().
+// =====================================================================================================
+int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T,
+                           const float* emb_table, const int* step_ptr, float* eps_out, float* taps) {
+    const int Tp = T + 1;
+    const int Mp = Bp * Tp;
+    const int Mcp = (Bp - n_uncond) * Tp;
+    const bool share = n_uncond > 0 && 2 * n_uncond == Bp && taps == nullptr;   // see forward(): shared guidance prefix
+    const int Bs = share ? Bp - n_uncond : Bp;
+    const int Msp = Bs * Tp;
+    float* h0 = act[0].p; float* h1 = act[1].p; float* A = act[2].p; float* Bb = act[3].p;
+    float* t1 = act[4].p; float* x1 = act[5].p; float* x2 = act[6].p;
+    float* sc_st = ss_st.p; float* sh_st = ss_st.p + (size_t)Bp * C;
+    __half* pgn = reinterpret_cast<__half*>(gnbuf.p);     // conv operand: silu(gn(x)), 192 or 384 columns
+    __half* praw = reinterpret_cast<__half*>(p_raw.p);    // raw concat [h | skip] (1x1 skip_connection operand), 384 columns
+    __half* pln = reinterpret_cast<__half*>(p_ln.p);      // LayerNorm outputs
+    __half* pao = reinterpret_cast<__half*>(ao.p);        // attention outputs
+    __half* px2 = reinterpret_cast<__half*>(p_x2.p);      // residual stream before the feed-forward, as an operand
+    __half* pff = reinterpret_cast<__half*>(ffb.p);       // GEGLU output, 768 columns
+    const float att_scale = 1.0f / sqrtf((float)HD);
+    int tap_idx = 0;
+    auto tap = [&](const float* p) -> int {
+        if (taps) {
+            CK(cudaMemcpy2DAsync(taps + (size_t)tap_idx * Bp * T * C, (size_t)T * C * sizeof(float), p, (size_t)Tp * C * sizeof(float),
+                                 (size_t)T * C * sizeof(float), (size_t)Bp, cudaMemcpyDeviceToDevice, st));
+            ++tap_idx;
+        }
+        return 0;
+    };
+    const int gn_cl = (T <= 320 && Bp * GN_SPLIT >= num_sms) ? GN_SPLIT : 8;
+    if (((T + gn_cl - 1) / gn_cl + 7) / 8 > GNF_MAXR) return fail("fp16x3 path: at most 640 frames per clip");
+    // GroupNorm of nb samples (data = sample b % src_nb of src): scale/shift and / or pair-format outputs
+    auto gnp = [&](const float* src, int src_nb, int nb, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh,
+                   __half* act_pair, __half* raw_pair, int act_C, int act_off) -> int {
+        cur_tag = TAG_GN;
+        CK(launch_ex(gn_pair_kernel, dim3(gn_cl, nb), dim3(GNF_THREADS), 0, st, pdl, gn_cl, src, src_nb, T, Tp, cpg, eps_, g, b, osc, osh, C, 0,
+                     act_pair, raw_pair, act_C, act_off, status_flag));
+        LAUNCH_CHECK();
+        return 0;
+    };
+    auto ln_pair = [&](const float* src, int m, const float* ps, const float* pb, const float* g, const float* b, __half* dst, __half* raw) -> int {
+        cur_tag = TAG_GN;
+        CK(launch_ex(ln192_pair_kernel, dim3((unsigned)(((long long)m * 16 + 255) / 256)), dim3(256), 0, st, pdl, 1, src, m, Tp, ps, pb, g, b,
+                     1e-5f, dst, raw, status_flag));
+        LAUNCH_CHECK();
+        return 0;
+    };
+    auto psrc = [](const __half* base, int Cc, long long rows) { return HSrc{base, Cc, rows}; };
+    // ResBlock (openaimodel.py:207-227)
+    auto resblock = [&](int i, const float* a, int a_nb, const float* skip, int skip_nb, int nb, float* out) -> int {
+        const ResBlockW& W = rb[i];
+        const int cin = W.cin;
+        const int m = nb * Tp;
+        if (skip) {
+            CKI(gnp(a, a_nb, nb, 12, 1e-5f, W.gn1_g, W.gn1_b, nullptr, nullptr, pgn, praw, cin, 0));
+            CKI(gnp(skip, skip_nb, nb, 12, 1e-5f, W.gn1_g + C, W.gn1_b + C, nullptr, nullptr, pgn, praw, cin, C));
+        } else {
+            CKI(gnp(a, a_nb, nb, 6, 1e-5f, W.gn1_g, W.gn1_b, nullptr, nullptr, pgn, nullptr, cin, 0));
+        }
+        {
+            const HSrc g1 = psrc(pgn, cin, m);
+            EpiStd ep = mk_epi(t1, C, C);
+            ep.bias = W.b1;
+            ep.emb = emb_table + (size_t)i * C;
+            ep.emb_ld = 5 * C;
+            ep.step_ptr = step_ptr;
+            ep.T = Tp;
+            CKI(gemm_h(st, m, C, {{g1, 0, cin, -1}, {g1, 0, cin, 0}, {g1, 0, cin, 1}}, W.w1, ep, TAG_GEMM_CONV));
+        }
+        CKI(gnp(t1, nb, nb, 6, 1e-5f, W.gn2_g, W.gn2_b, nullptr, nullptr, pgn, nullptr, C, 0));
+        const HSrc g2 = psrc(pgn, C, m);
+        EpiStd ep = mk_epi(out, C, C);
+        ep.bias = W.b2;
+        if (skip) {   // second conv and the 1x1 skip_connection over the raw concat as ONE contraction (K = 576 + 384)
+            CKI(gemm_h(st, m, C, {{g2, 0, C, -1}, {g2, 0, C, 0}, {g2, 0, C, 1}, {psrc(praw, cin, m), 0, cin, 0}}, W.b2 /*key of the fused image*/,
+                       ep, TAG_GEMM_CONV));
+        } else {
+            ep.res = a;
+            ep.ldr = C;
+            ep.res_mod = a_nb * Tp;
+            CKI(gemm_h(st, m, C, {{g2, 0, C, -1}, {g2, 0, C, 0}, {g2, 0, C, 1}}, W.w2, ep, TAG_GEMM_CONV));
+        }
+        return 0;
+    };
+    // SpatialTransformer + BasicTransformerBlock (attention.py:223-234, 167-193)
+    auto transformer = [&](int i, const float* h, int h_nb, float* out) -> int {
+        const TransformerW& W = tr[i];
+        const int mh = h_nb * Tp;
+        const bool shared_front = h_nb < Bp;
+        CKI(gnp(h, h_nb, h_nb, 6, 1e-6f, W.gn_g, W.gn_b, sc_st, sh_st, nullptr, nullptr, C, 0));
+        CKI(ln_pair(h, mh, sc_st, sh_st, W.ln1_g, W.ln1_b, pln, nullptr));
+        {   // q,k,v = LN1(GN(h)) W   (no bias)
+            EpiStd ep = mk_epi(qkv.p, 3 * C, 3 * C);
+            CKI(gemm_h(st, mh, 3 * C, {{psrc(pln, C, mh), 0, C, 0}}, W.wqkv, ep, TAG_GEMM_PLAIN));
+        }
+        cur_tag = TAG_ATTN;
+        if (T <= tc::ATC_MAXKEYS) {
+            CK(launch_ex(tc::self_attention_tc_kernel, dim3(HEADS, h_nb), dim3(tc::ATC_THREADS), tc::attention_tc_smem_bytes(T), st, pdl, 1,
+                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag));
+        } else {
+            CK(launch_ex(self_attention_kernel<32>, dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, h_nb), dim3(ATT_THREADS),
+                         attention_smem_bytes<32>(), st, pdl, 1, (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp,
+                         pao, status_flag));
+        }
+        LAUNCH_CHECK();
+        {   // x1 = to_out(attn) + GN(h)
+            EpiStd ep = mk_epi(x1, C, C);
+            ep.bias = W.bo1;
+            ep.res = h;
+            ep.ldr = C;
+            ep.res_scale = sc_st;
+            ep.res_shift = sh_st;
+            ep.res_aff_ld = C;
+            ep.T = Tp;
+            CKI(gemm_h(st, mh, C, {{psrc(pao, C, mh), 0, C, 0}}, W.wo1, ep, TAG_GEMM_PLAIN));
+        }
+        const size_t x1c = shared_front ? 0 : (size_t)n_uncond * Tp * C;   // first row of the conditional samples in x1
+        const size_t r0 = (size_t)n_uncond * Tp;                           // ... in the full-batch tensors
+        if (Mcp > 0) {   // cross-attention queries, conditional samples only
+            CKI(ln_pair(x1 + x1c, Mcp, nullptr, nullptr, W.ln2_g, W.ln2_b, pln, nullptr));
+            EpiStd ep = mk_epi(q2.p, C, C);
+            CKI(gemm_h(st, Mcp, C, {{psrc(pln, C, Mcp), 0, C, 0}}, W.wq2, ep, TAG_GEMM_LN));
+        }
+        {
+            const long long tot = (long long)Bp * T * HEADS * 8;   // 8 lanes per (frame, head)
+            cur_tag = TAG_XATTN;
+            CK(launch_ex(cross_attention_band_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, pdl, 1, (const float*)q2.p,
+                         (const float*)kv.p, 8 * C, i * 2 * C, (const int2*)band_dev, (const float*)(cnull.p + i * C), (const float*)x1, x2,
+                         mh, n_uncond, Bp, T, Tp, ctx_T, att_scale, (float*)nullptr, pao, status_flag));
+            LAUNCH_CHECK();
+        }
+        if (Mcp > 0) {   // x2 = to_out(attn2) + x1 on the conditional rows (the kernel above wrote the unconditional ones)
+            EpiStd ep = mk_epi(x2 + r0 * C, C, C);
+            ep.bias = W.bo2;
+            ep.res = x1 + x1c;
+            ep.ldr = C;
+            CKI(gemm_h(st, Mcp, C, {{psrc(pao + r0 * 2 * C, C, Mcp), 0, C, 0}}, W.wo2, ep, TAG_GEMM_PLAIN));
+        }
+        CKI(ln_pair(x2, Mp, nullptr, nullptr, W.ln3_g, W.ln3_b, pln, px2));
+        {   // GEGLU
+            EpiGegluPair ep{pff, FF, 2 * FF, W.bff1, 1.0f, status_flag};
+            CKI(gemm_h(st, Mp, 2 * FF, {{psrc(pln, C, Mp), 0, C, 0}}, W.wff1, ep, TAG_GEMM_PLAIN));
+        }
+        {   // out = proj_out(ff2(ff) + x2) + h as ONE contraction over [ff | x2] with the folded weights
+            EpiStd ep = mk_epi(out, C, C);
+            ep.bias = W.bffp;
+            ep.res = h;
+            ep.ldr = C;
+            ep.res_mod = mh;
+            CKI(gemm_h(st, Mp, C, {{psrc(pff, FF, Mp), 0, FF, 0}, {psrc(px2, C, Mp), 0, C, 0}}, W.wffp, ep, TAG_GEMM_PLAIN));
+        }
+        return 0;
+    };
+
+    {   // input conv (openaimodel.py:473-479): K = 96, straight from the fp32 latents (B, T, in_ch) into the padded row space
+        ALoadConv3 al{x, nullptr, in_ch, 0, in_ch, Tp, Msp, src_batch, nullptr, nullptr, 3 * in_ch, 0};
+        al.Tsrc = T;
+        EpiStd ep = mk_epi(h0, C, C);
+        ep.bias = b_in;
+        CKI(gemm(st, Msp, C, 3 * in_ch, al, w_in, C, ep));
+    }
+    CKI(tap(h0));
+    CKI(resblock(0, h0, Bs, nullptr, 0, Bs, A));       CKI(tap(A));
+    CKI(transformer(0, A, Bs, h1));                    CKI(tap(h1));
+    CKI(resblock(1, h1, Bp, nullptr, 0, Bp, Bb));      CKI(tap(Bb));
+    CKI(transformer(1, Bb, Bp, A));                    CKI(tap(A));
+    CKI(resblock(2, A, Bp, nullptr, 0, Bp, Bb));       CKI(tap(Bb));
+    CKI(resblock(3, Bb, Bp, h1, Bp, Bp, A));           CKI(tap(A));
+    CKI(transformer(2, A, Bp, Bb));                    CKI(tap(Bb));
+    CKI(resblock(4, Bb, Bp, h0, Bs, Bp, A));           CKI(tap(A));
+    CKI(transformer(3, A, Bp, Bb));                    CKI(tap(Bb));
+    {   // out: GN + SiLU + conv3 -> in_ch   (openaimodel.py:665-669), written densely as (Bp, T, in_ch)
+        CKI(gnp(Bb, Bp, Bp, 6, 1e-5f, out_gn_g, out_gn_b, nullptr, nullptr, pgn, nullptr, C, 0));
+        const HSrc g = psrc(pgn, C, Mp);
+        EpiStd ep = mk_epi(eps_out, in_ch, in_ch);
+        ep.bias = b_out;
+        ep.out_period = Tp;
+        ep.out_valid = T;
+        CKI(gemm_h(st, Mp, in_ch, {{g, 0, C, -1}, {g, 0, C, 0}, {g, 0, C, 1}}, w_out, ep, TAG_GEMM_CONV));
+    }
+    return 0;
+}
+
+// =====================================================================================================
 // Denoising loop
 // =====================================================================================================
 int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
     if (!ready) return fail("weights not committed");
     if (a.B <= 0 || a.T <= 0 || a.n_steps < 0) return fail("denoise: bad sizes");
     if (a.scheduler != 0 && a.scheduler != 1) return fail("denoise: scheduler must be 0 (DDIM) or 1 (DDPM)");
-    if (ctx_B != a.B || ctx_T != a.T || ctx_uncond != (a.do_cfg ? 1 : 0))
-        return fail("denoise: said_prepare_context was not called for this (B, T, cfg)");
+    if (ctx_B != a.B || ctx_T <= 0 || ctx_uncond != (a.do_cfg ? 1 : 0))
+        return fail("denoise: said_prepare_context was not called for this (B, cfg)");
     const int B = a.B, T = a.T, Bp = a.do_cfg ? 2 * B : B;
     const long long n = (long long)T * in_ch, tot = (long long)B * n;
     CKI(ensure_denoiser_ws(Bp, T));
+    CKI(ensure_band(T, ctx_T, own_stream));
     CK(lat.ensure((size_t)tot));
     CK(init_lat.ensure((size_t)tot));
     cudaStream_t st = own_stream;
@@ -1280,7 +1603,8 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         if (sp.mask && !sp.edit_noise) return fail("denoise: mask given without edit noise");
 
         auto one_step = [&]() -> int {
-            CKI(forward(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
+            if (use_h(Bp * T)) CKI(forward_h(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
+            else CKI(forward(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
             cur_tag = TAG_STEP;
             CK(launch_ex(ddim_step_kernel, dim3(B, DDIM_SPLIT), dim3(256), 0, st, pdl, 1, sp));
             LAUNCH_CHECK();
@@ -1291,7 +1615,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         if (a.use_graph && a.n_steps > 1) {
             GraphKey key;
             memset(&key, 0, sizeof(key));
-            key.B = B; key.T = T; key.do_cfg = a.do_cfg; key.n_steps = a.n_steps; key.pred_type = a.prediction_type;
+            key.B = B; key.T = T; key.Tc = ctx_T; key.do_cfg = a.do_cfg; key.n_steps = a.n_steps; key.pred_type = a.prediction_type;
             key.scheduler = a.scheduler; key.precision = precision; key.tc_min_rows = tc_min_rows;
             key.gscale = a.guidance_scale; key.grescale = a.guidance_rescale; key.latent_scale = a.latent_scale;
             key.eta_noise = a.eta_noise_dev; key.edit_noise = a.edit_noise_dev; key.mask = a.mask_dev;
@@ -1424,22 +1748,77 @@ int said_denoise(said_engine* e, const said_denoise_args* args, void* stream) {
 }
 
 int said_denoiser_forward(said_engine* e, const float* x_dev, const float* timesteps_host, const float* ctx_dev, int Bp,
-                          int T, float* out_dev, float* taps_dev, void* stream) {
+                          int T, int T_ctx, float* out_dev, float* taps_dev, void* stream) {
     if (!e) return fail("null engine");
     if (!e->ready) return fail("weights not committed");
-    if (Bp <= 0 || T <= 0) return fail("denoiser_forward: empty batch");
+    if (Bp <= 0 || T <= 0 || T_ctx <= 0) return fail("denoiser_forward: empty batch");
     CK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CKI(e->prepare_context(ctx_dev, Bp, T, 0, st));
+    CKI(e->prepare_context(ctx_dev, Bp, T_ctx, 0, st));
     CKI(e->ensure_denoiser_ws(Bp, T));
+    CKI(e->ensure_band(T, T_ctx, st));
     CK(e->tvals.ensure((size_t)Bp));
     CK(e->emb_tab.ensure((size_t)Bp * 5 * C));
     CK(cudaMemcpyAsync(e->tvals.p, timesteps_host, Bp * sizeof(float), cudaMemcpyHostToDevice, st));
     time_embed_table_kernel<<<Bp, 256, 0, st>>>(e->tvals.p, e->te, e->emb_tab.p, nullptr);
     ++e->launches;
     CK(cudaGetLastError());
-    CKI(e->forward(st, x_dev, Bp, Bp, 0, T, e->emb_tab.p, nullptr, out_dev, taps_dev));
+    if (e->use_h(Bp * T)) CKI(e->forward_h(st, x_dev, Bp, Bp, 0, T, e->emb_tab.p, nullptr, out_dev, taps_dev));
+    else CKI(e->forward(st, x_dev, Bp, Bp, 0, T, e->emb_tab.p, nullptr, out_dev, taps_dev));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int said_check_status(said_engine* e, void* stream, int* status_out) {
+    if (!e || !status_out) return fail("said_check_status: bad arguments");
+    *status_out = 0;
+    if (!e->status_flag) return 0;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int v = 0;
+    CK(cudaMemcpyAsync(&v, e->status_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (v != 0) CK(cudaMemsetAsync(e->status_flag, 0, sizeof(int), st));
+    *status_out = v;
+    return 0;
+}
+
+int said_op_gemm_h(said_engine* e, const float* a_dev, int M, int Cin, int taps, const float* wt_host, int N, const float* bias_dev,
+                   float* out_dev, void* stream) {
+    // unit test of the fp16x3 GEMM: out (M, N) = sum over taps of A[m + tap - (taps - 1) / 2, :] . Wt[tap * Cin : (tap + 1) * Cin, :] + bias
+    // (rows outside [0, M) are zero); A is converted to the pair format first.  N must be 192 or 32, Cin a multiple of 64.
+    if (!e) return fail("null engine");
+    if (!(taps == 1 || taps == 3) || Cin % hx::HBK != 0 || (N != 192 && N != 32 && N % 192 != 0)) return fail("said_op_gemm_h: unsupported shape");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    static DevBuf apair;
+    CK(apair.ensure((size_t)M * Cin));
+    if (!e->status_flag) {
+        CK(cudaMalloc((void**)&e->status_flag, sizeof(int)));
+        CK(cudaMemset(e->status_flag, 0, sizeof(int)));
+    }
+    const long long nq = (long long)M * (Cin / 4);
+    f32_to_pair_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(a_dev, M, Cin, reinterpret_cast<__half*>(apair.p), e->status_flag);
+    CK(cudaGetLastError());
+    const int K = taps * Cin, bn = N == 32 ? 32 : 192;
+    std::vector<uint16_t> himg;
+    const int ex = hx::pack_weights_h(wt_host, K, N, N, bn, himg);
+    uint8_t* wd = nullptr;
+    CK(cudaMalloc((void**)&wd, himg.size() * sizeof(uint16_t)));
+    CK(cudaMemcpyAsync(wd, himg.data(), himg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    const float* key = reinterpret_cast<const float*>(wd);
+    e->hmap[key] = said_engine::HW{wd, K, N, bn, ex};
+    const said_engine::HSrc src{reinterpret_cast<const __half*>(apair.p), Cin, M};
+    EpiStd ep = mk_epi(out_dev, N, N);
+    ep.bias = bias_dev;
+    int rc;
+    if (taps == 1) rc = e->gemm_h(st, M, N, {{src, 0, Cin, 0}}, key, ep, said_engine::TAG_GEMM_PLAIN);
+    else rc = e->gemm_h(st, M, N, {{src, 0, Cin, -1}, {src, 0, Cin, 0}, {src, 0, Cin, 1}}, key, ep, said_engine::TAG_GEMM_CONV);
+    cudaError_t se = cudaStreamSynchronize(st);
+    e->hmap.erase(key);
+    cudaFree(wd);
+    if (rc != 0) return rc;
+    CK(se);
     return 0;
 }
 
@@ -1507,7 +1886,7 @@ int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int B, int T
     const int Cw = heads * 32;
     CK(cudaFuncSetAttribute(tc::self_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::attention_tc_smem_bytes(T)));
     tc::self_attention_tc_kernel<<<dim3(heads, B), tc::ATC_THREADS, tc::attention_tc_smem_bytes(T), st>>>(
-        qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw);
+        qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr);
     ++e->launches;
     CK(cudaGetLastError());
     return 0;
@@ -1559,7 +1938,7 @@ int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int with_res
 
 int said_set_precision(said_engine* e, int mode, int tc_min_rows, int encoder_mode) {
     if (!e) return fail("null engine");
-    if (mode < 0 || mode > 2) return fail("said_set_precision: mode must be 0 (fp32 FFMA), 1 (3xTF32 tcgen05) or 2 (TF32 tcgen05)");
+    if (mode < 0 || mode > 3) return fail("said_set_precision: mode must be 0 (fp32 FFMA), 1 (3xTF32 tcgen05), 2 (TF32 tcgen05) or 3 (fp16 hi/lo x3 tcgen05)");
     if (encoder_mode < 0 || encoder_mode > 2) return fail("said_set_precision: encoder_mode must be 0, 1 or 2");
     e->precision = mode;
     e->enc_precision = encoder_mode;

@@ -12,6 +12,7 @@
 // Requirements: K % 16 == 0, N % 4 == 0, all row strides % 4 == 0 (16-byte vector access).
 #pragma once
 #include "common.cuh"
+#include "pair.cuh"
 
 namespace said {
 
@@ -204,6 +205,9 @@ struct ALoadConv3 {
     const float* shift;
     int K3;                 // 3*Cin
     int src1_batch;         // same for src1 (0: use src_batch) -- the UNet skip tensor of the shared CFG prefix
+    int Tsrc = 0;           // frames per sample in the SOURCE tensors when it differs from the row period T of the GEMM
+                            // (fp16x3 path: GEMM rows live in the padded space, period T + 1, the latents are (B, T, C)); 0: T
+    SAID_DEVINL int tv() const { return Tsrc ? Tsrc : T; }
     struct Ctx { int b, t; long long row, row1; bool ok; };
     SAID_DEVINL void set_z(int) {}
     SAID_DEVINL Ctx prep(int m, int) const {
@@ -212,8 +216,8 @@ struct ALoadConv3 {
         const int mm = c.ok ? m : 0;
         c.b = mm / T;
         c.t = mm - c.b * T;
-        c.row = (long long)(c.b % src_batch) * T + c.t;
-        c.row1 = (long long)(c.b % (src1_batch ? src1_batch : src_batch)) * T + c.t;
+        c.row = (long long)(c.b % src_batch) * tv() + c.t;
+        c.row1 = (long long)(c.b % (src1_batch ? src1_batch : src_batch)) * tv() + c.t;
         return c;
     }
     SAID_DEVINL float4 load4(const Ctx& c, int k) const {
@@ -225,7 +229,7 @@ struct ALoadConv3 {
             ch = k - tap * Cin;
         }
         const int tt = c.t + tap - 1;
-        if (tt < 0 || tt >= T) return zero4();
+        if (tt < 0 || tt >= tv()) return zero4();
         float4 x = (ch < C0) ? ldg4(src0 + (c.row + (tap - 1)) * C0 + ch) : ldg4(src1 + (c.row1 + (tap - 1)) * C1 + (ch - C0));
         if (scale != nullptr && !raw) {
             const float4 a = ldg4(scale + (long long)c.b * Cin + ch), d = ldg4(shift + (long long)c.b * Cin + ch);
@@ -241,8 +245,8 @@ struct ALoadConv3 {
         const int mm = c.ok ? m : 0;
         const int b = mm / T;
         c.t = mm - b * T;
-        const long long row = (long long)(b % src_batch) * T + c.t;
-        const long long row1 = (long long)(b % (src1_batch ? src1_batch : src_batch)) * T + c.t;
+        const long long row = (long long)(b % src_batch) * tv() + c.t;
+        const long long row1 = (long long)(b % (src1_batch ? src1_batch : src_batch)) * tv() + c.t;
         c.p0 = src0 + row * C0;
         c.p1 = src1 ? src1 + row1 * C1 : src0;
         return c;
@@ -254,7 +258,7 @@ struct ALoadConv3 {
             ch = k - tap * Cin;
         }
         const int tt = c.t + tap - 1;
-        valid = c.ok && tt >= 0 && tt < T;
+        valid = c.ok && tt >= 0 && tt < tv();
         if (!valid) return src0;
         return (ch < C0) ? c.p0 + (tap - 1) * C0 + ch : c.p1 + (tap - 1) * C1 + (ch - C0);
     }
@@ -267,7 +271,7 @@ struct ALoadConv3 {
         const int tap = (k >= Cin) + (k >= 2 * Cin);
         const int ch = k - tap * Cin;
         const int tt = c.t + tap - 1;
-        if (tt < 0 || tt >= T) return zero4();           // zero padding applies after GN + SiLU
+        if (tt < 0 || tt >= tv()) return zero4();        // zero padding applies after GN + SiLU
         const float4 a = ldg4(scale + (long long)c.b * Cin + ch), d = ldg4(shift + (long long)c.b * Cin + ch);
         x.x = silu_fast(x.x * a.x + d.x); x.y = silu_fast(x.y * a.y + d.y);
         x.z = silu_fast(x.z * a.z + d.z); x.w = silu_fast(x.w * a.w + d.w);
@@ -298,6 +302,9 @@ struct EpiStd {
     int res_mod;             // > 0: the residual tensor has only res_mod rows, row m reads row m % res_mod (shared CFG prefix)
     int zdiv;                // batched: out/res += (z / zdiv) * zs0 + (z % zdiv) * zs1, bias += (z % zdiv) * bias_zs
     long long zs0, zs1, bias_zs;
+    float acc_scale;         // tcgen05 fp16x3 path: the accumulator is multiplied by this first (inverse of the power-of-two weight scale)
+    int out_period, out_valid;   // > 0: GEMM row m = b * out_period + t is written to output row b * out_valid + t, rows with
+                                 // t >= out_valid are dropped (padded row space -> dense (B, T, C) output); only `out` is remapped
     SAID_DEVINL void set_z(int z) {
         const long long off = (long long)(z / zdiv) * zs0 + (long long)(z % zdiv) * zs1;
         out += off;
@@ -383,6 +390,12 @@ struct EpiStd {
     SAID_DEVINL float4 tc_prefetch4(const RowCtx& c, int n) const { return ldg4_l2pf(c.res + (n < N ? n : 0)); }
     SAID_DEVINL void store4(const RowCtx& c, int m, int n, float4 a, float4 r) const {
         if (n >= N) return;
+        if (acc_scale != 1.0f) { a.x *= acc_scale; a.y *= acc_scale; a.z *= acc_scale; a.w *= acc_scale; }
+        if (out_period > 0) {
+            const int b = m / out_period, t = m - b * out_period;
+            if (t >= out_valid) return;
+            m = b * out_valid + t;
+        }
         if (bias) {
             const float4 bq = ldg4(bias + n);
             a.x += bq.x; a.y += bq.y; a.z += bq.z; a.w += bq.w;
@@ -500,6 +513,34 @@ struct EpiGeglu {
         float* o = out + (long long)m * ldo + (n >> 1);
         st4(o, make_float4(r[0], r[1], r[2], r[3]));
         st4(o + 4, make_float4(r[4], r[5], r[6], r[7]));
+    }
+};
+
+// GEGLU with the result written as a pair tensor (pair.cuh) of `Cout` = N / 2 columns: the operand of the following
+// ff.net.2 contraction on the fp16x3 path.  Same interleaved weight / bias packing as EpiGeglu.
+struct EpiGegluPair {
+    __half* out;             // pair tensor, Cout columns
+    int Cout;
+    int N;                   // GEMM N (= 2 * Cout)
+    const float* bias;       // (N) interleaved
+    float acc_scale;
+    int* flag;               // overflow flag (|x| >= fp16 max)
+    struct RowCtx {};
+    SAID_DEVINL bool tc_has_res() const { return false; }
+    SAID_DEVINL RowCtx tc_row(int, int) const { return RowCtx{}; }
+    SAID_DEVINL float4 tc_prefetch4(const RowCtx&, int) const { return zero4(); }
+    SAID_DEVINL void store4(const RowCtx&, int m, int n, float4 a, float4) const {
+        if (n >= N) return;
+        const float4 bq = ldg4(bias + n);
+        const float o0 = (a.x * acc_scale + bq.x) * gelu_erf(a.y * acc_scale + bq.y);
+        const float o1 = (a.z * acc_scale + bq.z) * gelu_erf(a.w * acc_scale + bq.w);
+        const __half2 h = __floats2half2_rn(o0, o1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(o0 - hf.x, o1 - hf.y);
+        __half* p = out + (long long)m * (2LL * Cout) + (n >> 1);
+        *reinterpret_cast<__half2*>(p) = h;
+        *reinterpret_cast<__half2*>(p + Cout) = l;
+        if (fmaxf(fabsf(o0), fabsf(o1)) > P16_LIMIT) atomicOr(flag, 1);
     }
 };
 

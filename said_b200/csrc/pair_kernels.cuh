@@ -1,0 +1,286 @@
+// Kernels that PRODUCE pair-format ("P16", pair.cuh) operands for the TMA-fed tensor-core GEMM (gemm_h.cuh), and the banded
+// cross-attention.  Row space: sample b, frame t lives at row b * Tstr + t with Tstr >= T (the fp16x3 path keeps one zero row
+// between clips, Tstr = T + 1, so that a Conv1d tap that leaves a clip reads zeros; the fp32 paths use Tstr = T).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "norm_kernels.cuh"
+#include "pair.cuh"
+
+namespace said {
+
+// fp32 (rows, C) -> pair tensor (rows, [hi(C) | lo(C)]);  C % 4 == 0
+__global__ void __launch_bounds__(256)
+f32_to_pair_kernel(const float* __restrict__ x, long long rows, int C, __half* __restrict__ out, int* __restrict__ flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = C / 4;
+    if (i >= rows * q) return;
+    const long long r = i / q;
+    const int c = (int)(i - r * q) * 4;
+    const float4 v = ldg4(x + r * C + c);
+    store_pair4(out, r, C, c, v);
+    if (amax4(0.f, v) > P16_LIMIT) atomicOr(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm (GroupNorm32, ldm/util.py:111-122; Normalize, attention.py:63-66) in ONE launch, one thread-block cluster per
+// sample (see gn_fused_kernel in norm_kernels.cuh for the reduction scheme), writing
+//   scale / shift   per (sample, channel):  gn(x)[c] = x[c] * scale + shift          (consumers that fold the norm)
+//   act_pair        silu(gn(x)) as a pair tensor with act_C columns at column offset act_off   (conv operand; optional)
+//   raw_pair        x itself as a pair tensor, same geometry                          (1x1 skip_connection operand; optional)
+// and a zero row at frame T of the pair outputs when Tstr > T.  x is read once.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GNF_THREADS)
+gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, int cpg, float eps, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int out_ld, int out_off,
+               __half* __restrict__ act_pair, __half* __restrict__ raw_pair, int act_C, int act_off, int* __restrict__ flag) {
+    constexpr int C = 192, Q = C / 4, PH = GNF_THREADS / Q;
+    __shared__ double s_red[PH][2][C];
+    __shared__ double s_part[2][32];
+    __shared__ float s_mean[32], s_rstd[32];
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    pdl_wait();
+    pdl_trigger();
+    const int nsp = (int)cluster.num_blocks(), sp = (int)cluster.block_rank(), b = blockIdx.y;
+    const int q = threadIdx.x % Q, ph = threadIdx.x / Q;
+    const int rows = (T + nsp - 1) / nsp;
+    const int t0 = sp * rows, t1 = min(T, t0 + rows);
+    const float* xb = x + (long long)(b % src_samples) * Tstr * C + q * 4;
+    float4 v[GNF_MAXR];
+#pragma unroll
+    for (int i = 0; i < GNF_MAXR; ++i) {
+        const int t = t0 + ph + PH * i;
+        v[i] = t < t1 ? ldg4(xb + (long long)t * C) : zero4();
+    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < GNF_MAXR; ++i) {
+        s0 += (double)v[i].x; q0 += (double)v[i].x * (double)v[i].x;
+        s1 += (double)v[i].y; q1 += (double)v[i].y * (double)v[i].y;
+        s2 += (double)v[i].z; q2 += (double)v[i].z * (double)v[i].z;
+        s3 += (double)v[i].w; q3 += (double)v[i].w * (double)v[i].w;
+    }
+    s_red[ph][0][q * 4 + 0] = s0; s_red[ph][0][q * 4 + 1] = s1; s_red[ph][0][q * 4 + 2] = s2; s_red[ph][0][q * 4 + 3] = s3;
+    s_red[ph][1][q * 4 + 0] = q0; s_red[ph][1][q * 4 + 1] = q1; s_red[ph][1][q * 4 + 2] = q2; s_red[ph][1][q * 4 + 3] = q3;
+    __syncthreads();
+    const int ng = C / cpg;
+    if ((int)threadIdx.x < 2 * ng) {
+        const int g = threadIdx.x % ng, w = threadIdx.x / ng;
+        double a = 0.0;
+        for (int j = 0; j < cpg; ++j) {
+            const int c = g * cpg + j;
+            double cs = 0.0;
+#pragma unroll
+            for (int p2 = 0; p2 < PH; ++p2) cs += s_red[p2][w][c];
+            a += cs;
+        }
+        s_part[w][g] = a;
+    }
+    cluster.sync();
+    if ((int)threadIdx.x < ng) {
+        double gs = 0.0, gq = 0.0;
+        for (int r = 0; r < nsp; ++r) {
+            const double* rp = cluster.map_shared_rank(&s_part[0][0], r);
+            gs += rp[threadIdx.x];
+            gq += rp[32 + threadIdx.x];
+        }
+        const double n = (double)cpg * T;
+        const double mean = gs / n;
+        double var = gq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    cluster.sync();
+    const float4 gm = ldg4(gamma + q * 4), bt = ldg4(beta + q * 4);
+    float4 sc, sh;
+    {
+        const int g0 = (q * 4) / cpg, g1 = (q * 4 + 1) / cpg, g2 = (q * 4 + 2) / cpg, g3 = (q * 4 + 3) / cpg;
+        sc.x = s_rstd[g0] * gm.x; sh.x = bt.x - s_mean[g0] * sc.x;
+        sc.y = s_rstd[g1] * gm.y; sh.y = bt.y - s_mean[g1] * sc.y;
+        sc.z = s_rstd[g2] * gm.z; sh.z = bt.z - s_mean[g2] * sc.z;
+        sc.w = s_rstd[g3] * gm.w; sh.w = bt.w - s_mean[g3] * sc.w;
+    }
+    if (sp == 0 && ph == 0 && scale != nullptr) {
+        st4(scale + (long long)b * out_ld + out_off + q * 4, sc);
+        st4(shift + (long long)b * out_ld + out_off + q * 4, sh);
+    }
+    if (act_pair == nullptr && raw_pair == nullptr) return;
+    const long long row0 = (long long)b * Tstr;
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < GNF_MAXR; ++i) {
+        const int t = t0 + ph + PH * i;
+        if (t < t1) {
+            if (act_pair != nullptr) {
+                const float4 a = make_float4(silu(v[i].x * sc.x + sh.x), silu(v[i].y * sc.y + sh.y), silu(v[i].z * sc.z + sh.z),
+                                             silu(v[i].w * sc.w + sh.w));
+                amax = amax4(amax, a);
+                store_pair4(act_pair, row0 + t, act_C, act_off + q * 4, a);
+            }
+            if (raw_pair != nullptr) {
+                amax = amax4(amax, v[i]);
+                store_pair4(raw_pair, row0 + t, act_C, act_off + q * 4, v[i]);
+            }
+        }
+    }
+    if (Tstr > T && sp == nsp - 1 && ph == 0) {      // the zero row between clips (Conv1d padding)
+        for (int t = T; t < Tstr; ++t) {
+            if (act_pair != nullptr) store_pair4_zero(act_pair, row0 + t, act_C, act_off + q * 4);
+            if (raw_pair != nullptr) store_pair4_zero(raw_pair, row0 + t, act_C, act_off + q * 4);
+        }
+    }
+    if (amax > P16_LIMIT) atomicOr(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm(192) of every row (optionally preceded by the folded GroupNorm affine of the SpatialTransformer) written as a pair
+// tensor:  y = LN(x * ps + pb) * gamma + beta   (attention.py:168-192 norm1 / norm2 / norm3); optionally also x itself as a
+// pair tensor (the residual stream as an operand of the folded ff.net.2 + proj_out GEMM).  16 lanes per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln192_pair_kernel(const float* __restrict__ x, int M, int Tstr, const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ y_pair,
+                  __half* __restrict__ raw_pair, int* __restrict__ flag) {
+    constexpr int C = 192;
+    pdl_wait();
+    pdl_trigger();
+    const int row = (blockIdx.x * 256 + threadIdx.x) >> 4, l = threadIdx.x & 15;
+    const bool ok = row < M;
+    const int r = ok ? row : M - 1;
+    const float* xr = x + (long long)r * C;
+    float4 v[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[j] = ldg4(xr + (l + 16 * j) * 4);
+    float amax = 0.f;
+    if (raw_pair != nullptr && ok) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            amax = amax4(amax, v[j]);
+            store_pair4(raw_pair, row, C, (l + 16 * j) * 4, v[j]);
+        }
+    }
+    if (pre_scale != nullptr) {
+        const int b = r / Tstr;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 a = ldg4(pre_scale + (long long)b * C + (l + 16 * j) * 4), d = ldg4(pre_shift + (long long)b * C + (l + 16 * j) * 4);
+            v[j].x = v[j].x * a.x + d.x; v[j].y = v[j].y * a.y + d.y; v[j].z = v[j].z * a.z + d.z; v[j].w = v[j].w * a.w + d.w;
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float qq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float a = v[j].x - mean, b2 = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+        qq += (a * a + b2 * b2) + (d * d + e * e);
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    const float rstd = 1.0f / sqrtf(qq * (1.0f / C) + eps);
+    if (!ok) return;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int k = (l + 16 * j) * 4;
+        const float4 g = ldg4(gamma + k), bb = ldg4(beta + k);
+        const float4 o4 = make_float4((v[j].x - mean) * rstd * g.x + bb.x, (v[j].y - mean) * rstd * g.y + bb.y,
+                                      (v[j].z - mean) * rstd * g.z + bb.z, (v[j].w - mean) * rstd * g.w + bb.w);
+        amax = amax4(amax, o4);
+        store_pair4(y_pair, row, C, k, o4);
+    }
+    if (amax > P16_LIMIT) atomicOr(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Banded cross-attention (BasicTransformerBlock attn2 with the alignment bias, attention.py:170-191).  The mask leaves query
+// frame i the context frames [band[i].x, band[i].x + band[i].y) -- the host evaluates the reference's window formula
+// (Python round(), attention.py:177-189) once per (T, T_ctx): three frames when the audio features are interpolated to one
+// per coefficient frame (diffusion.py:387), a few more or fewer when init_samples is shorter or longer than the audio window.
+// K/V depend only on the audio, so they are projected once per clip into kv: row (clip * Tc + j), K at column kv_off, V at
+// kv_off + 192, row stride kv_ld.  Unconditional samples (null embedding on every context frame, diffusion.py:397-400) see
+// identical keys and values, so their attention output is the constant v_null and the whole "to_out(attn2) + x" step collapses
+// to x_out = x_res + c_null (c_null = W_o v_null + b_o), written here directly.
+// q rows exist for the conditional samples only: q[(b - n_uncond) * Tstr + t].  Eight lanes per (row, head).
+// Output: fp32 `out` (row stride 192) or, when out_pair != nullptr, the pair tensor.
+// ------------------------------------------------------------------------------------------------
+constexpr int XATT_MAXW = 8;
+__global__ void __launch_bounds__(256)
+cross_attention_band_kernel(const float* __restrict__ q, const float* __restrict__ kv, int kv_ld, int kv_off, const int2* __restrict__ band,
+                            const float* __restrict__ c_null, const float* __restrict__ x_res, float* __restrict__ x_out,
+                            int res_rows, int n_uncond, int Bp, int T, int Tstr, int Tc, float scale, float* __restrict__ out,
+                            __half* __restrict__ out_pair, int* __restrict__ flag) {
+    constexpr int C = 192, HD = 32, H = 6;
+    pdl_wait();
+    pdl_trigger();
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx = gid >> 3;                       // (sample, frame, head) over the VALID frames
+    const int j8 = (int)(gid & 7);
+    const bool live = idx < (long long)Bp * T * H;        // dead lanes still take part in the shuffles
+    const long long ci = live ? idx : 0;
+    const int h = (int)(ci % H);
+    const long long vr = ci / H;
+    const int b = (int)(vr / T), t = (int)(vr - (long long)b * T);
+    const long long row = (long long)b * Tstr + t;        // row in the (padded) activation buffers
+    const int col = h * HD + j8 * 4;
+    const bool uncond = b < n_uncond;
+    int start = 0, cnt = 0;
+    float4 qv = zero4();
+    const float* kr = kv;
+    if (live && uncond) {
+        const float4 a = ldg4(x_res + (row % res_rows) * C + col), c4 = ldg4(c_null + col);   // x_res may hold only the shared samples
+        st4(x_out + row * C + col, make_float4(a.x + c4.x, a.y + c4.y, a.z + c4.z, a.w + c4.w));
+    } else if (live) {
+        const int2 bd = __ldg(band + t);
+        start = bd.x;
+        cnt = bd.y;
+        qv = ldg4(q + ((long long)(b - n_uncond) * Tstr + t) * C + col);
+        kr = kv + ((long long)(b - n_uncond) * Tc + start) * kv_ld + kv_off + col;
+    }
+    const int cmax = __reduce_max_sync(0xffffffffu, cnt);   // warp-uniform loop bound for the shuffles
+    float s[XATT_MAXW];
+    float4 vv[XATT_MAXW];
+#pragma unroll
+    for (int j = 0; j < XATT_MAXW; ++j) {
+        s[j] = 0.f;
+        vv[j] = zero4();
+        if (j < cmax) {
+            if (j < cnt) {
+                const float4 k4 = ldg4(kr + (long long)j * kv_ld);
+                vv[j] = ldg4(kr + (long long)j * kv_ld + C);
+                s[j] = (qv.x * k4.x + qv.y * k4.y) + (qv.z * k4.z + qv.w * k4.w);
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        }
+    }
+    if (!live || uncond) return;
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < XATT_MAXW; ++j)
+        if (j < cnt) { s[j] *= scale; m = fmaxf(m, s[j]); }
+    float den = 0.f;
+    float4 acc = zero4();
+#pragma unroll
+    for (int j = 0; j < XATT_MAXW; ++j)
+        if (j < cnt) {
+            const float pj = expf(s[j] - m);
+            den += pj;
+            acc.x = fmaf(pj, vv[j].x, acc.x); acc.y = fmaf(pj, vv[j].y, acc.y);
+            acc.z = fmaf(pj, vv[j].z, acc.z); acc.w = fmaf(pj, vv[j].w, acc.w);
+        }
+    const float inv = 1.0f / den;
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    if (out_pair != nullptr) {
+        store_pair4(out_pair, row, C, col, acc);
+        if (amax4(0.f, acc) > P16_LIMIT) atomicOr(flag, 1);
+    } else {
+        st4(out + row * C + col, acc);
+    }
+}
+
+}  // namespace said

@@ -173,6 +173,7 @@ class SAID(ABC, nn.Module):
         self.use_cuda_graph = True
         self.dedup_audio = True           # a batch that repeats one clip (script/test_inference.py:167) is encoded once
         # contraction precision of the denoiser GEMMs: "tf32x3" (tcgen05, 3xTF32 split: fp32-level accuracy),
+        # "fp16x3" (tcgen05 over fp16 hi/lo operand pairs loaded by TMA: same accuracy class at twice the tensor-core rate),
         # "tf32" (tcgen05, single pass) or "fp32" (FFMA); GEMMs below tc_min_rows rows stay on the FFMA kernel
         self.precision = "tf32x3"
         self.encoder_precision = "fp32"   # the audio encoder runs once per clip: IEEE fp32 unless asked otherwise
@@ -318,19 +319,22 @@ class SAID(ABC, nn.Module):
         else:
             noise = torch.randn(init_samples.shape, device=init_samples.device)           # diffusion.py:270
         n_loop = self._loop_length(num_inference_steps, strength)
+        # the latents keep init_samples' own length in the editing mode (reference diffusion.py:366); only the audio features
+        # are resampled to window_size frames
+        n_frames = window_size if init_samples is None else int(init_samples.shape[1])
         eta_noise = None
         if eta > 0 and n_loop > 0 and self._scheduler_has_eta():
             # DDIMScheduler.step draws randn(model_output.shape) once per iteration
             eta_noise = torch.stack(
-                [torch.randn(batch_size, window_size, in_channels, device=device) for _ in range(n_loop)]
+                [torch.randn(batch_size, n_frames, in_channels, device=device) for _ in range(n_loop)]
             )
         elif self._scheduler_is_ddpm() and n_loop > 0:
             # DDPMScheduler.step draws randn(model_output.shape) in every iteration whose timestep is > 0
             self.noise_scheduler.set_timesteps(num_inference_steps, device=device)
             loop_ts = [int(t) for t in self.noise_scheduler.timesteps.detach().cpu().numpy()][num_inference_steps - n_loop:]
             eta_noise = torch.stack(
-                [torch.randn(batch_size, window_size, in_channels, device=device) if t > 0
-                 else torch.zeros(batch_size, window_size, in_channels, device=device) for t in loop_ts]
+                [torch.randn(batch_size, n_frames, in_channels, device=device) if t > 0
+                 else torch.zeros(batch_size, n_frames, in_channels, device=device) for t in loop_ts]
             )
         return self._run(
             waveform_processed, noise, init_samples, mask, num_inference_steps, strength, guidance_scale,
@@ -392,10 +396,16 @@ class SAID(ABC, nn.Module):
 
         editing = init_samples is not None
         src = (init_samples if editing else noise).to(device=device, dtype=torch.float32)
-        if tuple(src.shape) != (batch_size, window_size, in_channels):
+        # Editing: init_samples may be a few frames shorter or longer than the audio window (a previous result cut to
+        # floor(len * fps / sr) frames, script/inference.py:188, against audio zero-padded by fit_audio_unet): the latents keep
+        # their own length and the cross-attention uses the reference's general alignment window (attention.py:170-189).
+        if src.dim() != 3 or src.shape[0] != batch_size or src.shape[2] != in_channels or (not editing and src.shape[1] != window_size):
             raise ValueError(
-                f"init_samples must be (batch={batch_size}, frames={window_size}, channels={in_channels}); got {tuple(src.shape)}"
+                f"{'init_samples' if editing else 'noise'} must be (batch={batch_size}, frames, channels={in_channels}); got {tuple(src.shape)}"
             )
+        if noise.shape != src.shape:
+            raise ValueError(f"noise {tuple(noise.shape)} does not match the latents {tuple(src.shape)}")
+        n_frames = int(src.shape[1])
         edit_noise, edit_coefs = None, (1.0, 0.0)
         if editing:
             edit_noise = noise.to(device=device, dtype=torch.float32)
@@ -432,7 +442,7 @@ class SAID(ABC, nn.Module):
 
         inter = None
         if save_intermediate and n_loop > 0:
-            inter = torch.empty((n_loop, batch_size, window_size, in_channels), dtype=torch.float32, device=device)
+            inter = torch.empty((n_loop, batch_size, n_frames, in_channels), dtype=torch.float32, device=device)
         latents_out = torch.empty_like(src) if return_latents else None
         if getattr(self, "_profile_loop", False):   # bench.py: per-kernel timing of the loop only
             eng.profile_begin()
@@ -443,6 +453,7 @@ class SAID(ABC, nn.Module):
             eta_noise=eta_noise, intermediates=inter, latents_out=latents_out, use_graph=self.use_cuda_graph,
             scheduler=1 if is_ddpm else 0,
         )
+        eng.check_status()     # synchronises; raises if the fp16x3 path met an activation beyond fp16's range
         if show_process:
             from tqdm import tqdm
 

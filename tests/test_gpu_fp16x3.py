@@ -1,0 +1,199 @@
+"""GPU tests of the fp16x3 path: the TMA-fed tcgen05 kind::f16 GEMM over fp16 hi/lo operand pairs (gemm_h.cuh), the kernels that
+produce pair-format operands, and the denoiser forward / step loop built from them -- against fp64 torch math, the golden
+vectors of the unmodified reference and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def maxdiff(a, b):
+    return float((torch.as_tensor(a).detach().cpu().double() - torch.as_tensor(b).detach().cpu().double()).abs().max())
+
+
+def _engine(gpu_model):
+    return gpu_model()._engine(torch.device(DEV))
+
+
+@pytest.mark.parametrize("M,Cin,N", [(128, 192, 192), (300, 192, 192), (1000, 64, 192), (4096, 768, 192), (2000, 192, 576),
+                                     (1500, 192, 1536), (19264, 192, 192), (38528, 192, 192), (700, 192, 32)])
+def test_gemm_h_plain_vs_fp64(gpu_model, M, Cin, N):
+    """out = A W + bias on the tensor cores with fp16 hi/lo operands (3 passes) against fp64: the error of an fp32 GEMM, not of
+    an fp16 one.  19264 / 38528 rows = 151 / 301 row tiles on 148 SMs: the leftover tiles run as N-slivers."""
+    eng = _engine(gpu_model)
+    g = torch.Generator().manual_seed(M + Cin + N)
+    a = torch.randn(M, Cin, generator=g) * (1.0 + 3.0 * torch.rand(M, 1, generator=g))
+    w = torch.randn(Cin, N, generator=g) / np.sqrt(Cin)
+    bias = torch.randn(N, generator=g)
+    out = eng.op_gemm_h(a.to(DEV), w, 1, bias.to(DEV)).cpu()
+    ref = a.double() @ w.double() + bias.double()
+    err = maxdiff(out, ref)
+    scale = float(ref.abs().max())
+    print(f"gemm_h plain M={M} K={Cin} N={N}: max err {err:.3e} (|ref| max {scale:.2f})")
+    assert err < 4e-6 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("M,Cin,N", [(602, 192, 192), (1204, 384, 192), (38528, 192, 192), (903, 192, 32)])
+def test_gemm_h_conv3_vs_fp64(gpu_model, M, Cin, N):
+    """Conv1d(k=3, pad=1) as three row-shifted TMA boxes: rows m-1, m, m+1 (rows outside the tensor read as zero)."""
+    eng = _engine(gpu_model)
+    g = torch.Generator().manual_seed(7 * M + Cin + N)
+    a = torch.randn(M, Cin, generator=g)
+    w = torch.randn(3 * Cin, N, generator=g) / np.sqrt(3 * Cin)
+    out = eng.op_gemm_h(a.to(DEV), w, 3, None).cpu()
+    ad = a.double()
+    z = torch.zeros(1, Cin, dtype=torch.float64)
+    prev, nxt = torch.cat([z, ad[:-1]]), torch.cat([ad[1:], z])
+    wd = w.double()
+    ref = prev @ wd[:Cin] + ad @ wd[Cin:2 * Cin] + nxt @ wd[2 * Cin:]
+    err = maxdiff(out, ref)
+    print(f"gemm_h conv3 M={M} Cin={Cin} N={N}: max err {err:.3e}")
+    assert err < 4e-6 * max(1.0, float(ref.abs().max()))
+
+
+def test_gemm_h_small_and_large_magnitudes(gpu_model):
+    """The pair format keeps ~22 bits from 2^-3 up to fp16's range and an absolute error of 2^-25 below; weights are pre-scaled
+    by a power of two per matrix, so tiny weights lose nothing."""
+    eng = _engine(gpu_model)
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(512, 192, generator=g)
+    a[:128] *= 1e-3
+    a[128:256] *= 300.0
+    w = torch.randn(192, 192, generator=g) * 1e-4
+    out = eng.op_gemm_h(a.to(DEV), w, 1, None).cpu()
+    ref = a.double() @ w.double()
+    rel = ((out.double() - ref).abs().amax(dim=1) / ref.abs().amax(dim=1))
+    print("gemm_h magnitudes: rel err small rows", float(rel[:128].max()), "large rows", float(rel[128:256].max()), "unit rows", float(rel[256:].max()))
+    assert float(rel[128:].max()) < 4e-6
+    assert float(rel[:128].max()) < 1e-4      # |a| ~ 1e-3: the lo plane is an fp16 subnormal, absolute error 2^-25
+
+
+def test_fp16_overflow_is_reported(gpu_model):
+    eng = _engine(gpu_model)
+    a = torch.ones(128, 64)
+    a[5, 7] = 1.0e5
+    from said_b200._lib import SaidLibraryError
+
+    eng.op_gemm_h(a.to(DEV), torch.ones(64, 192), 1, None)
+    with pytest.raises(SaidLibraryError):
+        eng.check_status()
+    eng.check_status()      # cleared
+
+
+TAP_ORDER = ["input_blocks.0", "input_blocks.1.0", "input_blocks.1.1", "middle_block.0", "middle_block.1",
+             "middle_block.2", "output_blocks.0.0", "output_blocks.0.1", "output_blocks.1.0", "output_blocks.1.1"]
+
+
+def test_denoiser_forward_fp16x3_golden(golden_dir, gpu_model):
+    """One UNet forward on the fp16x3 path (forced on for this small problem) against the reference's own block activations
+    and output.  Same tolerance as the 3xTF32 mode (2e-4 on activations; the fp32 kernels: 2e-5)."""
+    gd = np.load(os.path.join(golden_dir, "denoiser_forward.npz"))
+    m = gpu_model()
+    eng = m._engine(torch.device(DEV))
+    eng.set_precision("fp16x3", 1, "fp32")
+    try:
+        out, taps = eng.denoiser_forward(torch.from_numpy(gd["x"]).to(DEV), torch.from_numpy(gd["t"]),
+                                         torch.from_numpy(gd["ctx"]).to(DEV), taps=True)
+    finally:
+        eng.set_precision(m.precision, 2048, m.encoder_precision)
+    errs = {name: maxdiff(taps[i].transpose(1, 2), gd["act_" + name]) for i, name in enumerate(TAP_ORDER) if "act_" + name in gd.files}
+    errs["out"] = maxdiff(out, gd["y64"])
+    print("fp16x3", errs)
+    assert all(v < 2e-4 for v in errs.values()), errs
+
+
+def _run(m, wave, noise, init=None, mask=None, steps=10, strength=1.0, gs=2.0):
+    wave = torch.as_tensor(wave).to(DEV)
+    T = int(wave.shape[1] / 16000 * 60)
+    cv = lambda a: None if a is None else torch.as_tensor(a).to(DEV)  # noqa: E731
+    with torch.no_grad():
+        return m._run(wave, cv(noise), cv(init), cv(mask), steps, strength, gs, 0.0, 0.0, T, False, False, None, return_latents=True)
+
+
+class _Mode:
+    def __init__(self, m, precision, tc_min_rows=0):
+        self.m, self.p, self.r = m, precision, tc_min_rows
+
+    def __enter__(self):
+        self.saved = (self.m.precision, self.m.tc_min_rows)
+        self.m.precision, self.m.tc_min_rows = self.p, self.r
+        return self.m
+
+    def __exit__(self, *a):
+        self.m.precision, self.m.tc_min_rows = self.saved
+        self.m._engine(torch.device(DEV)).set_precision(self.m.precision, 2048, self.m.encoder_precision)
+
+
+def test_chain_1000_steps_fp16x3(golden_dir, gpu_model):
+    """The 1000-step free-running v-prediction chain with every denoiser contraction on the fp16x3 path (forced on for this single
+    clip) against the reference: the stated tolerance of the tensor-core modes, 1e-3 (3xTF32 measures 2.6e-4)."""
+    from said_b200.synth import normalise_waveform, synthetic_waveform
+
+    gd = np.load(os.path.join(golden_dir, "chain_5s_1000steps_v_prediction.npz"))
+    wave = torch.from_numpy(normalise_waveform(synthetic_waveform(0, 5.0)))[None]
+    with _Mode(gpu_model("v_prediction"), "fp16x3", 1) as m:
+        out = _run(m, wave, gd["noise"], steps=1000)
+    e32, e64 = maxdiff(out.result, gd["result"]), maxdiff(out.result, gd["result64"])
+    print("fp16x3 1000-step chain", e32, e64)
+    assert e32 < 1e-3 and e64 < 1e-3
+
+
+def test_bench_shape_chain_fp16x3_vs_oracle(gpu_model, state_dict):
+    """32 clips x 5 s, CFG with the shared guidance prefix, 4 DDIM steps on the fp16x3 path against the CPU oracle (two clips)
+    and against the 3xTF32 mode of the same engine."""
+    from oracle import said_oracle as O
+    from said_b200.synth import synthetic_batch
+
+    B = 32
+    wave = synthetic_batch(B, 5.0)
+    g = torch.Generator().manual_seed(17)
+    noise = torch.randn(B, 300, 32, generator=g)
+    with _Mode(gpu_model("epsilon"), "fp16x3") as m:
+        out = _run(m, wave, noise, steps=4)
+    res, lat = out.result.cpu(), out.latents.cpu()
+    with _Mode(gpu_model("epsilon"), "tf32x3") as m:
+        lat_tf = _run(m, wave, noise, steps=4).latents.cpu()
+    sel = [0, B - 1]
+    with torch.no_grad():
+        ref, pre = O.inference(state_dict, wave[sel], num_inference_steps=4, guidance_scale=2.0, noise=noise[sel], return_preclamp=True)
+    e, ep, em = maxdiff(res[sel], ref), maxdiff(lat[sel], pre[-1]), maxdiff(lat, lat_tf)
+    print("fp16x3 bench-shape chain vs oracle: result", e, "pre-clamp", ep, "vs tf32x3 (all clips)", em)
+    assert bool(torch.isfinite(res).all())
+    assert e < 5e-4 and ep < 1e-3 and em < 1e-3
+
+
+def test_editing_fp16x3_and_mismatched_init_length(gpu_model, state_dict):
+    """Editing on the fp16x3 path at batch scale, with init_samples two frames SHORTER than the audio window (a previous result
+    cut to floor(len * 60 / 16000) frames used as --init_sample_path: the reference keeps the init length for the latents and
+    aligns the cross-attention with its general window, attention.py:170-189).  Also checked on the fp32 kernels (one clip)."""
+    from oracle import said_oracle as O
+    from said_b200.synth import synthetic_batch
+
+    m = gpu_model("epsilon")
+    B, T = 12, 298
+    wave = synthetic_batch(B, 5.0)                       # audio window: 300 frames
+    g = torch.Generator().manual_seed(31)
+    t = torch.arange(T, dtype=torch.float32)[None, :, None] / 60.0
+    init = (0.3 * (1.0 + torch.sin(6.2832 * (0.5 + torch.rand(B, 1, 32, generator=g)) * t))).clamp(0, 0.75)
+    noise = torch.randn(B, T, 32, generator=g)
+    mask = torch.zeros(B, T, 32)
+    mask[:, :90] = 1.0
+    mask[:, 210:] = 1.0
+    sel = [0, B - 1]
+    with torch.no_grad():
+        ref, _ = O.inference(state_dict, wave[sel], init_samples=init[sel], mask=mask[sel], num_inference_steps=20,
+                             guidance_scale=2.0, noise=noise[sel])
+    for mode in ("fp16x3", "fp32"):
+        with _Mode(m, mode, 1):
+            res = _run(m, wave, noise, init=init, mask=mask, steps=20).result.cpu()
+        assert res.shape == (B, T, 32)
+        kept = mask.bool()
+        assert torch.equal(res[kept], init.clamp(0, 1)[kept]), mode
+        e = maxdiff(res[sel], ref)
+        print("editing, init 298 frames vs 300-frame audio window:", mode, e)
+        assert e < 2e-3
