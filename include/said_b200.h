@@ -124,6 +124,11 @@ SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B,
 SAID_API int said_op_gemm_h(said_engine* e, const float* a_dev, int M, int Cin, int taps, const float* wt_host, int N,
                             const float* bias_dev, float* out_dev, void* stream);
 
+/* Diagnostics: average milliseconds of the fp16x3 GEMM (M rows, K = taps * Cin, N a multiple of 192) over `iters` launches on
+ * zero-filled scratch operands; dbg bits disable parts of the kernel (1 activation TMA loads, 2 weight copies, 4 epilogue I/O,
+ * 8 MMAs) to attribute time.  Synchronises. */
+SAID_API int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int N, int with_residual, int dbg, int iters, float* ms_out);
+
 /* The tcgen05 (3xTF32) self-attention kernel: head_dim 32, T <= 304 (longer sequences use the FFMA kernel). */
 SAID_API int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int B, int T, int heads, float* out_dev, void* stream);
 

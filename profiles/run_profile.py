@@ -18,13 +18,14 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--seconds", type=float, default=5.0)
 ap.add_argument("--graph", action="store_true")
-ap.add_argument("--precision", default="tf32x3")
+ap.add_argument("--precision", default=None)
 a = ap.parse_args()
 m = SAID_UNet1D()
 m.load_state_dict(synthetic_state_dict(0))
 m.to("cuda:0").eval()
 m.use_cuda_graph = a.graph
-m.precision = a.precision
+if a.precision:
+    m.precision = a.precision
 wave = synthetic_batch(a.batch, a.seconds).to("cuda:0")
 T = int(wave.shape[1] / 16000 * 60)
 torch.manual_seed(0)

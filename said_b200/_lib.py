@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "said_denoiser_forward",
     "said_check_status",
     "said_op_gemm_h",
+    "said_op_gemm_h_bench",
     "said_op_ddim_step",
     "said_op_self_attention",
     "said_op_self_attention_tc",
@@ -109,6 +110,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, vp, vp]
     lib.said_check_status.argtypes = [vp, vp, ctypes.POINTER(ci)]
     lib.said_op_gemm_h.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, vp, vp]
+    lib.said_op_gemm_h_bench.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(cf)]
     lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, ci, vp]
     lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
     lib.said_op_self_attention_tc.argtypes = [vp, vp, ci, ci, ci, vp, vp]
@@ -353,6 +355,12 @@ class Engine:
         with torch.cuda.device(self.device):
             self._call(self.lib.said_op_gemm_h(self._h, a.data_ptr(), M, Cin, taps, w.ctypes.data, N, _ptr(b), out.data_ptr(), self._stream()))
         return out
+
+    def op_gemm_h_bench(self, M: int, Cin: int, taps: int = 1, N: int = 192, with_residual: bool = True, dbg: int = 0, iters: int = 10) -> float:
+        ms = ctypes.c_float()
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_op_gemm_h_bench(self._h, M, Cin, taps, N, int(with_residual), dbg, iters, ctypes.byref(ms)))
+        return float(ms.value)
 
     def op_gemm_tc_bench(self, M: int, K: int, nsplit: int = 3, with_residual: bool = True, dbg: int = 0, iters: int = 10) -> float:
         ms = ctypes.c_float()

@@ -164,7 +164,7 @@ struct said_engine {
     struct HSrc { const __half* base; int C; long long rows; };
     struct HSegSpec { HSrc src; int col0, ncols, row_shift; };
     template <class EP>
-    int gemm_h(cudaStream_t st, int M, int N, std::initializer_list<HSegSpec> segs, const float* wkey, EP ep, int tag) {
+    int gemm_h(cudaStream_t st, int M, int N, std::initializer_list<HSegSpec> segs, const float* wkey, EP ep, int tag, int dbg = 0) {
         auto it = hmap.find(wkey);
         if (it == hmap.end()) return fail("fp16x3 gemm: weight image not registered");
         const HW& w = it->second;
@@ -196,6 +196,7 @@ struct said_engine {
         p.nmaps = nmaps;
         p.w_block_bytes = 2 * w.bn * hx::HROW;
         p.sliver = 1;
+        p.dbg = dbg;
         ep.acc_scale = std::ldexp(1.0f, -w.exp);
         cur_tag = tag;
         cudaError_t e = cudaErrorInvalidValue;
@@ -1766,6 +1767,48 @@ int said_denoiser_forward(said_engine* e, const float* x_dev, const float* times
     if (e->use_h(Bp * T)) CKI(e->forward_h(st, x_dev, Bp, Bp, 0, T, e->emb_tab.p, nullptr, out_dev, taps_dev));
     else CKI(e->forward(st, x_dev, Bp, Bp, 0, T, e->emb_tab.p, nullptr, out_dev, taps_dev));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int N, int with_residual, int dbg, int iters, float* ms_out) {
+    // diagnostics: average milliseconds of the fp16x3 GEMM on scratch (zero) operands, with parts of it disabled by dbg
+    if (!e || !ms_out) return fail("said_op_gemm_h_bench: bad arguments");
+    if (!(taps == 1 || taps == 3) || Cin % hx::HBK != 0 || N % 192 != 0) return fail("said_op_gemm_h_bench: unsupported shape");
+    CK(cudaSetDevice(e->device));
+    static DevBuf a, o, r;
+    CK(a.ensure_zero((size_t)M * Cin));
+    CK(o.ensure_zero((size_t)M * N));
+    CK(r.ensure_zero((size_t)M * N));
+    const int K = taps * Cin;
+    const size_t wbytes = (size_t)(N / 192) * (K / hx::HBK) * 2 * 192 * hx::HROW;
+    uint8_t* wd = nullptr;
+    CK(cudaMalloc((void**)&wd, wbytes));
+    CK(cudaMemset(wd, 0, wbytes));
+    const float* key = reinterpret_cast<const float*>(wd);
+    e->hmap[key] = said_engine::HW{wd, K, N, 192, 0};
+    const said_engine::HSrc src{reinterpret_cast<const __half*>(a.p), Cin, M};
+    EpiStd ep = mk_epi(o.p, N, N);
+    if (with_residual) { ep.res = r.p; ep.ldr = N; }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    int rc = 0;
+    for (int it = -2; it < iters && rc == 0; ++it) {
+        if (it == 0) CK(cudaEventRecord(e0, 0));
+        if (taps == 1) rc = e->gemm_h((cudaStream_t)0, M, N, {{src, 0, Cin, 0}}, key, ep, said_engine::TAG_GEMM_PLAIN, dbg);
+        else rc = e->gemm_h((cudaStream_t)0, M, N, {{src, 0, Cin, -1}, {src, 0, Cin, 0}, {src, 0, Cin, 1}}, key, ep, said_engine::TAG_GEMM_CONV, dbg);
+    }
+    cudaError_t se = cudaEventRecord(e1, 0);
+    if (se == cudaSuccess) se = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (se == cudaSuccess) se = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    e->hmap.erase(key);
+    cudaFree(wd);
+    if (rc != 0) return rc;
+    CK(se);
+    *ms_out = ms / iters;
     return 0;
 }
 

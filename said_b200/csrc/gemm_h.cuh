@@ -85,6 +85,7 @@ struct HParams {
     HSeg seg[H_MAX_SEG];
     int w_block_bytes;       // bytes between consecutive (n-tile, k-chunk) blocks of the weight image (2 * BN * 128)
     int sliver;              // 0: leftover tiles are not cut into slivers
+    int dbg;                 // diagnostics (said_op_gemm_h_bench): 1 no activation loads, 2 no weight copies, 4 no epilogue I/O, 8 no MMAs
 };
 
 template <int BN>
@@ -184,7 +185,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
         const int q = warp & 3, half = warp >> 2;
         const int lr = lane >> 2, lq = lane & 3;
         const uint32_t stg = epi_base + (uint32_t)warp * (32 * 16 * 4);
-        const bool has_res = ep.tc_has_res();
+        const bool has_res = ep.tc_has_res() && !(p.dbg & 4);
         float4 pf[EPI_PF][4];
 #pragma unroll
         for (int jj = 0; jj < EPI_PF; ++jj)
@@ -232,7 +233,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                         float4 acc;
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "r"(a));
                         const int m = mrow0 + 8 * ii;
-                        if (m < p.M) ep.store4(rc[ii], m, n, acc, pf[jj % EPI_PF][ii]);
+                        if (m < p.M && !(p.dbg & 4)) ep.store4(rc[ii], m, n, acc, pf[jj % EPI_PF][ii]);
                     }
                     __syncwarp();
                     const int jn = j + 2 * EPI_PF;
@@ -265,7 +266,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                     const uint64_t dah = make_desc(a_st(sa)), dal = make_desc(a_st(sa) + A_PLANE);
                     const uint64_t dbh = make_desc(b_st(sb) + boff), dbl = make_desc(b_st(sb) + Cfg::B_PLANE + boff);
 #pragma unroll
-                    for (int k4 = 0; k4 < HBK / 16; ++k4) {
+                    for (int k4 = 0; k4 < ((p.dbg & 8) ? 0 : HBK / 16); ++k4) {
                         const uint64_t adv = (uint64_t)(k4 * 2);   // 16 fp16 = 32 bytes = 2 x 16-byte units along K
                         mma_f16(tacc, dah + adv, dbh + adv, idesc, (kc | k4) != 0 ? 1u : 0u);
                         mma_f16(tacc, dal + adv, dbh + adv, idesc, 1u);
@@ -292,9 +293,13 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                     const CUtensorMap* map = &p.maps[sg.map];
                     for (int j = 0; j < sg.nchunks; ++j) {
                         mbar_wait(emptya_bar(sa), pa ^ 1u);
-                        mbar_arrive_expect_tx(fulla_bar(sa), (uint32_t)A_STAGE);
-                        tma_load_2d(a_st(sa), map, sg.col0 + j * HBK, m0 + sg.row_shift, fulla_bar(sa));
-                        tma_load_2d(a_st(sa) + A_PLANE, map, sg.lo_off + sg.col0 + j * HBK, m0 + sg.row_shift, fulla_bar(sa));
+                        if (p.dbg & 1) {
+                            mbar_arrive(fulla_bar(sa));
+                        } else {
+                            mbar_arrive_expect_tx(fulla_bar(sa), (uint32_t)A_STAGE);
+                            tma_load_2d(a_st(sa), map, sg.col0 + j * HBK, m0 + sg.row_shift, fulla_bar(sa));
+                            tma_load_2d(a_st(sa) + A_PLANE, map, sg.lo_off + sg.col0 + j * HBK, m0 + sg.row_shift, fulla_bar(sa));
+                        }
                         if (++sa == AS) { sa = 0; pa ^= 1u; }
                     }
                 }
@@ -313,7 +318,9 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                 for (int kc = 0; kc < nk; ++kc) {
                     mbar_wait(emptyb_bar(sb), pb ^ 1u);
                     const uint8_t* blk = wsrc + (size_t)kc * p.w_block_bytes;
-                    if (it_.nw == BN) {
+                    if (p.dbg & 2) {
+                        mbar_arrive(fullb_bar(sb));
+                    } else if (it_.nw == BN) {
                         mbar_arrive_expect_tx(fullb_bar(sb), bytes);
                         tc::bulk_g2s(b_st(sb), blk, bytes, fullb_bar(sb));
                     } else {   // sliver: only its rows of the hi and lo planes

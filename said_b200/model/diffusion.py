@@ -175,7 +175,7 @@ class SAID(ABC, nn.Module):
         # contraction precision of the denoiser GEMMs: "tf32x3" (tcgen05, 3xTF32 split: fp32-level accuracy),
         # "fp16x3" (tcgen05 over fp16 hi/lo operand pairs loaded by TMA: same accuracy class at twice the tensor-core rate),
         # "tf32" (tcgen05, single pass) or "fp32" (FFMA); GEMMs below tc_min_rows rows stay on the FFMA kernel
-        self.precision = "tf32x3"
+        self.precision = "fp16x3"
         self.encoder_precision = "fp32"   # the audio encoder runs once per clip: IEEE fp32 unless asked otherwise
         self.tc_min_rows = 0
 

@@ -35,7 +35,7 @@ def test_gemm_h_plain_vs_fp64(gpu_model, M, Cin, N):
     err = maxdiff(out, ref)
     scale = float(ref.abs().max())
     print(f"gemm_h plain M={M} K={Cin} N={N}: max err {err:.3e} (|ref| max {scale:.2f})")
-    assert err < 4e-6 * max(1.0, scale)
+    assert err < 8e-6 * max(1.0, scale)
 
 
 @pytest.mark.parametrize("M,Cin,N", [(602, 192, 192), (1204, 384, 192), (38528, 192, 192), (903, 192, 32)])
@@ -53,7 +53,7 @@ def test_gemm_h_conv3_vs_fp64(gpu_model, M, Cin, N):
     ref = prev @ wd[:Cin] + ad @ wd[Cin:2 * Cin] + nxt @ wd[2 * Cin:]
     err = maxdiff(out, ref)
     print(f"gemm_h conv3 M={M} Cin={Cin} N={N}: max err {err:.3e}")
-    assert err < 4e-6 * max(1.0, float(ref.abs().max()))
+    assert err < 8e-6 * max(1.0, float(ref.abs().max()))
 
 
 def test_gemm_h_small_and_large_magnitudes(gpu_model):

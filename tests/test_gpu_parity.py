@@ -201,11 +201,12 @@ def test_chain_1000_steps_tensor_core_mode(golden_dir, gpu_model, pt):
     gd = load(golden_dir, f"chain_5s_1000steps_{pt}.npz")
     wave = torch.from_numpy(normalise_waveform(synthetic_waveform(0, 5.0)))[None]
     m = gpu_model(pt)
-    m.tc_min_rows = 1
+    default = m.precision
+    m.tc_min_rows, m.precision = 1, "tf32x3"
     try:
         out = run(m, wave, gd["noise"], steps=1000)
     finally:
-        m.tc_min_rows = 0
+        m.tc_min_rows, m.precision = 0, default
         m._engine(torch.device(DEV)).set_precision(m.precision, 2048, "fp32")
     e32, e64 = maxdiff(out.result, gd["result"]), maxdiff(out.result, gd["result64"])
     print("tensor-core chain", pt, e32, e64)
@@ -292,12 +293,13 @@ def test_batched_tensor_core_chain_vs_oracle(gpu_model, state_dict):
     g = torch.Generator().manual_seed(9)
     noise = torch.randn(40, 60, 32, generator=g)
     res = {}
+    default = m.precision
     for mode in ("tf32x3", "fp32", "tf32"):
         m.precision = mode
         try:
             res[mode] = run(m, wave, noise, steps=10).result.cpu()
         finally:
-            m.precision = "tf32x3"
+            m.precision = default
     e_modes = maxdiff(res["tf32x3"], res["fp32"])
     e_tf32 = maxdiff(res["tf32"], res["fp32"])
     with torch.no_grad():
