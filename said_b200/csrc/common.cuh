@@ -60,6 +60,23 @@ SAID_DEVINL float silu(float x) { return x / (1.0f + expf(-x)); }
 // exact (erf) GELU: attention.py:32 F.gelu default, transformers "gelu" activation
 SAID_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// exact-GELU with erf from Abramowitz & Stegun 7.1.26 on the hardware exp2 / reciprocal units: |gelu error| <= 5e-7 (a few fp32 ulps
+// at 1.0) for a third of erff's instructions.  Used by the tensor-core GEGLU epilogue, where the activation math -- not the MMA --
+// was the per-tile critical path.
+SAID_DEVINL float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+    const float erf_abs = fmaf(-pl * t, e, 1.0f);           // erf(|x| / sqrt 2)
+    return 0.5f * x + 0.5f * fabsf(x) * erf_abs;             // x * Phi(x):  0.5 x (1 + sign(x) erf(|x|/sqrt 2))
+}
+
 SAID_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

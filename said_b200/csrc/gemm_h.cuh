@@ -48,7 +48,8 @@ constexpr int HBK = 64;                     // fp16 elements per stage row: 128 
 constexpr int HROW = 128;                   // bytes per stage row
 constexpr int A_PLANE = HBM * HROW;         // 16 KB: one plane (hi or lo) of an activation stage
 constexpr int A_STAGE = 2 * A_PLANE;
-constexpr int H_EPI_WARPS = 8;
+constexpr int H_EPI_WARPS = 16;                     // 4 per TMEM lane quarter: the epilogue is latency-bound (TMEM -> smem -> global)
+constexpr int H_EPI_PARTS = H_EPI_WARPS / 4;         // warps sharing a lane quarter split the 16-column chunks round-robin
 constexpr int H_THREADS = (H_EPI_WARPS + 3) * 32;   // + MMA warp, activation-TMA warp, weight-copy warp
 constexpr int H_MAX_SEG = 4;
 static_assert(tc::ROW_BYTES == HROW, "make_desc() assumes 128-byte rows");
@@ -180,9 +181,9 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
     if (warp < H_EPI_WARPS) {
         // ===================== epilogue (same structure as gemm_tc_kernel) =====================
         constexpr int NCH = BN / 16;
-        constexpr int MYCH = (NCH + 1) / 2;
+        constexpr int MYCH = (NCH + H_EPI_PARTS - 1) / H_EPI_PARTS;
         constexpr int EPI_PF = MYCH < 2 ? MYCH : 2;
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, half = warp >> 2;          // lane quarter; part of the chunk round-robin
         const int lr = lane >> 2, lq = lane & 3;
         const uint32_t stg = epi_base + (uint32_t)warp * (32 * 16 * 4);
         const bool has_res = ep.tc_has_res() && !(p.dbg & 4);
@@ -204,7 +205,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
             if (has_res) {
 #pragma unroll
                 for (int jj = 0; jj < EPI_PF; ++jj) {
-                    const int j = 2 * jj + half;
+                    const int j = H_EPI_PARTS * jj + half;
 #pragma unroll
                     for (int ii = 0; ii < 4; ++ii) pf[jj][ii] = ep.tc_prefetch4(rc[ii], ncol0 + (j < nch_i ? j : 0) * 16 + lq * 4);
                 }
@@ -214,7 +215,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::ACC_STRIDE);
 #pragma unroll
             for (int jj = 0; jj < MYCH; ++jj) {
-                const int j = 2 * jj + half;
+                const int j = H_EPI_PARTS * jj + half;
                 if (j < nch_i) {                           // warp-uniform
                     float v[16];
                     tmem_ld16(taddr + j * 16, v);
@@ -236,7 +237,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                         if (m < p.M && !(p.dbg & 4)) ep.store4(rc[ii], m, n, acc, pf[jj % EPI_PF][ii]);
                     }
                     __syncwarp();
-                    const int jn = j + 2 * EPI_PF;
+                    const int jn = j + H_EPI_PARTS * EPI_PF;
                     if (has_res && jn < nch_i) {
 #pragma unroll
                         for (int ii = 0; ii < 4; ++ii) pf[jj % EPI_PF][ii] = ep.tc_prefetch4(rc[ii], ncol0 + jn * 16 + lq * 4);
@@ -249,21 +250,32 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
     } else if (warp == H_EPI_WARPS) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            int sa = 0, sb = 0;
+            int sa = 0, sb = 0, sa0 = 0;
             uint32_t pa = 0, pb = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int buf = i & 1;
                 const Item it_ = item(i);
+                // A-stationary: when the whole K extent fits the activation ring, consecutive n-tiles of one row block reuse the
+                // stages the first of them loaded (GEGLU: 8 n-tiles, q/k/v: 3) instead of reloading them from L2
+                const bool a_first = !(nk <= AS && i > 0 && item(i - 1).mt == it_.mt);
+                const bool a_last = !(nk <= AS && i + 1 < my_tiles && item(i + 1).mt == it_.mt);
+                if (a_first) sa0 = sa;
                 const uint32_t idesc = make_idesc_f16(HBM, it_.nw);
                 const uint32_t boff = (uint32_t)it_.n0 * HROW;               // n0 is a multiple of 16 rows: whole swizzle atoms
                 mbar_wait(acce_bar(buf), ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_STRIDE);
                 for (int kc = 0; kc < nk; ++kc) {
-                    mbar_wait(fulla_bar(sa), pa);
+                    int sa_use = sa;
+                    if (a_first) {
+                        mbar_wait(fulla_bar(sa), pa);
+                    } else {
+                        sa_use = sa0 + kc;
+                        if (sa_use >= AS) sa_use -= AS;
+                    }
                     mbar_wait(fullb_bar(sb), pb);
                     tc_fence_after();
-                    const uint64_t dah = make_desc(a_st(sa)), dal = make_desc(a_st(sa) + A_PLANE);
+                    const uint64_t dah = make_desc(a_st(sa_use)), dal = make_desc(a_st(sa_use) + A_PLANE);
                     const uint64_t dbh = make_desc(b_st(sb) + boff), dbl = make_desc(b_st(sb) + Cfg::B_PLANE + boff);
 #pragma unroll
                     for (int k4 = 0; k4 < ((p.dbg & 8) ? 0 : HBK / 16); ++k4) {
@@ -272,9 +284,9 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                         mma_f16(tacc, dal + adv, dbh + adv, idesc, 1u);
                         mma_f16(tacc, dah + adv, dbl + adv, idesc, 1u);
                     }
-                    mma_commit(emptya_bar(sa));
+                    if (a_last) mma_commit(emptya_bar(sa_use));      // the stage is free once the LAST n-tile's MMAs have read it
                     mma_commit(emptyb_bar(sb));
-                    if (++sa == AS) { sa = 0; pa ^= 1u; }
+                    if (a_first && ++sa == AS) { sa = 0; pa ^= 1u; }
                     if (++sb == BS) { sb = 0; pb ^= 1u; }
                 }
                 mma_commit(accf_bar(buf));
@@ -288,6 +300,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
             uint32_t pa = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int m0 = item(i).mt * HBM;
+                if (nk <= AS && i > 0 && item(i - 1).mt == item(i).mt) continue;   // A-stationary (see the MMA issuer)
                 for (int s = 0; s < p.nseg; ++s) {
                     const HSeg sg = p.seg[s];
                     const CUtensorMap* map = &p.maps[sg.map];

@@ -532,8 +532,8 @@ struct EpiGegluPair {
     SAID_DEVINL void store4(const RowCtx&, int m, int n, float4 a, float4) const {
         if (n >= N) return;
         const float4 bq = ldg4(bias + n);
-        const float o0 = (a.x * acc_scale + bq.x) * gelu_erf(a.y * acc_scale + bq.y);
-        const float o1 = (a.z * acc_scale + bq.z) * gelu_erf(a.w * acc_scale + bq.w);
+        const float o0 = (a.x * acc_scale + bq.x) * gelu_erf_fast(a.y * acc_scale + bq.y);
+        const float o1 = (a.z * acc_scale + bq.z) * gelu_erf_fast(a.w * acc_scale + bq.w);
         const __half2 h = __floats2half2_rn(o0, o1);
         const float2 hf = __half22float2(h);
         const __half2 l = __floats2half2_rn(o0 - hf.x, o1 - hf.y);
