@@ -132,6 +132,10 @@ SAID_API int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int 
 /* The tcgen05 (3xTF32) self-attention kernel: head_dim 32, T <= 304 (longer sequences use the FFMA kernel). */
 SAID_API int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int B, int T, int heads, float* out_dev, void* stream);
 
+/* The fp16x3 self-attention kernel (attention_h.cuh): tcgen05 kind::f16 over fp16 hi/lo pairs, online softmax with the
+ * probabilities kept in tensor memory, head_dim 32, T <= 512. */
+SAID_API int said_op_self_attention_h(said_engine* e, const float* qkv_dev, int B, int T, int heads, float* out_dev, void* stream);
+
 /* Number of kernels this engine has launched (graph replays counted node by node). */
 SAID_API long long said_launch_count(const said_engine* e);
 /* Number of times said_denoise had to capture + instantiate its per-step CUDA graph (the instantiated graph is cached and

@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "said_op_ddim_step",
     "said_op_self_attention",
     "said_op_self_attention_tc",
+    "said_op_self_attention_h",
     "said_launch_count",
     "said_graph_captures",
     "said_op_gemm_tc_bench",
@@ -114,6 +115,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, ci, vp]
     lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
     lib.said_op_self_attention_tc.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.said_op_self_attention_h.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.said_launch_count.argtypes = [vp]
     lib.said_launch_count.restype = ctypes.c_longlong
     lib.said_graph_captures.argtypes = [vp]
@@ -341,6 +343,15 @@ class Engine:
         out = torch.empty((B, T, heads * 32), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._call(self.lib.said_op_self_attention_tc(self._h, qkv.data_ptr(), B, T, heads, out.data_ptr(), self._stream()))
+        return out
+
+    def op_self_attention_h(self, qkv: torch.Tensor, heads: int) -> torch.Tensor:
+        qkv = _check_dev(qkv, self.device, "qkv")
+        B, T, W = qkv.shape
+        assert W == 3 * heads * 32
+        out = torch.empty((B, T, heads * 32), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_op_self_attention_h(self._h, qkv.data_ptr(), B, T, heads, out.data_ptr(), self._stream()))
         return out
 
     def op_gemm_h(self, a: torch.Tensor, wt: torch.Tensor, taps: int = 1, bias: Optional[torch.Tensor] = None) -> torch.Tensor:

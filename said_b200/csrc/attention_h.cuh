@@ -1,0 +1,342 @@
+// Self-attention on tcgen05 with fp16 hi/lo operand pairs ("fp16x3"), flash-style, head dim 32, any T <= 512.
+//
+//   out = softmax(q k^T * scale) v          (CrossAttention.forward with context=None, ldm/attention.py:86-128)
+//
+// One CTA per (head, sample), TWO CTAs resident per SM (256 TMEM columns and ~99 KB of shared memory each at T = 300): the kernel is
+// a chain of short dependent phases (MMA -> softmax -> MMA), so the second CTA fills the first one's latency bubbles.
+//   * K and V^T of the head are staged once: fp32 -> fp16 hi/lo, each row [hi(32 dims) | lo(32 dims)] = one 128-byte
+//     SWIZZLE_128B row, so the three passes of the split product (hi*hi + lo*hi + hi*lo) are just different 32-byte K-slices of
+//     the same tiles; V^T per 64 keys is a 64-row tile [hi dims | lo dims] x 64 keys.
+//   * per tile of 128 queries (Q pre-multiplied by scale * log2 e) and per block of 128 keys:
+//       S(128 x 128) = Q K^T into TMEM; two threads per row read their 64 scores ONCE, keep the running row maximum / sum
+//       (online softmax), and write P = exp2(S - m) back to TMEM IN PLACE as packed fp16 hi / lo (P never touches shared
+//       memory); the running output O (in TMEM) is rescaled when the maximum moved; then
+//       O[:, 0:64] += P_hi [V_hi | V_lo],  O[:, 0:32] += P_lo V_hi      (A operand from TMEM: the "TS" form of tcgen05.mma)
+//   * (O[:, 0:32] + O[:, 32:64]) / rowsum -> global, as fp32 or directly in the pair format of the next GEMM's operand.
+#pragma once
+#include "gemm_h.cuh"
+
+namespace said {
+namespace hx {
+
+constexpr int AH_HD = 32;
+constexpr int AH_SM_THREADS = 256;                 // warps 0-7: staging / softmax / epilogue, two threads per query row
+constexpr int AH_MMA_WARP = AH_SM_THREADS / 32;    // warp 8: MMA issuer
+constexpr int AH_THREADS = AH_SM_THREADS + 32;
+constexpr int AH_KB = 128;                         // keys per block
+constexpr int AH_S_COL = 0;                        // TMEM columns [0, 128): scores, then P_hi (cols 0-63) | P_lo (cols 64-127) packed 2 per column
+constexpr int AH_O_COL = 128;                      // TMEM columns [128, 192): output accumulators
+constexpr int AH_TMEM_COLS = 256;
+constexpr int AH_MAXT = 512;
+
+inline size_t attention_h_smem_bytes(int T) {
+    const int Tkp = (T + 15) / 16 * 16;
+    const int nch = (T + 63) / 64;
+    return (size_t)Tkp * 128 + 1024 /*V tile alignment*/ + (size_t)nch * 8192 + 16384 /*Q*/ + 2 * AH_SM_THREADS * 4 + 64 + 1024;
+}
+
+SAID_DEVINL void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+SAID_DEVINL void tmem_st32u(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+          "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+          "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+SAID_DEVINL uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+SAID_DEVINL float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// eight fp32 values -> 16 bytes of fp16 hi and 16 bytes of fp16 lo
+SAID_DEVINL void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+SAID_DEVINL void sts16(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(AH_THREADS, 2)
+self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int T, float scale,
+                        float* __restrict__ out, int ldo, int Tstr /*rows per sample in qkv / out*/,
+                        __half* __restrict__ out_pair /*non-null: write the pair tensor (ldo columns) instead of fp32*/,
+                        int* __restrict__ flag) {
+    extern __shared__ uint8_t smem_raw[];
+    const int Tkp = (T + 15) / 16 * 16;
+    const int nch = (T + 63) / 64;                    // 64-key chunks of V^T
+    const int nkb = (T + AH_KB - 1) / AH_KB;          // 128-key blocks
+    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t k_sm = base;                                            // [Tkp rows][hi 64 B | lo 64 B]
+    const uint32_t v_sm = (k_sm + (uint32_t)Tkp * 128u + 1023u) & ~1023u;  // per 64-key chunk: [32 hi-dim rows | 32 lo-dim rows] x 128 B
+    const uint32_t q_sm = v_sm + (uint32_t)nch * 8192u;                    // [128 rows][hi | lo]
+    const uint32_t xch = q_sm + 16384u;                                    // float[2][AH_SM_THREADS]
+    const uint32_t bars = xch + 2u * AH_SM_THREADS * 4u;
+    const uint32_t bar_q = bars, bar_s = bars + 8u, bar_p = bars + 16u, bar_o = bars + 24u;
+    const uint32_t tmem_slot = bars + 32u;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const float* gbase = qkv + (long long)b * Tstr * ld + h * AH_HD;
+
+    if (tid == AH_SM_THREADS) {
+        mbar_init(bar_q, AH_SM_THREADS);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_p, AH_SM_THREADS);
+        mbar_init(bar_o, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == AH_MMA_WARP) tmem_alloc(tmem_slot, AH_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    pdl_trigger();
+    const int n_qtiles = (T + 127) / 128;
+
+    if (warp < AH_MMA_WARP) {
+        // ---------------- stage K: row = key, [hi dims | lo dims] ----------------
+        for (int i = tid; i < Tkp * 4; i += AH_SM_THREADS) {
+            const int key = i >> 2, c2 = i & 3;                  // dims 8 c2 .. 8 c2 + 7
+            float x[8];
+            if (key < T) {
+                const float4 a = ldg4(gbase + (long long)key * ld + k_off + c2 * 8), c = ldg4(gbase + (long long)key * ld + k_off + c2 * 8 + 4);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = 0.f;
+            }
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const uint32_t row = k_sm + (uint32_t)key * 128u;
+            sts16(row + (uint32_t)((c2 ^ (key & 7)) << 4), hi);
+            sts16(row + (uint32_t)(((4 + c2) ^ (key & 7)) << 4), lo);
+        }
+        // ---------------- stage V^T: per 64-key chunk, row = dim (hi rows 0-31, lo rows 32-63), 8 keys per 16-byte store ----------------
+        for (int i = tid; i < nch * 8 * 8; i += AH_SM_THREADS) {
+            const int kg = i >> 3, c4 = i & 7;                   // key group (8 keys), dims 4 c4 .. 4 c4 + 3
+            float4 xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int key = kg * 8 + u;
+                xv[u] = (key < T) ? ldg4(gbase + (long long)key * ld + v_off + c4 * 4) : zero4();
+            }
+            const int chunk = kg >> 3, kq = kg & 7;              // 16-byte slot of the 128-byte row
+            const float* xf = reinterpret_cast<const float*>(xv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float col[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) col[u] = xf[4 * u + e];
+                uint4 hi, lo;
+                split8(col, hi, lo);
+                const int dd = c4 * 4 + e;
+                const uint32_t tile = v_sm + (uint32_t)chunk * 8192u;
+                sts16(tile + (uint32_t)dd * 128u + (uint32_t)((kq ^ (dd & 7)) << 4), hi);
+                sts16(tile + (uint32_t)(32 + dd) * 128u + (uint32_t)((kq ^ ((32 + dd) & 7)) << 4), lo);
+            }
+        }
+        const int row = tid & 127, part = tid >> 7;            // two threads per query row: 64 of the 128 score columns each
+        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const float qscale = scale * 1.4426950408889634f;       // softmax in base 2
+        uint32_t n_s = 0, n_o = 0;
+        for (int qt = 0; qt < n_qtiles; ++qt) {
+            // ---------------- Q tile: 128 rows x [hi | lo], pre-scaled ----------------
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = tid + u * AH_SM_THREADS, r = i >> 2, c2 = i & 3;
+                float x[8];
+                if (qt * 128 + r < T) {
+                    const float* src = gbase + (long long)(qt * 128 + r) * ld + q_off + c2 * 8;
+                    const float4 a = ldg4(src), c = ldg4(src + 4);
+                    x[0] = a.x * qscale; x[1] = a.y * qscale; x[2] = a.z * qscale; x[3] = a.w * qscale;
+                    x[4] = c.x * qscale; x[5] = c.y * qscale; x[6] = c.z * qscale; x[7] = c.w * qscale;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+                }
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                const uint32_t ra = q_sm + (uint32_t)r * 128u;
+                sts16(ra + (uint32_t)((c2 ^ (r & 7)) << 4), hi);
+                sts16(ra + (uint32_t)(((4 + c2) ^ (r & 7)) << 4), lo);
+            }
+            tc_fence_before();                                 // (TMEM reads of the previous tile's O are complete)
+            tc::fence_proxy_async();
+            mbar_arrive(bar_q);
+            float m_run = -INFINITY, l_part = 0.f;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int nvalid = min(AH_KB, T - kb * AH_KB);         // valid keys of this block
+                const int my0 = part * 64;                              // first column of this thread
+                mbar_wait(bar_s, n_s & 1u);
+                ++n_s;
+                tc_fence_after();
+                float s[64];
+                const bool have = my0 < nvalid;                         // warp-uniform (part is)
+                if (have) {
+                    float (*s16)[16] = reinterpret_cast<float (*)[16]>(s);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) tc::tmem_ld16_issue(trow + AH_S_COL + my0 + 16 * u, s16[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) tc::tmem_ld_wait16(s16[u]);
+                }
+                float mx = -INFINITY;
+                if (have) {
+                    if (my0 + 64 <= nvalid) {
+#pragma unroll
+                        for (int e = 0; e < 64; ++e) mx = fmaxf(mx, s[e]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 64; ++e)
+                            if (my0 + e < nvalid) mx = fmaxf(mx, s[e]);
+                    }
+                }
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)tid * 4u), "f"(mx) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(AH_SM_THREADS) : "memory");   // also: every thread holds its scores in registers now
+                float other;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + (uint32_t)(tid ^ 128) * 4u));
+                const float m_new = fmaxf(m_run, fmaxf(mx, other));
+                const float alpha = ex2f(m_run - m_new);                // 0 on the first block (m_run = -inf)
+                m_run = m_new;
+                // P = 2^(s - m) as packed fp16 hi / lo, written over the score columns
+                uint32_t ph[32], pl[32];
+                float ls = 0.f;
+#pragma unroll
+                for (int w = 0; w < 32; ++w) {
+                    float p0 = 0.f, p1 = 0.f;
+                    if (have) {
+                        p0 = (my0 + 2 * w < nvalid) ? ex2f(s[2 * w] - m_new) : 0.f;
+                        p1 = (my0 + 2 * w + 1 < nvalid) ? ex2f(s[2 * w + 1] - m_new) : 0.f;
+                    }
+                    ls += p0 + p1;
+                    const __half2 hh = __floats2half2_rn(p0, p1);
+                    const float2 hf = __half22float2(hh);
+                    ph[w] = *reinterpret_cast<const uint32_t*>(&hh);
+                    pl[w] = pack_h2(p0 - hf.x, p1 - hf.y);
+                }
+                l_part = l_part * alpha + ls;
+                tmem_st32u(trow + AH_S_COL + part * 32, ph);
+                tmem_st32u(trow + AH_S_COL + 64 + part * 32, pl);
+                // rescale the running output when the maximum moved (warp-uniform decision: tcgen05.ld/st are warp-wide)
+                if (kb > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+                    float o[32];
+                    float (*o16)[16] = reinterpret_cast<float (*)[16]>(o);
+                    tc::tmem_ld16_issue(trow + AH_O_COL + part * 32, o16[0]);
+                    tc::tmem_ld16_issue(trow + AH_O_COL + part * 32 + 16, o16[1]);
+                    tc::tmem_ld_wait16(o16[0]);
+                    tc::tmem_ld_wait16(o16[1]);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) o[e] *= alpha;
+                    tc::tmem_st32(trow + AH_O_COL + part * 32, o);
+                }
+                tc::tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar_p);
+            }
+            // ---------------- O / rowsum -> global ----------------
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(AH_SM_THREADS + tid) * 4u), "f"(l_part) : "memory");
+            mbar_wait(bar_o, n_o & 1u);
+            ++n_o;
+            tc_fence_after();
+            asm volatile("bar.sync 1, %0;" ::"n"(AH_SM_THREADS) : "memory");
+            float l_other;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xch + (uint32_t)(AH_SM_THREADS + (tid ^ 128)) * 4u));
+            const float inv = 1.0f / (l_part + l_other);
+            float oa[16], ob[16];
+            tc::tmem_ld16_issue(trow + AH_O_COL + part * 16, oa);            // dims 16 part .. +15 of the P V_hi terms
+            tc::tmem_ld16_issue(trow + AH_O_COL + 32 + part * 16, ob);       // ... of the P_hi V_lo term
+            tc::tmem_ld_wait16(oa);
+            tc::tmem_ld_wait16(ob);
+            const int q = qt * 128 + row;
+            if (q < T) {
+                const long long orow = (long long)b * Tstr + q;
+                float amax = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 ov = make_float4((oa[4 * c] + ob[4 * c]) * inv, (oa[4 * c + 1] + ob[4 * c + 1]) * inv,
+                                                  (oa[4 * c + 2] + ob[4 * c + 2]) * inv, (oa[4 * c + 3] + ob[4 * c + 3]) * inv);
+                    const int col = h * AH_HD + part * 16 + 4 * c;
+                    if (out_pair != nullptr) {
+                        store_pair4(out_pair, orow, ldo, col, ov);
+                        amax = amax4(amax, ov);
+                    } else {
+                        st4(out + orow * ldo + col, ov);
+                    }
+                }
+                if (amax > P16_LIMIT) atomicOr(flag, 1);
+            }
+        }
+    } else if (lane == 0) {
+        // ---------------- MMA issuer ----------------
+        uint32_t n_q = 0, n_p = 0;
+        const uint64_t dq = make_desc(q_sm);
+        for (int qt = 0; qt < n_qtiles; ++qt) {
+            mbar_wait(bar_q, n_q & 1u);
+            ++n_q;
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int nvalid = min(AH_KB, T - kb * AH_KB);
+                const int nb = (nvalid + 15) / 16 * 16;                              // UMMA N of the score block
+                const uint32_t ids = make_idesc_f16(128, nb);
+                const uint64_t dk = make_desc(k_sm + (uint32_t)kb * AH_KB * 128u);
+                // S = Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T: the hi / lo halves are 32-byte K-slices 0,1 / 2,3 of the same 128-byte rows
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint64_t hi = (uint64_t)(k * 2), lo = (uint64_t)((2 + k) * 2);
+                    mma_f16(tmem_base + AH_S_COL, dq + hi, dk + hi, ids, k != 0 ? 1u : 0u);
+                    mma_f16(tmem_base + AH_S_COL, dq + lo, dk + hi, ids, 1u);
+                    mma_f16(tmem_base + AH_S_COL, dq + hi, dk + lo, ids, 1u);
+                }
+                mma_commit(bar_s);
+                mbar_wait(bar_p, n_p & 1u);
+                ++n_p;
+                tc_fence_after();
+                const int ksteps = (nvalid + 15) / 16;
+                const uint32_t id64 = make_idesc_f16(128, 64), id32 = make_idesc_f16(128, 32);
+                for (int j = 0; j < ksteps; ++j) {
+                    const int key0 = kb * AH_KB + 16 * j;
+                    const uint64_t dv = make_desc(v_sm + (uint32_t)(key0 >> 6) * 8192u) + (uint64_t)(((key0 & 63) >> 4) * 2);
+                    mma_f16_ts(tmem_base + AH_O_COL, tmem_base + AH_S_COL + 8 * j, dv, id64, (kb | j) != 0 ? 1u : 0u);   // P_hi [V_hi | V_lo]
+                    mma_f16_ts(tmem_base + AH_O_COL, tmem_base + AH_S_COL + 64 + 8 * j, dv, id32, 1u);                   // P_lo V_hi
+                }
+                if (kb == nkb - 1) mma_commit(bar_o);
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == AH_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, AH_TMEM_COLS);
+    }
+}
+
+}  // namespace hx
+}  // namespace said

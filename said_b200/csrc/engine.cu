@@ -21,6 +21,7 @@
 
 #include "../../include/said_b200.h"
 #include "attention.cuh"
+#include "attention_h.cuh"
 #include "attention_tc.cuh"
 #include "diffusion_kernels.cuh"
 #include "encoder_kernels.cuh"
@@ -412,6 +413,7 @@ struct said_engine {
                 const int* step_ptr, float* eps_out, float* taps);
     int forward_h(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T, const float* emb_table,
                   const int* step_ptr, float* eps_out, float* taps);
+    bool attn_h = getenv("SAID_ATTN_TF32") == nullptr;   // fp16x3 path: flash-style fp16 hi/lo attention (attention_h.cuh); the env switch keeps the 3xTF32 kernel reachable for A/B runs
     bool use_h(int M) const { return precision == 3 && M >= tc_min_rows && in_ch == 32; }
     int denoise(const said_denoise_args& a, cudaStream_t user);
 };
@@ -1114,6 +1116,9 @@ int said_engine::ensure_denoiser_ws(int Bp, int T) {
     if (T <= tc::ATC_MAXKEYS)
         CK(cudaFuncSetAttribute(tc::self_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)tc::attention_tc_smem_bytes(T)));
+    if (T <= hx::AH_MAXT)
+        CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)hx::attention_h_smem_bytes(T)));
     return 0;
 }
 
@@ -1455,7 +1460,10 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
             CKI(gemm_h(st, mh, 3 * C, {{psrc(pln, C, mh), 0, C, 0}}, W.wqkv, ep, TAG_GEMM_PLAIN));
         }
         cur_tag = TAG_ATTN;
-        if (T <= tc::ATC_MAXKEYS) {
+        if (T <= hx::AH_MAXT && attn_h) {
+            CK(launch_ex(hx::self_attention_h_kernel, dim3(HEADS, h_nb), dim3(hx::AH_THREADS), hx::attention_h_smem_bytes(T), st, pdl, 1,
+                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag));
+        } else if (T <= tc::ATC_MAXKEYS) {
             CK(launch_ex(tc::self_attention_tc_kernel, dim3(HEADS, h_nb), dim3(tc::ATC_THREADS), tc::attention_tc_smem_bytes(T), st, pdl, 1,
                          (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag));
         } else {
@@ -1929,6 +1937,20 @@ int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int B, int T
     const int Cw = heads * 32;
     CK(cudaFuncSetAttribute(tc::self_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::attention_tc_smem_bytes(T)));
     tc::self_attention_tc_kernel<<<dim3(heads, B), tc::ATC_THREADS, tc::attention_tc_smem_bytes(T), st>>>(
+        qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr);
+    ++e->launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int said_op_self_attention_h(said_engine* e, const float* qkv_dev, int B, int T, int heads, float* out_dev, void* stream) {
+    if (!e) return fail("null engine");
+    if (T > hx::AH_MAXT) return fail("self_attention_h: at most 512 keys");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Cw = heads * 32;
+    CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hx::attention_h_smem_bytes(T)));
+    hx::self_attention_h_kernel<<<dim3(heads, B), hx::AH_THREADS, hx::attention_h_smem_bytes(T), st>>>(
         qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr);
     ++e->launches;
     CK(cudaGetLastError());

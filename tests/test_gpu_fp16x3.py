@@ -85,6 +85,26 @@ def test_fp16_overflow_is_reported(gpu_model):
     eng.check_status()      # cleared
 
 
+@pytest.mark.parametrize("T,B", [(300, 2), (60, 3), (128, 1), (129, 1), (257, 2), (304, 1), (17, 2), (469, 2), (512, 1)])
+def test_self_attention_h_vs_fp64(gpu_model, T, B):
+    """Flash-style tcgen05 attention over fp16 hi/lo pairs (online softmax, probabilities kept in tensor memory) against fp64
+    math, including the longest sequence in the reference's data (469 frames); tolerance 2e-5 like the 3xTF32 kernel."""
+    eng = _engine(gpu_model)
+    heads, hd = 6, 32
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn(B, T, 3 * heads * hd, generator=g)
+    qkv[:, :, : heads * hd] *= 1.5        # sharper softmax than unit-variance q k: exercises the running-max rescale
+    qkv = qkv.to(DEV)
+    out = eng.op_self_attention_h(qkv, heads)
+    q, k, v = qkv.double().chunk(3, dim=-1)
+    sh = lambda t: t.reshape(B, T, heads, hd).transpose(1, 2)  # noqa: E731
+    ref = torch.softmax(sh(q) @ sh(k).transpose(-1, -2) * hd**-0.5, dim=-1) @ sh(v)
+    ref = ref.transpose(1, 2).reshape(B, T, heads * hd)
+    err = maxdiff(out, ref)
+    print("fp16x3 attention", T, err)
+    assert err < 2e-5
+
+
 TAP_ORDER = ["input_blocks.0", "input_blocks.1.0", "input_blocks.1.1", "middle_block.0", "middle_block.1",
              "middle_block.2", "output_blocks.0.0", "output_blocks.0.1", "output_blocks.1.0", "output_blocks.1.1"]
 
