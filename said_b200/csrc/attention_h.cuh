@@ -197,24 +197,27 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 mbar_wait(bar_s, n_s & 1u);
                 ++n_s;
                 tc_fence_after();
-                float s[64];
+                float s[4][16];
                 const bool have = my0 < nvalid;                         // warp-uniform (part is)
                 if (have) {
-                    float (*s16)[16] = reinterpret_cast<float (*)[16]>(s);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) tc::tmem_ld16_issue(trow + AH_S_COL + my0 + 16 * u, s16[u]);
+                    for (int u = 0; u < 4; ++u) tc::tmem_ld16_issue(trow + AH_S_COL + my0 + 16 * u, s[u]);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) tc::tmem_ld_wait16(s16[u]);
+                    for (int u = 0; u < 4; ++u) tc::tmem_ld_wait16(s[u]);
                 }
                 float mx = -INFINITY;
                 if (have) {
                     if (my0 + 64 <= nvalid) {
 #pragma unroll
-                        for (int e = 0; e < 64; ++e) mx = fmaxf(mx, s[e]);
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, s[u][e]);
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 64; ++e)
-                            if (my0 + e < nvalid) mx = fmaxf(mx, s[e]);
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                if (my0 + 16 * u + e < nvalid) mx = fmaxf(mx, s[u][e]);
                     }
                 }
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)tid * 4u), "f"(mx) : "memory");
@@ -231,8 +234,8 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 for (int w = 0; w < 32; ++w) {
                     float p0 = 0.f, p1 = 0.f;
                     if (have) {
-                        p0 = (my0 + 2 * w < nvalid) ? ex2f(s[2 * w] - m_new) : 0.f;
-                        p1 = (my0 + 2 * w + 1 < nvalid) ? ex2f(s[2 * w + 1] - m_new) : 0.f;
+                        p0 = (my0 + 2 * w < nvalid) ? ex2f(s[w >> 3][(2 * w) & 15] - m_new) : 0.f;
+                        p1 = (my0 + 2 * w + 1 < nvalid) ? ex2f(s[w >> 3][(2 * w + 1) & 15] - m_new) : 0.f;
                     }
                     ls += p0 + p1;
                     const __half2 hh = __floats2half2_rn(p0, p1);
@@ -245,14 +248,13 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 tmem_st32u(trow + AH_S_COL + 64 + part * 32, pl);
                 // rescale the running output when the maximum moved (warp-uniform decision: tcgen05.ld/st are warp-wide)
                 if (kb > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-                    float o[32];
-                    float (*o16)[16] = reinterpret_cast<float (*)[16]>(o);
-                    tc::tmem_ld16_issue(trow + AH_O_COL + part * 32, o16[0]);
-                    tc::tmem_ld16_issue(trow + AH_O_COL + part * 32 + 16, o16[1]);
-                    tc::tmem_ld_wait16(o16[0]);
-                    tc::tmem_ld_wait16(o16[1]);
+                    float o0[16], o1[16], o[32];
+                    tc::tmem_ld16_issue(trow + AH_O_COL + part * 32, o0);
+                    tc::tmem_ld16_issue(trow + AH_O_COL + part * 32 + 16, o1);
+                    tc::tmem_ld_wait16(o0);
+                    tc::tmem_ld_wait16(o1);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) o[e] *= alpha;
+                    for (int e = 0; e < 16; ++e) { o[e] = o0[e] * alpha; o[16 + e] = o1[e] * alpha; }
                     tc::tmem_st32(trow + AH_O_COL + part * 32, o);
                 }
                 tc::tmem_wait_st();

@@ -1116,9 +1116,12 @@ int said_engine::ensure_denoiser_ws(int Bp, int T) {
     if (T <= tc::ATC_MAXKEYS)
         CK(cudaFuncSetAttribute(tc::self_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)tc::attention_tc_smem_bytes(T)));
-    if (T <= hx::AH_MAXT)
+    if (T <= hx::AH_MAXT) {
         CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)hx::attention_h_smem_bytes(T)));
+        // two CTAs per SM need ~200 KB of the SM's unified L1 / shared memory: ask for the largest shared-memory carve-out
+        CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     return 0;
 }
 
@@ -1950,6 +1953,12 @@ int said_op_self_attention_h(said_engine* e, const float* qkv_dev, int B, int T,
     cudaStream_t st = (cudaStream_t)stream;
     const int Cw = heads * 32;
     CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hx::attention_h_smem_bytes(T)));
+    CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("SAID_DEBUG")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hx::self_attention_h_kernel, hx::AH_THREADS, hx::attention_h_smem_bytes(T));
+        fprintf(stderr, "[said] self_attention_h_kernel: T=%d smem=%zu B, resident CTAs per SM = %d\n", T, hx::attention_h_smem_bytes(T), nb);
+    }
     hx::self_attention_h_kernel<<<dim3(heads, B), hx::AH_THREADS, hx::attention_h_smem_bytes(T), st>>>(
         qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr);
     ++e->launches;
