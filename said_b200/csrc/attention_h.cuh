@@ -20,9 +20,9 @@ namespace said {
 namespace hx {
 
 constexpr int AH_HD = 32;
-constexpr int AH_SM_THREADS = 256;                 // warps 0-7: staging / softmax / epilogue, two threads per query row
-constexpr int AH_MMA_WARP = AH_SM_THREADS / 32;    // warp 8: MMA issuer
-constexpr int AH_THREADS = AH_SM_THREADS + 32;
+constexpr int AH_SM_THREADS = 256;                 // 8 warps: staging / softmax / epilogue, two threads per query row
+constexpr int AH_THREADS = AH_SM_THREADS;          // thread 0 also issues the MMAs: with a ninth warp one SM sub-partition would host 3 warps
+                                                   // per CTA and its 16 K registers could not hold two CTAs (measured: 1 CTA per SM)
 constexpr int AH_KB = 128;                         // keys per block
 constexpr int AH_S_COL = 0;                        // TMEM columns [0, 128): scores, then P_hi (cols 0-63) | P_lo (cols 64-127) packed 2 per column
 constexpr int AH_O_COL = 128;                      // TMEM columns [128, 192): output accumulators
@@ -102,7 +102,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
     const int h = blockIdx.x, b = blockIdx.y;
     const float* gbase = qkv + (long long)b * Tstr * ld + h * AH_HD;
 
-    if (tid == AH_SM_THREADS) {
+    if (tid == 0) {
         mbar_init(bar_q, AH_SM_THREADS);
         mbar_init(bar_s, 1);
         mbar_init(bar_p, AH_SM_THREADS);
@@ -110,7 +110,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
         fence_mbar_init();
     }
     __syncwarp();
-    if (warp == AH_MMA_WARP) tmem_alloc(tmem_slot, AH_TMEM_COLS);
+    if (warp == 0) tmem_alloc(tmem_slot, AH_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -120,7 +120,35 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
     pdl_trigger();
     const int n_qtiles = (T + 127) / 128;
 
-    if (warp < AH_MMA_WARP) {
+    // ---------------- MMA issue (thread 0 only, between its softmax duties) ----------------
+    const uint64_t dq = make_desc(q_sm);
+    const uint32_t id64 = make_idesc_f16(128, 64), id32 = make_idesc_f16(128, 32);
+    auto issue_s = [&](int kb) {     // S = Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T: hi / lo are the 32-byte K-slices 0,1 / 2,3 of the same 128-byte rows
+        const int nvalid = min(AH_KB, T - kb * AH_KB);
+        const uint32_t ids = make_idesc_f16(128, (nvalid + 15) / 16 * 16);
+        const uint64_t dk = make_desc(k_sm + (uint32_t)kb * AH_KB * 128u);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint64_t hi = (uint64_t)(k * 2), lo = (uint64_t)((2 + k) * 2);
+            mma_f16(tmem_base + AH_S_COL, dq + hi, dk + hi, ids, k != 0 ? 1u : 0u);
+            mma_f16(tmem_base + AH_S_COL, dq + lo, dk + hi, ids, 1u);
+            mma_f16(tmem_base + AH_S_COL, dq + hi, dk + lo, ids, 1u);
+        }
+        mma_commit(bar_s);
+    };
+    auto issue_pv = [&](int kb) {    // O[:, 0:64] += P_hi [V_hi | V_lo],  O[:, 0:32] += P_lo V_hi   (A operand = P in tensor memory)
+        const int nvalid = min(AH_KB, T - kb * AH_KB);
+        const int ksteps = (nvalid + 15) / 16;
+        for (int j = 0; j < ksteps; ++j) {
+            const int key0 = kb * AH_KB + 16 * j;
+            const uint64_t dv = make_desc(v_sm + (uint32_t)(key0 >> 6) * 8192u) + (uint64_t)(((key0 & 63) >> 4) * 2);
+            mma_f16_ts(tmem_base + AH_O_COL, tmem_base + AH_S_COL + 8 * j, dv, id64, (kb | j) != 0 ? 1u : 0u);
+            mma_f16_ts(tmem_base + AH_O_COL, tmem_base + AH_S_COL + 64 + 8 * j, dv, id32, 1u);
+        }
+    };
+    uint32_t n_q = 0, n_p = 0;
+
+    {
         // ---------------- stage K: row = key, [hi dims | lo dims] ----------------
         for (int i = tid; i < Tkp * 4; i += AH_SM_THREADS) {
             const int key = i >> 2, c2 = i & 3;                  // dims 8 c2 .. 8 c2 + 7
@@ -190,6 +218,13 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             tc_fence_before();                                 // (TMEM reads of the previous tile's O are complete)
             tc::fence_proxy_async();
             mbar_arrive(bar_q);
+            if (tid == 0) {
+                mbar_wait(bar_q, n_q & 1u);
+                ++n_q;
+                tc_fence_after();
+                issue_s(0);
+            }
+            __syncwarp();
             float m_run = -INFINITY, l_part = 0.f;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int nvalid = min(AH_KB, T - kb * AH_KB);         // valid keys of this block
@@ -260,6 +295,15 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 tc::tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar_p);
+                if (tid == 0) {
+                    mbar_wait(bar_p, n_p & 1u);
+                    ++n_p;
+                    tc_fence_after();
+                    issue_pv(kb);
+                    if (kb == nkb - 1) mma_commit(bar_o);
+                    else issue_s(kb + 1);                      // executes after the P V MMAs above (tcgen05.mma runs in issue order)
+                }
+                __syncwarp();
             }
             // ---------------- O / rowsum -> global ----------------
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(AH_SM_THREADS + tid) * 4u), "f"(l_part) : "memory");
@@ -294,47 +338,11 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 if (amax > P16_LIMIT) atomicOr(flag, 1);
             }
         }
-    } else if (lane == 0) {
-        // ---------------- MMA issuer ----------------
-        uint32_t n_q = 0, n_p = 0;
-        const uint64_t dq = make_desc(q_sm);
-        for (int qt = 0; qt < n_qtiles; ++qt) {
-            mbar_wait(bar_q, n_q & 1u);
-            ++n_q;
-            tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int nvalid = min(AH_KB, T - kb * AH_KB);
-                const int nb = (nvalid + 15) / 16 * 16;                              // UMMA N of the score block
-                const uint32_t ids = make_idesc_f16(128, nb);
-                const uint64_t dk = make_desc(k_sm + (uint32_t)kb * AH_KB * 128u);
-                // S = Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T: the hi / lo halves are 32-byte K-slices 0,1 / 2,3 of the same 128-byte rows
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const uint64_t hi = (uint64_t)(k * 2), lo = (uint64_t)((2 + k) * 2);
-                    mma_f16(tmem_base + AH_S_COL, dq + hi, dk + hi, ids, k != 0 ? 1u : 0u);
-                    mma_f16(tmem_base + AH_S_COL, dq + lo, dk + hi, ids, 1u);
-                    mma_f16(tmem_base + AH_S_COL, dq + hi, dk + lo, ids, 1u);
-                }
-                mma_commit(bar_s);
-                mbar_wait(bar_p, n_p & 1u);
-                ++n_p;
-                tc_fence_after();
-                const int ksteps = (nvalid + 15) / 16;
-                const uint32_t id64 = make_idesc_f16(128, 64), id32 = make_idesc_f16(128, 32);
-                for (int j = 0; j < ksteps; ++j) {
-                    const int key0 = kb * AH_KB + 16 * j;
-                    const uint64_t dv = make_desc(v_sm + (uint32_t)(key0 >> 6) * 8192u) + (uint64_t)(((key0 & 63) >> 4) * 2);
-                    mma_f16_ts(tmem_base + AH_O_COL, tmem_base + AH_S_COL + 8 * j, dv, id64, (kb | j) != 0 ? 1u : 0u);   // P_hi [V_hi | V_lo]
-                    mma_f16_ts(tmem_base + AH_O_COL, tmem_base + AH_S_COL + 64 + 8 * j, dv, id32, 1u);                   // P_lo V_hi
-                }
-                if (kb == nkb - 1) mma_commit(bar_o);
-            }
-        }
     }
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == AH_MMA_WARP) {
+    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, AH_TMEM_COLS);
     }

@@ -149,7 +149,7 @@ struct said_engine {
         float* d = nullptr;
         CKI(upload(img, &d));
         tcmap[key] = TcW{d, K, N, bn};
-        if (reg_h && K % hx::HBK == 0 && (bn == 192 || bn == 32)) {
+        if (reg_h && K % hx::HBK == 0) {
             std::vector<uint16_t> himg;
             const int e = hx::pack_weights_h(host_wt, K, N, ldw, bn, himg);
             uint8_t* hd = nullptr;
@@ -162,7 +162,7 @@ struct said_engine {
     }
     // One contraction on the fp16x3 path.  The K dimension is the concatenation of `segs`: columns [col0, col0 + ncols) of
     // the pair tensor `src` (C columns, `rows` rows), rows shifted by row_shift (Conv1d taps).  Weight = the image of `wkey`.
-    struct HSrc { const __half* base; int C; long long rows; };
+    struct HSrc { const __half* base; int C; long long rows; long long pitch_halfs = 0; /* 0: 2 * C */ };
     struct HSegSpec { HSrc src; int col0, ncols, row_shift; };
     template <class EP>
     int gemm_h(cudaStream_t st, int M, int N, std::initializer_list<HSegSpec> segs, const float* wkey, EP ep, int tag, int dbg = 0) {
@@ -181,7 +181,7 @@ struct said_engine {
                 if (bases[j] == sg.src.base) mi = j;
             if (mi < 0) {
                 if (nmaps >= 3) return fail("fp16x3 gemm: too many source tensors");
-                if (!hx::make_pair_map(&p.maps[nmaps], sg.src.base, sg.src.C, sg.src.rows))
+                if (!hx::make_pair_map(&p.maps[nmaps], sg.src.base, sg.src.C, sg.src.rows, sg.src.pitch_halfs))
                     return fail("cuTensorMapEncodeTiled failed (driver entry point unavailable or bad tensor geometry)");
                 bases[nmaps] = sg.src.base;
                 mi = nmaps++;
@@ -202,6 +202,7 @@ struct said_engine {
         cur_tag = tag;
         cudaError_t e = cudaErrorInvalidValue;
         if (w.bn == 192) e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, ep, pdl);
+        else if (w.bn == 128) e = hx::launch_gemm_h<128>(st, num_sms, p, w.img, ep, pdl);
         else if (w.bn == 32) e = hx::launch_gemm_h<32>(st, num_sms, p, w.img, ep, pdl);
         if (e != cudaSuccess) return fail(std::string("fp16x3 gemm launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
@@ -328,6 +329,7 @@ struct said_engine {
     DevBuf e_a, e_b, e_c, e_d, e_qkv, e_ff, e_xp, e_emb;
     // pair-format (fp16 hi/lo) operands of the fp16x3 path, sized in floats (a pair element takes 4 bytes like an fp32 one)
     DevBuf p_gn, p_raw, p_ln, p_ao, p_x2, p_ff;
+    DevBuf pe_a, pe_b, pe_x, pe_att, pe_ff;     // encoder, fp16x3 mode: conv ping-pong, layer input, attention output, FFN intermediate
     double* c0_partial = nullptr;
     double* gn_partial = nullptr;
     size_t gn_partial_cap = 0;
@@ -407,6 +409,7 @@ struct said_engine {
 
     // ------------------------------------------------------------------ programs
     int encode_audio(const float* wave, int B, int T_a, int T, float* emb_out, cudaStream_t st);
+    int encode_audio_h(const float* wave, int B, int T_a, int T, float* emb_out, cudaStream_t st);
     int prepare_context(const float* emb, int B, int T, int with_uncond, cudaStream_t st);
     int ensure_denoiser_ws(int Bp, int T);
     int forward(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T, const float* emb_table,
@@ -784,9 +787,10 @@ int said_engine::commit() {
     ctx_B = ctx_T = 0;
     reg_h = true;
     const int rc_d = commit_denoiser();
+    const int rc_e = rc_d == 0 ? commit_encoder() : 0;
     reg_h = false;
     CKI(rc_d);
-    CKI(commit_encoder());
+    CKI(rc_e);
     const int enc_out = proj_dim > 0 ? proj_dim : enc_hidden;
     if (enc_out != ctx_dim)
         return fail("audio feature width " + std::to_string(enc_out) + " != denoiser context dim " + std::to_string(ctx_dim));
@@ -839,6 +843,7 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
     } scope(precision, enc_precision);
     if (!ready) return fail("weights not committed");
     if (B <= 0 || T <= 0) return fail("encode_audio: empty batch");
+    if (enc_precision == 3 && (long long)B * T >= tc_min_rows) return encode_audio_h(wave, B, T_a, T, emb_out, st);
     int L[8];
     L[0] = (T_a - conv_k[0]) / conv_s[0] + 1;
     if (T_a < conv_k[0]) return fail("encode_audio: waveform shorter than the first conv kernel");
@@ -1039,6 +1044,240 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         LAUNCH_CHECK();
     }
     if (!last_direct) {   // audio_proj_layer (diffusion.py:228-229)
+        EpiStd ep = mk_epi(emb_out, proj_dim, proj_dim);
+        ep.bias = b_aproj;
+        CKI(gemm(st, M, proj_dim, H, mk_plain(e_d.p, H, M), w_aproj, proj_dim, ep));
+    }
+    return 0;
+}
+
+// =====================================================================================================
+// Audio encoder, fp16x3 mode: every dense contraction (conv1..6, feature projection, q/k/v, attention output, feed-forward)
+// is a TMA-fed tcgen05 kind::f16 GEMM over pair-format operands (gemm_h.cuh); the kernels in between write pairs.
+// A strided Conv1d(k, stride 2) over the channel-last pair tensor is k segments of one GEMM: tap t is a tensor map whose
+// row pitch is two frames and whose base is shifted by t frames.  conv0, the positional conv (grouped, K = 6144 per group)
+// and the attention core stay on their fp32 kernels.
+// =====================================================================================================
+int said_engine::encode_audio_h(const float* wave, int B, int T_a, int T, float* emb_out, cudaStream_t st) {
+    int L[8];
+    L[0] = (T_a - conv_k[0]) / conv_s[0] + 1;
+    if (T_a < conv_k[0]) return fail("encode_audio: waveform shorter than the first conv kernel");
+    for (int i = 1; i < n_conv; ++i) {
+        L[i] = (L[i - 1] - conv_k[i]) / conv_s[i] + 1;
+        if (L[i - 1] < conv_k[i] || L[i] < 1) return fail("encode_audio: waveform too short for the conv stack");
+        if (conv_s[i] != 2 || conv_k[i] > 3) return fail("audio encoder: conv layers other than (k <= 3, stride 2) are not supported");
+    }
+    const int H = enc_hidden, CD = enc_conv_dim;
+    const int Lf = L[n_conv - 1];
+    int S[8];
+    {
+        int s_last = 1;
+        for (int i = 0; i < n_conv; ++i) {
+            const int sh = n_conv - 1 - i;
+            s_last = std::max(s_last, (L[i] + (1 << sh) - 1) >> sh);
+        }
+        for (int i = 0; i < n_conv; ++i) S[i] = s_last << (n_conv - 1 - i);
+    }
+    if (!status_flag) {
+        CK(cudaMalloc((void**)&status_flag, sizeof(int)));
+        CK(cudaMemset(status_flag, 0, sizeof(int)));
+    }
+    CK(e_a.ensure((size_t)(B * S[0] + 4) * CD));
+    CK(e_b.ensure((size_t)(B * S[1] + 4) * CD));
+    CK(pe_a.ensure_zero((size_t)(B * S[0] + 4) * CD));
+    CK(pe_b.ensure_zero((size_t)(B * S[1] + 4) * CD));
+    // ---- conv0 + norm + GELU (fp32 kernels), then the pair format
+    if (enc_fe_layer_norm) {
+        const long long warps = (long long)B * L[0];
+        conv0_layernorm_gelu_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(wave, T_a, L[0], B, c0_w, c0_bias, c0_g, c0_b, 1e-5f,
+                                                                                          e_a.p, S[0]);
+        LAUNCH_CHECK();
+    } else {
+        const int nchunk = 32;
+        const int fpc = (L[0] + nchunk - 1) / nchunk;
+        const size_t need_partial = (size_t)B * nchunk * 2 * CD;
+        if (need_partial > c0_partial_cap) {
+            if (c0_partial) cudaFree(c0_partial);
+            c0_partial = nullptr;
+            c0_partial_cap = 0;
+            CK(cudaMalloc((void**)&c0_partial, need_partial * sizeof(double)));
+            c0_partial_cap = need_partial;
+        }
+        conv0_stats_kernel<<<dim3(nchunk, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, fpc, c0_partial);
+        LAUNCH_CHECK();
+        conv0_apply_kernel<<<dim3((L[0] + C0_TILE - 1) / C0_TILE, B), C0_CH, 0, st>>>(wave, T_a, L[0], c0_w, c0_partial, nchunk,
+                                                                                       c0_g, c0_b, 1e-5f, e_a.p, S[0]);
+        LAUNCH_CHECK();
+    }
+    auto to_pair = [&](const float* src, long long rows, int Cc, __half* dst) -> int {
+        const long long nq = rows * (Cc / 4);
+        f32_to_pair_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(src, rows, Cc, dst, status_flag);
+        LAUNCH_CHECK();
+        return 0;
+    };
+    __half* psrc = reinterpret_cast<__half*>(pe_a.p);
+    __half* pdst = reinterpret_cast<__half*>(pe_b.p);
+    CKI(to_pair(e_a.p, (long long)B * S[0], CD, psrc));
+    // ---- conv1..6 (stride 2, GELU): row m of layer i reads frames 2m + tap of layer i - 1
+    float* last_f32 = e_b.p;       // the last conv layer's output in fp32 (input of the interpolation)
+    for (int i = 1; i < n_conv; ++i) {
+        const int rows = B * S[i];
+        const bool last = i == n_conv - 1;
+        HSrc taps[3];
+        for (int t = 0; t < conv_k[i]; ++t) taps[t] = HSrc{psrc + (size_t)t * 2 * CD, CD, rows, 4LL * CD};
+        EpiStd ep = mk_epi(nullptr, CD, CD);
+        ep.flag = status_flag;
+        ep.pair_C = CD;
+        if (enc_fe_layer_norm) {   // conv + bias -> fp32, then LayerNorm(512) + GELU -> pair (fp32 for the last layer)
+            ep.out = e_b.p;
+            ep.bias = conv_bias_p[i];
+        } else {
+            ep.act = 1;
+            if (last) ep.out = last_f32;
+            else ep.out_pair = pdst;
+        }
+        if (conv_k[i] == 3) CKI(gemm_h(st, rows, CD, {{taps[0], 0, CD, 0}, {taps[1], 0, CD, 0}, {taps[2], 0, CD, 0}}, conv_w[i], ep, TAG_OTHER));
+        else CKI(gemm_h(st, rows, CD, {{taps[0], 0, CD, 0}, {taps[1], 0, CD, 0}}, conv_w[i], ep, TAG_OTHER));
+        if (enc_fe_layer_norm) {
+            layernorm_rows_kernel<8><<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(
+                e_b.p, nullptr, rows, CD, 1e-5f, conv_ln_g[i], conv_ln_b[i], last ? last_f32 : nullptr, 1, last ? nullptr : pdst, status_flag);
+            LAUNCH_CHECK();
+        }
+        std::swap(psrc, pdst);
+    }
+    const int M = B * T;
+    CK(e_c.ensure((size_t)M * std::max(CD, H)));
+    CK(e_d.ensure((size_t)M * H));
+    CK(e_qkv.ensure((size_t)M * 3 * H));
+    CK(e_xp.ensure((size_t)B * pos_g * (T + pos_k) * (H / pos_g)));
+    CK(pe_x.ensure_zero((size_t)M * std::max(CD, H)));
+    CK(pe_att.ensure_zero((size_t)M * H));
+    CK(pe_ff.ensure_zero((size_t)M * enc_ffn));
+    __half* px = reinterpret_cast<__half*>(pe_x.p);
+    __half* patt = reinterpret_cast<__half*>(pe_att.p);
+    __half* pffn = reinterpret_cast<__half*>(pe_ff.p);
+    // ---- interpolate to T frames + LayerNorm(512) -> pair
+    interp_layernorm_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(last_f32, B, Lf, S[n_conv - 1], T, CD, 1e-5f, fp_ln_g, fp_ln_b,
+                                                                      (float*)nullptr, px, status_flag);
+    LAUNCH_CHECK();
+    {   // projection 512 -> H  -> e_d (fp32)
+        EpiStd ep = mk_epi(e_d.p, H, H);
+        ep.bias = fp_b;
+        CKI(gemm_h(st, M, H, {{HSrc{px, CD, M}, 0, CD, 0}}, fp_w, ep, TAG_OTHER));
+    }
+    // ---- positional conv embedding: x + gelu(conv(x)) then LayerNorm (fp32 batched grouped GEMM, as in encode_audio)
+    {
+        const int cg = H / pos_g, Tpd = T + pos_k;
+        const long long tot = (long long)B * pos_g * Tpd * cg;
+        posconv_regroup_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(e_d.p, B, T, H, pos_g, pos_k, e_xp.p);
+        LAUNCH_CHECK();
+        ALoadPlain al = mk_plain(e_xp.p, cg, T);
+        al.zdiv = pos_g;
+        al.zstride = (long long)pos_g * Tpd * cg;
+        al.zstride2 = (long long)Tpd * cg;
+        EpiStd ep = mk_epi(e_c.p, H, cg);
+        ep.bias = pos_b;
+        ep.act = 1;
+        ep.res = e_d.p;
+        ep.ldr = H;
+        ep.zdiv = pos_g;
+        ep.zs0 = (long long)T * H;
+        ep.zs1 = cg;
+        ep.bias_zs = cg;
+        CKI(gemm(st, T, cg, pos_k * cg, al, pos_w, cg, ep, B * pos_g, pos_g, (long long)pos_k * cg * cg));
+    }
+    CK(cudaFuncSetAttribute(self_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attention_smem_bytes<64>()));
+    auto ln = [&](const float* src, const float* g, const float* b, float* dst, __half* dst_pair) -> int {
+        layernorm_rows_kernel<8><<<(M * 32 + 255) / 256, 256, 0, st>>>(src, nullptr, M, H, 1e-5f, g, b, dst, 0, dst_pair, status_flag);
+        LAUNCH_CHECK();
+        return 0;
+    };
+    auto attention = [&]() -> int {
+        self_attention_kernel<64><<<dim3((T + ATT_QTILE - 1) / ATT_QTILE, enc_heads, B), ATT_THREADS, attention_smem_bytes<64>(), st>>>(
+            e_qkv.p, 3 * H, 0, H, 2 * H, T, 0.125f, nullptr, H, T, patt, status_flag);
+        LAUNCH_CHECK();
+        return 0;
+    };
+    const HSrc sx{px, H, M}, satt{patt, H, M}, sff{pffn, enc_ffn, M};
+    if (enc_stable_ln) {
+        // pre-LN layers (TF modeling_wav2vec2.py:612-655, 730-803) over h = e_c: h += attn(LN1(h)); h += ffn(LN2(h)); final LayerNorm
+        float* h = e_c.p;
+        for (int l = 0; l < enc_layers; ++l) {
+            const EncLayerW& W = enc[l];
+            CKI(ln(h, W.ln1_g, W.ln1_b, nullptr, px));
+            {
+                EpiStd ep = mk_epi(e_qkv.p, 3 * H, 3 * H);
+                ep.bias = W.bqkv;
+                CKI(gemm_h(st, M, 3 * H, {{sx, 0, H, 0}}, W.wqkv, ep, TAG_OTHER));
+            }
+            CKI(attention());
+            {
+                EpiStd ep = mk_epi(h, H, H);
+                ep.bias = W.bo;
+                ep.res = h;
+                ep.ldr = H;
+                CKI(gemm_h(st, M, H, {{satt, 0, H, 0}}, W.wo, ep, TAG_OTHER));
+            }
+            CKI(ln(h, W.ln2_g, W.ln2_b, nullptr, px));
+            {
+                EpiStd ep = mk_epi(nullptr, enc_ffn, enc_ffn);
+                ep.bias = W.bff1;
+                ep.act = 1;
+                ep.out_pair = pffn;
+                ep.pair_C = enc_ffn;
+                ep.flag = status_flag;
+                CKI(gemm_h(st, M, enc_ffn, {{sx, 0, H, 0}}, W.wff1, ep, TAG_OTHER));
+            }
+            {
+                EpiStd ep = mk_epi(h, H, H);
+                ep.bias = W.bff2;
+                ep.res = h;
+                ep.ldr = H;
+                CKI(gemm_h(st, M, H, {{sff, 0, enc_ffn, 0}}, W.wff2, ep, TAG_OTHER));
+            }
+        }
+        float* dst_ln = proj_dim == 0 ? emb_out : e_d.p;
+        CKI(ln(h, enc_ln_g, enc_ln_b, dst_ln, nullptr));
+    } else {
+        // post-LN layers (TF :576-609): x lives in e_d (fp32) and px (pair)
+        CKI(ln(e_c.p, enc_ln_g, enc_ln_b, e_d.p, px));
+        for (int l = 0; l < enc_layers; ++l) {
+            const EncLayerW& W = enc[l];
+            {
+                EpiStd ep = mk_epi(e_qkv.p, 3 * H, 3 * H);
+                ep.bias = W.bqkv;
+                CKI(gemm_h(st, M, 3 * H, {{sx, 0, H, 0}}, W.wqkv, ep, TAG_OTHER));
+            }
+            CKI(attention());
+            {   // attention output projection + residual -> e_c
+                EpiStd ep = mk_epi(e_c.p, H, H);
+                ep.bias = W.bo;
+                ep.res = e_d.p;
+                ep.ldr = H;
+                CKI(gemm_h(st, M, H, {{satt, 0, H, 0}}, W.wo, ep, TAG_OTHER));
+            }
+            CKI(ln(e_c.p, W.ln1_g, W.ln1_b, e_d.p, px));
+            {
+                EpiStd ep = mk_epi(nullptr, enc_ffn, enc_ffn);
+                ep.bias = W.bff1;
+                ep.act = 1;
+                ep.out_pair = pffn;
+                ep.pair_C = enc_ffn;
+                ep.flag = status_flag;
+                CKI(gemm_h(st, M, enc_ffn, {{sx, 0, H, 0}}, W.wff1, ep, TAG_OTHER));
+            }
+            {
+                EpiStd ep = mk_epi(e_c.p, H, H);
+                ep.bias = W.bff2;
+                ep.res = e_d.p;
+                ep.ldr = H;
+                CKI(gemm_h(st, M, H, {{sff, 0, enc_ffn, 0}}, W.wff2, ep, TAG_OTHER));
+            }
+            const bool final_direct = l == enc_layers - 1 && proj_dim == 0;
+            CKI(ln(e_c.p, W.ln2_g, W.ln2_b, final_direct ? emb_out : e_d.p, final_direct ? nullptr : px));
+        }
+    }
+    if (proj_dim != 0) {   // audio_proj_layer (diffusion.py:228-229): fp32 GEMM of the generic path
         EpiStd ep = mk_epi(emb_out, proj_dim, proj_dim);
         ep.bias = b_aproj;
         CKI(gemm(st, M, proj_dim, H, mk_plain(e_d.p, H, M), w_aproj, proj_dim, ep));
@@ -1957,7 +2196,10 @@ int said_op_self_attention_h(said_engine* e, const float* qkv_dev, int B, int T,
     if (getenv("SAID_DEBUG")) {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hx::self_attention_h_kernel, hx::AH_THREADS, hx::attention_h_smem_bytes(T));
-        fprintf(stderr, "[said] self_attention_h_kernel: T=%d smem=%zu B, resident CTAs per SM = %d\n", T, hx::attention_h_smem_bytes(T), nb);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, hx::self_attention_h_kernel);
+        fprintf(stderr, "[said] self_attention_h_kernel: T=%d smem=%zu B, %d regs, resident CTAs per SM = %d\n", T, hx::attention_h_smem_bytes(T),
+                fa.numRegs, nb);
     }
     hx::self_attention_h_kernel<<<dim3(heads, B), hx::AH_THREADS, hx::attention_h_smem_bytes(T), st>>>(
         qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr);
@@ -2013,7 +2255,7 @@ int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int with_res
 int said_set_precision(said_engine* e, int mode, int tc_min_rows, int encoder_mode) {
     if (!e) return fail("null engine");
     if (mode < 0 || mode > 3) return fail("said_set_precision: mode must be 0 (fp32 FFMA), 1 (3xTF32 tcgen05), 2 (TF32 tcgen05) or 3 (fp16 hi/lo x3 tcgen05)");
-    if (encoder_mode < 0 || encoder_mode > 2) return fail("said_set_precision: encoder_mode must be 0, 1 or 2");
+    if (encoder_mode < 0 || encoder_mode > 3) return fail("said_set_precision: encoder_mode must be 0, 1, 2 or 3");
     e->precision = mode;
     e->enc_precision = encoder_mode;
     if (tc_min_rows > 0) e->tc_min_rows = tc_min_rows;

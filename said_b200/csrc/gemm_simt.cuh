@@ -302,6 +302,9 @@ struct EpiStd {
     int res_mod;             // > 0: the residual tensor has only res_mod rows, row m reads row m % res_mod (shared CFG prefix)
     int zdiv;                // batched: out/res += (z / zdiv) * zs0 + (z % zdiv) * zs1, bias += (z % zdiv) * bias_zs
     long long zs0, zs1, bias_zs;
+    __half* out_pair;        // non-null: the result is (also) written as a pair tensor of pair_C columns (operand of the next fp16x3 GEMM);
+    int pair_C;              //           `out` may then be null
+    int* flag;               // overflow flag of the pair format
     float acc_scale;         // tcgen05 fp16x3 path: the accumulator is multiplied by this first (inverse of the power-of-two weight scale)
     int out_period, out_valid;   // > 0: GEMM row m = b * out_period + t is written to output row b * out_valid + t, rows with
                                  // t >= out_valid are dropped (padded row space -> dense (B, T, C) output); only `out` is remapped
@@ -413,7 +416,11 @@ struct EpiStd {
             }
             a.x = r.x + a.x; a.y = r.y + a.y; a.z = r.z + a.z; a.w = r.w + a.w;
         }
-        st4(out + (long long)m * ldo + n, a);
+        if (out != nullptr) st4(out + (long long)m * ldo + n, a);
+        if (out_pair != nullptr) {
+            store_pair4(out_pair, m, pair_C, n, a);
+            if (amax4(0.f, a) > P16_LIMIT) atomicOr(flag, 1);
+        }
     }
     struct Pref { float4 r[4]; };
     SAID_DEVINL Pref prefetch16(int m, int n) const {

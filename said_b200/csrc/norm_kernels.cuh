@@ -3,6 +3,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "pair.cuh"
 
 namespace said {
 
@@ -262,7 +263,9 @@ ln192_rows_kernel(const float* __restrict__ x, int M, int T, const float* __rest
 template <int MAXV>   // float4 per lane, C <= 128*MAXV
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ r, int M, int C, float eps,
-                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int act = 0 /*1: GELU after*/) {
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int act = 0 /*1: GELU after*/,
+                      __half* __restrict__ y_pair = nullptr /*also (or only, y == null) as a pair tensor of C columns*/,
+                      int* __restrict__ flag = nullptr) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= M) return;
     const float* xr = x + (long long)warp * C;
@@ -302,7 +305,11 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ r, 
             o.z = (v[j].z - mean) * rstd * g.z + bb.z;
             o.w = (v[j].w - mean) * rstd * g.w + bb.w;
             if (act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
-            st4(y + (long long)warp * C + k, o);
+            if (y != nullptr) st4(y + (long long)warp * C + k, o);
+            if (y_pair != nullptr) {
+                store_pair4(y_pair, warp, C, k, o);
+                if (amax4(0.f, o) > P16_LIMIT) atomicOr(flag, 1);
+            }
         }
     }
 }
@@ -314,7 +321,8 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ r, 
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 interp_layernorm_kernel(const float* __restrict__ x, int B, int L, int Lstride, int T, int C, float eps,
-                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y) {
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                        __half* __restrict__ y_pair = nullptr, int* __restrict__ flag = nullptr) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * T) return;
     const int b = warp / T, j = warp - b * T;
@@ -359,7 +367,11 @@ interp_layernorm_kernel(const float* __restrict__ x, int B, int L, int Lstride, 
             o.y = (v[jj].y - mean) * rstd * g.y + bb.y;
             o.z = (v[jj].z - mean) * rstd * g.z + bb.z;
             o.w = (v[jj].w - mean) * rstd * g.w + bb.w;
-            st4(y + (long long)warp * C + k, o);
+            if (y != nullptr) st4(y + (long long)warp * C + k, o);
+            if (y_pair != nullptr) {
+                store_pair4(y_pair, warp, C, k, o);
+                if (amax4(0.f, o) > P16_LIMIT) atomicOr(flag, 1);
+            }
         }
     }
 }

@@ -217,3 +217,43 @@ def test_editing_fp16x3_and_mismatched_init_length(gpu_model, state_dict):
         e = maxdiff(res[sel], ref)
         print("editing, init 298 frames vs 300-frame audio window:", mode, e)
         assert e < 2e-3
+
+
+def test_audio_encoder_fp16x3(golden_dir, gpu_model):
+    """Wav2Vec2 encoder with every dense contraction on the fp16x3 tensor-core path (forced on for this 1 s clip) against the
+    reference's (transformers) output, and a batch of 8 clips against the fp32 kernels of the same engine."""
+    from said_b200.synth import synthetic_batch
+
+    gd = np.load(os.path.join(golden_dir, "audio_encoder_1s.npz"))
+    m = gpu_model()
+    saved = (m.encoder_precision, m.tc_min_rows)
+    try:
+        m.encoder_precision, m.tc_min_rows = "fp16x3", 1
+        emb = m.get_audio_embedding(torch.from_numpy(gd["wave"]).to(DEV), 60)
+        wave = synthetic_batch(8, 1.0).to(DEV)
+        got = m.get_audio_embedding(wave, 60)
+        m.encoder_precision = "fp32"
+        ref = m.get_audio_embedding(wave, 60)
+    finally:
+        m.encoder_precision, m.tc_min_rows = saved
+        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, m.encoder_precision)
+    e32, e64, eb = maxdiff(emb, gd["emb"]), maxdiff(emb, gd["emb64"]), maxdiff(got, ref)
+    print("fp16x3 encoder vs reference", e32, e64, "batch of 8 vs fp32 kernels", eb)
+    assert e32 < 1e-4 and e64 < 1e-4 and eb < 1e-4
+
+
+def test_large_family_encoder_fp16x3(golden_dir, large_family):
+    """wav2vec2-large family (LayerNorm feature extractor with conv bias, pre-LN layers) on the fp16x3 path."""
+    from said_b200.model.diffusion import SAID_UNet1D
+
+    cfg, sd = large_family
+    gd = np.load(os.path.join(golden_dir, "audio_encoder_large_family_1s.npz"))
+    m = SAID_UNet1D(audio_config=cfg)
+    m.load_state_dict(sd, strict=False)
+    m.to(DEV).eval()
+    m.encoder_precision, m.tc_min_rows = "fp16x3", 1
+    with torch.no_grad():
+        emb = m.get_audio_embedding(torch.from_numpy(gd["wave"]).to(DEV), 60)
+    e32, e64 = maxdiff(emb, gd["emb"]), maxdiff(emb, gd["emb64"])
+    print("fp16x3 large-family encoder", e32, e64)
+    assert e32 < 2e-4 and e64 < 2e-4
