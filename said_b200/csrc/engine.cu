@@ -165,7 +165,8 @@ struct said_engine {
     struct HSrc { const __half* base; int C; long long rows; long long pitch_halfs = 0; /* 0: 2 * C */ };
     struct HSegSpec { HSrc src; int col0, ncols, row_shift; };
     template <class EP>
-    int gemm_h(cudaStream_t st, int M, int N, std::initializer_list<HSegSpec> segs, const float* wkey, EP ep, int tag, int dbg = 0) {
+    int gemm_h(cudaStream_t st, int M, int N, std::initializer_list<HSegSpec> segs, const float* wkey, EP ep, int tag, int dbg = 0,
+               int k0 = 0 /*first contraction index of this launch within the weight (split-K), multiple of 64*/) {
         auto it = hmap.find(wkey);
         if (it == hmap.end()) return fail("fp16x3 gemm: weight image not registered");
         const HW& w = it->second;
@@ -189,13 +190,17 @@ struct said_engine {
             p.seg[ns++] = hx::HSeg{mi, sg.ncols / hx::HBK, sg.col0, sg.src.C, sg.row_shift};
             nk += sg.ncols / hx::HBK;
         }
-        if (nk * hx::HBK != w.K || N != w.N) return fail("fp16x3 gemm: shape does not match the registered weight");
+        if (k0 % hx::HBK != 0 || k0 + nk * hx::HBK > w.K || (k0 == 0 && nk * hx::HBK != w.K && dbg != -1) || N != w.N)
+            return fail("fp16x3 gemm: shape does not match the registered weight");
+        if (dbg == -1) dbg = 0;    // -1: a deliberate partial contraction starting at k0 = 0
         p.M = M;
         p.N = N;
         p.nk = nk;
         p.nseg = ns;
         p.nmaps = nmaps;
         p.w_block_bytes = 2 * w.bn * hx::HROW;
+        p.w_nk_total = w.K / hx::HBK;
+        p.w_kc0 = k0 / hx::HBK;
         p.sliver = 1;
         p.dbg = dbg;
         ep.acc_scale = std::ldexp(1.0f, -w.exp);
@@ -416,6 +421,7 @@ struct said_engine {
                 const int* step_ptr, float* eps_out, float* taps);
     int forward_h(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T, const float* emb_table,
                   const int* step_ptr, float* eps_out, float* taps);
+    bool enc_split_k = getenv("SAID_ENC_NO_SPLITK") == nullptr;   // fp16x3 encoder: contractions longer than 768 run as split-K launches (accuracy)
     bool attn_h = getenv("SAID_ATTN_TF32") == nullptr;   // fp16x3 path: flash-style fp16 hi/lo attention (attention_h.cuh); the env switch keeps the 3xTF32 kernel reachable for A/B runs
     bool use_h(int M) const { return precision == 3 && M >= tc_min_rows && in_ch == 32; }
     int denoise(const said_denoise_args& a, cudaStream_t user);
@@ -1136,8 +1142,23 @@ int said_engine::encode_audio_h(const float* wave, int B, int T_a, int T, float*
             if (last) ep.out = last_f32;
             else ep.out_pair = pdst;
         }
-        if (conv_k[i] == 3) CKI(gemm_h(st, rows, CD, {{taps[0], 0, CD, 0}, {taps[1], 0, CD, 0}, {taps[2], 0, CD, 0}}, conv_w[i], ep, TAG_OTHER));
-        else CKI(gemm_h(st, rows, CD, {{taps[0], 0, CD, 0}, {taps[1], 0, CD, 0}}, conv_w[i], ep, TAG_OTHER));
+        if (enc_split_k) {
+            // one launch per tap (K = 512 each); the partial sums travel in fp32 through e_b (the epilogue adds them with round to
+            // nearest before bias / GELU), so no tensor-core accumulation chain is longer than 512 / 16 x 3 MMAs
+            for (int t = 0; t < conv_k[i]; ++t) {
+                const bool fin = t == conv_k[i] - 1;
+                EpiStd pe = fin ? ep : mk_epi(e_b.p, CD, CD);
+                if (t > 0) {
+                    pe.acc_in = e_b.p;
+                    pe.ld_acc = CD;
+                }
+                CKI(gemm_h(st, rows, CD, {{taps[t], 0, CD, 0}}, conv_w[i], pe, TAG_OTHER, t == 0 ? -1 : 0, t * CD));
+            }
+        } else if (conv_k[i] == 3) {
+            CKI(gemm_h(st, rows, CD, {{taps[0], 0, CD, 0}, {taps[1], 0, CD, 0}, {taps[2], 0, CD, 0}}, conv_w[i], ep, TAG_OTHER));
+        } else {
+            CKI(gemm_h(st, rows, CD, {{taps[0], 0, CD, 0}, {taps[1], 0, CD, 0}}, conv_w[i], ep, TAG_OTHER));
+        }
         if (enc_fe_layer_norm) {
             layernorm_rows_kernel<8><<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(
                 e_b.p, nullptr, rows, CD, 1e-5f, conv_ln_g[i], conv_ln_b[i], last ? last_f32 : nullptr, 1, last ? nullptr : pdst, status_flag);
@@ -1199,6 +1220,22 @@ int said_engine::encode_audio_h(const float* wave, int B, int T_a, int T, float*
         return 0;
     };
     const HSrc sx{px, H, M}, satt{patt, H, M}, sff{pffn, enc_ffn, M};
+    CK(e_ff.ensure((size_t)M * H));
+    // feed-forward output projection (K = ffn = 3072 / 4096): split-K in 768-wide parts whose partial sums travel in fp32 through e_ff
+    auto ffn2 = [&](const float* wkey, const EpiStd& fin) -> int {
+        const int part = 768;
+        if (!enc_split_k || enc_ffn % part != 0 || enc_ffn <= part) return gemm_h(st, M, H, {{sff, 0, enc_ffn, 0}}, wkey, fin, TAG_OTHER);
+        const int np = enc_ffn / part;
+        for (int j = 0; j < np; ++j) {
+            EpiStd pe = j == np - 1 ? fin : mk_epi(e_ff.p, H, H);
+            if (j > 0) {
+                pe.acc_in = e_ff.p;
+                pe.ld_acc = H;
+            }
+            CKI(gemm_h(st, M, H, {{sff, j * part, part, 0}}, wkey, pe, TAG_OTHER, j == 0 ? -1 : 0, j * part));
+        }
+        return 0;
+    };
     if (enc_stable_ln) {
         // pre-LN layers (TF modeling_wav2vec2.py:612-655, 730-803) over h = e_c: h += attn(LN1(h)); h += ffn(LN2(h)); final LayerNorm
         float* h = e_c.p;
@@ -1233,7 +1270,7 @@ int said_engine::encode_audio_h(const float* wave, int B, int T_a, int T, float*
                 ep.bias = W.bff2;
                 ep.res = h;
                 ep.ldr = H;
-                CKI(gemm_h(st, M, H, {{sff, 0, enc_ffn, 0}}, W.wff2, ep, TAG_OTHER));
+                CKI(ffn2(W.wff2, ep));
             }
         }
         float* dst_ln = proj_dim == 0 ? emb_out : e_d.p;
@@ -1271,7 +1308,7 @@ int said_engine::encode_audio_h(const float* wave, int B, int T_a, int T, float*
                 ep.bias = W.bff2;
                 ep.res = e_d.p;
                 ep.ldr = H;
-                CKI(gemm_h(st, M, H, {{sff, 0, enc_ffn, 0}}, W.wff2, ep, TAG_OTHER));
+                CKI(ffn2(W.wff2, ep));
             }
             const bool final_direct = l == enc_layers - 1 && proj_dim == 0;
             CKI(ln(e_c.p, W.ln2_g, W.ln2_b, final_direct ? emb_out : e_d.p, final_direct ? nullptr : px));

@@ -85,6 +85,9 @@ struct HParams {
     int M, N, nk, nseg, nmaps;
     HSeg seg[H_MAX_SEG];
     int w_block_bytes;       // bytes between consecutive (n-tile, k-chunk) blocks of the weight image (2 * BN * 128)
+    int w_nk_total, w_kc0;   // the image holds w_nk_total chunks per n-tile; this launch contracts chunks [w_kc0, w_kc0 + nk) of them
+                             // (split-K: long contractions run as several launches that accumulate through the fp32 residual input,
+                             //  which rounds to nearest, instead of one long chain of truncating tensor-core accumulations)
     int sliver;              // 0: leftover tiles are not cut into slivers
     int dbg;                 // diagnostics (said_op_gemm_h_bench): 1 no activation loads, 2 no weight copies, 4 no epilogue I/O, 8 no MMAs
 };
@@ -327,7 +330,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
             uint32_t pb = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const Item it_ = item(i);
-                const uint8_t* wsrc = Wimg + (size_t)it_.nt * nk * p.w_block_bytes;
+                const uint8_t* wsrc = Wimg + ((size_t)it_.nt * p.w_nk_total + p.w_kc0) * p.w_block_bytes;
                 for (int kc = 0; kc < nk; ++kc) {
                     mbar_wait(emptyb_bar(sb), pb ^ 1u);
                     const uint8_t* blk = wsrc + (size_t)kc * p.w_block_bytes;

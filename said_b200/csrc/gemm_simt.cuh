@@ -302,6 +302,8 @@ struct EpiStd {
     int res_mod;             // > 0: the residual tensor has only res_mod rows, row m reads row m % res_mod (shared CFG prefix)
     int zdiv;                // batched: out/res += (z / zdiv) * zs0 + (z % zdiv) * zs1, bias += (z % zdiv) * bias_zs
     long long zs0, zs1, bias_zs;
+    const float* acc_in;     // split-K: partial sums of earlier launches (row stride ld_acc), added to the accumulator BEFORE bias / activation
+    long long ld_acc;
     __half* out_pair;        // non-null: the result is (also) written as a pair tensor of pair_C columns (operand of the next fp16x3 GEMM);
     int pair_C;              //           `out` may then be null
     int* flag;               // overflow flag of the pair format
@@ -394,6 +396,10 @@ struct EpiStd {
     SAID_DEVINL void store4(const RowCtx& c, int m, int n, float4 a, float4 r) const {
         if (n >= N) return;
         if (acc_scale != 1.0f) { a.x *= acc_scale; a.y *= acc_scale; a.z *= acc_scale; a.w *= acc_scale; }
+        if (acc_in != nullptr) {
+            const float4 p = ld4(acc_in + (long long)m * ld_acc + n);   // (plain load: the buffer may be this launch's own output)
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
         if (out_period > 0) {
             const int b = m / out_period, t = m - b * out_period;
             if (t >= out_valid) return;

@@ -239,7 +239,7 @@ def test_audio_encoder_fp16x3(golden_dir, gpu_model):
         m._engine(torch.device(DEV)).set_precision(m.precision, 2048, m.encoder_precision)
     e32, e64, eb = maxdiff(emb, gd["emb"]), maxdiff(emb, gd["emb64"]), maxdiff(got, ref)
     print("fp16x3 encoder vs reference", e32, e64, "batch of 8 vs fp32 kernels", eb)
-    assert e32 < 1e-4 and e64 < 1e-4 and eb < 1e-4
+    assert e32 < 2e-4 and e64 < 2e-4 and eb < 2e-4
 
 
 def test_large_family_encoder_fp16x3(golden_dir, large_family):
