@@ -136,6 +136,16 @@ SAID_API int said_op_self_attention_tc(said_engine* e, const float* qkv_dev, int
  * probabilities kept in tensor memory, head_dim 32, T <= 512. */
 SAID_API int said_op_self_attention_h(said_engine* e, const float* qkv_dev, int B, int T, int heads, float* out_dev, void* stream);
 
+/* Distribution-level evaluation on the device (reference said/model/vae.py:26-89, script/test_evaluate.py:53-106,
+ * said/metric/frechet_distance.py:17-64): the BCVAE encoder (eval mode) over sliding 120-frame windows of coefficient sequences,
+ * and the Frechet distance between two sets of 64-d latents.  Weights: said_set_tensor with the reference's BCVAE state-dict keys
+ * prefixed "bcvae." ("bcvae.encoder.conv_layers.0.weight", ..., running_mean / running_var included), then said_eval_commit_bcvae.
+ *   said_eval_bcvae_latents: coeffs_dev (B,T,32) -> latents_out_dev (B * nw, 64), nw = (T - 120) / step + 1, window-major per clip.
+ *   said_eval_frechet: out4_host = {distance, |mu1 - mu2|^2, tr S1 + tr S2, tr (S1 S2)^(1/2)}; synchronises. */
+SAID_API int said_eval_commit_bcvae(said_engine* e);
+SAID_API int said_eval_bcvae_latents(said_engine* e, const float* coeffs_dev, int B, int T, int step, float* latents_out_dev, void* stream);
+SAID_API int said_eval_frechet(said_engine* e, const float* lat1_dev, int n1, const float* lat2_dev, int n2, double* out4_host, void* stream);
+
 /* Number of kernels this engine has launched (graph replays counted node by node). */
 SAID_API long long said_launch_count(const said_engine* e);
 /* Number of times said_denoise had to capture + instantiate its per-step CUDA graph (the instantiated graph is cached and

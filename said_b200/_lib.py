@@ -31,6 +31,9 @@ EXPORTED_SYMBOLS = (
     "said_denoise",
     "said_denoiser_forward",
     "said_check_status",
+    "said_eval_commit_bcvae",
+    "said_eval_bcvae_latents",
+    "said_eval_frechet",
     "said_op_gemm_h",
     "said_op_gemm_h_bench",
     "said_op_ddim_step",
@@ -110,6 +113,9 @@ def load_library() -> ctypes.CDLL:
     lib.said_denoise.argtypes = [vp, ctypes.POINTER(DenoiseArgs), vp]
     lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, vp, vp]
     lib.said_check_status.argtypes = [vp, vp, ctypes.POINTER(ci)]
+    lib.said_eval_commit_bcvae.argtypes = [vp]
+    lib.said_eval_bcvae_latents.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.said_eval_frechet.argtypes = [vp, vp, ci, vp, ci, ctypes.POINTER(ctypes.c_double), vp]
     lib.said_op_gemm_h.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, vp, vp]
     lib.said_op_gemm_h_bench.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(cf)]
     lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, ci, vp]
@@ -309,6 +315,35 @@ class Engine:
                                                       out.data_ptr(), _ptr(tap_buf), self._stream()))
         self.check_status()
         return (out, tap_buf) if taps else out
+
+    # ------------------------------------------------------------------ evaluation
+    def load_bcvae(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """Encoder half of the reference's ``BCVAE`` state dict (``said/model/vae.py``; e.g. ``torch.load("model/vae.pth")``)."""
+        for k, v in state_dict.items():
+            if k.startswith("encoder.") and "num_batches_tracked" not in k and "fc_logvar" not in k:
+                self.set_tensor("bcvae." + k, v)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_eval_commit_bcvae(self._h))
+
+    def bcvae_latents(self, coeffs: torch.Tensor, step: int) -> torch.Tensor:
+        """(B, T, 32) coefficient sequences -> (B * nw, 64) BCVAE latent means over windows of 120 frames every `step` frames."""
+        coeffs = _check_dev(coeffs, self.device, "coefficients")
+        B, T, C = coeffs.shape
+        if C != 32 or T < 120:
+            raise ValueError("bcvae_latents: coefficients must be (B, T >= 120, 32)")
+        nw = (T - 120) // int(step) + 1
+        out = torch.empty((B * nw, 64), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_eval_bcvae_latents(self._h, coeffs.data_ptr(), B, T, int(step), out.data_ptr(), self._stream()))
+        return out
+
+    def frechet(self, lat1: torch.Tensor, lat2: torch.Tensor) -> Dict[str, float]:
+        lat1 = _check_dev(lat1, self.device, "latents 1")
+        lat2 = _check_dev(lat2, self.device, "latents 2")
+        out = (ctypes.c_double * 4)()
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_eval_frechet(self._h, lat1.data_ptr(), lat1.shape[0], lat2.data_ptr(), lat2.shape[0], out, self._stream()))
+        return {"frechet_distance": out[0], "mean_term": out[1], "trace_term": out[2], "sqrt_term": out[3]}
 
     def check_status(self) -> None:
         """Synchronise and raise if the device-side status word is set (fp16x3 path: an activation left fp16's range)."""

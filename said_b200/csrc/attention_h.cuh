@@ -80,8 +80,7 @@ SAID_DEVINL void sts16(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// 112 registers: two CTAs of 8 warps must fit the 64 K register file with room to spare (at exactly 128 the second CTA is not admitted)
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(AH_THREADS, 2)
 self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int T, float scale,
                         float* __restrict__ out, int ldo, int Tstr /*rows per sample in qkv / out*/,
                         __half* __restrict__ out_pair /*non-null: write the pair tensor (ldo columns) instead of fp32*/,
@@ -111,7 +110,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
         fence_mbar_init();
     }
     __syncwarp();
-    if (warp == 0) tmem_alloc(tmem_slot, AH_TMEM_COLS);
+    if (warp == 0) tc::tmem_alloc_imm<AH_TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -345,7 +344,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, AH_TMEM_COLS);
+        tc::tmem_dealloc_imm<AH_TMEM_COLS>(tmem_base);
     }
 }
 

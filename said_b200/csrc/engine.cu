@@ -25,6 +25,7 @@
 #include "attention_tc.cuh"
 #include "diffusion_kernels.cuh"
 #include "encoder_kernels.cuh"
+#include "eval_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_h.cuh"
 #include "gemm_tc.cuh"
@@ -366,6 +367,7 @@ struct said_engine {
         cudaDeviceSynchronize();
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (float* p : arena) cudaFree(p);
+        for (float* p : bcv_arena) cudaFree(p);
         if (c0_partial) cudaFree(c0_partial);
         if (gn_partial) cudaFree(gn_partial);
         if (step_ctr) cudaFree(step_ctr);
@@ -411,6 +413,11 @@ struct said_engine {
     int commit();
     int commit_denoiser();
     int commit_encoder();
+    // ---- evaluation embedder (BCVAE encoder, said/model/vae.py) : separate weight set, separate commit
+    BcvaeWeights bcv{};
+    bool bcv_ready = false;
+    std::vector<float*> bcv_arena;
+    int commit_bcvae();
 
     // ------------------------------------------------------------------ programs
     int encode_audio(const float* wave, int B, int T_a, int T, float* emb_out, cudaStream_t st);
@@ -778,6 +785,54 @@ int said_engine::commit_encoder() {
         CKI(upload_raw(p + "final_layer_norm.weight", {H}, &L.ln2_g));
         CKI(upload_raw(p + "final_layer_norm.bias", {H}, &L.ln2_b));
     }
+    return 0;
+}
+
+int said_engine::commit_bcvae() {
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceSynchronize());
+    for (float* p : bcv_arena) cudaFree(p);
+    bcv_arena.clear();
+    bcv_ready = false;
+    const std::string P = "bcvae.encoder.";
+    auto up = [&](const std::vector<float>& h, const float** d) -> int {
+        float* p = nullptr;
+        CK(cudaMalloc((void**)&p, std::max<size_t>(h.size(), 4) * sizeof(float)));
+        bcv_arena.push_back(p);
+        CK(cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        *d = p;
+        return 0;
+    };
+    auto raw_t = [&](const std::string& name, std::initializer_list<int64_t> shape, const float** d) -> int {
+        const HostTensor* t;
+        CKI(need(P + name, shape, &t));
+        return up(t->data, d);
+    };
+    // BatchNorm1d in eval mode -> per-channel scale / shift (vae.py:43-64; eps 1e-5)
+    auto bn = [&](const std::string& name, int64_t c, const float** sc, const float** sh) -> int {
+        const HostTensor *g, *b, *rm, *rv;
+        CKI(need(P + name + ".weight", {c}, &g));
+        CKI(need(P + name + ".bias", {c}, &b));
+        CKI(need(P + name + ".running_mean", {c}, &rm));
+        CKI(need(P + name + ".running_var", {c}, &rv));
+        std::vector<float> s(c), h(c);
+        for (int64_t i = 0; i < c; ++i) {
+            const double k = (double)g->data[i] / std::sqrt((double)rv->data[i] + 1e-5);
+            s[i] = (float)k;
+            h[i] = (float)((double)b->data[i] - (double)rm->data[i] * k);
+        }
+        CKI(up(s, sc));
+        return up(h, sh);
+    };
+    CKI(raw_t("conv_layers.0.weight", {32, BCV_IN, 3}, &bcv.c1w)); CKI(raw_t("conv_layers.0.bias", {32}, &bcv.c1b)); CKI(bn("conv_layers.1", 32, &bcv.bn1s, &bcv.bn1h));
+    CKI(raw_t("conv_layers.3.weight", {64, 32, 3}, &bcv.c2w));     CKI(raw_t("conv_layers.3.bias", {64}, &bcv.c2b)); CKI(bn("conv_layers.4", 64, &bcv.bn2s, &bcv.bn2h));
+    CKI(raw_t("conv_layers.6.weight", {64, 64, 4}, &bcv.c3w));     CKI(raw_t("conv_layers.6.bias", {64}, &bcv.c3b)); CKI(bn("conv_layers.7", 64, &bcv.bn3s, &bcv.bn3h));
+    CKI(raw_t("conv_layers.9.weight", {32, 64, 3}, &bcv.c4w));     CKI(raw_t("conv_layers.9.bias", {32}, &bcv.c4b));
+    CKI(raw_t("fc_layers.0.weight", {256, BCV_FLAT}, &bcv.f1w));   CKI(raw_t("fc_layers.0.bias", {256}, &bcv.f1b)); CKI(bn("fc_layers.1", 256, &bcv.bn4s, &bcv.bn4h));
+    CKI(raw_t("fc_layers.3.weight", {128, 256}, &bcv.f2w));        CKI(raw_t("fc_layers.3.bias", {128}, &bcv.f2b)); CKI(bn("fc_layers.4", 128, &bcv.bn5s, &bcv.bn5h));
+    CKI(raw_t("fc_layers.6.weight", {BCV_Z, 128}, &bcv.f3w));      CKI(raw_t("fc_layers.6.bias", {BCV_Z}, &bcv.f3b));
+    CKI(raw_t("fc_mu.weight", {BCV_Z, BCV_Z}, &bcv.muw));          CKI(raw_t("fc_mu.bias", {BCV_Z}, &bcv.mub));
+    bcv_ready = true;
     return 0;
 }
 
@@ -2096,6 +2151,42 @@ int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int N, int wi
     if (rc != 0) return rc;
     CK(se);
     *ms_out = ms / iters;
+    return 0;
+}
+
+int said_eval_commit_bcvae(said_engine* e) {
+    if (!e) return fail("null engine");
+    return e->commit_bcvae();
+}
+
+int said_eval_bcvae_latents(said_engine* e, const float* coeffs_dev, int B, int T, int step, float* latents_out_dev, void* stream) {
+    if (!e) return fail("null engine");
+    if (!e->bcv_ready) return fail("BCVAE weights not committed (said_set_tensor \"bcvae.encoder.*\" + said_eval_commit_bcvae)");
+    if (B <= 0 || step <= 0 || T < BCV_SEQ) return fail("said_eval_bcvae_latents: need B > 0, step > 0 and at least 120 frames");
+    CK(cudaSetDevice(e->device));
+    const int nw = (T - BCV_SEQ) / step + 1;
+    CK(cudaFuncSetAttribute(bcvae_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bcvae_smem_bytes()));
+    bcvae_encode_kernel<<<B * nw, 256, bcvae_smem_bytes(), (cudaStream_t)stream>>>(coeffs_dev, T, nw, step, e->bcv, latents_out_dev);
+    ++e->launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int said_eval_frechet(said_engine* e, const float* lat1_dev, int n1, const float* lat2_dev, int n2, double* out4_host, void* stream) {
+    if (!e || !out4_host) return fail("said_eval_frechet: bad arguments");
+    if (n1 < 2 || n2 < 2) return fail("said_eval_frechet: at least two latents per set");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, 4 * sizeof(double)));
+    CK(cudaFuncSetAttribute(frechet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frechet_smem_bytes()));
+    frechet_kernel<<<1, 256, frechet_smem_bytes(), st>>>(lat1_dev, n1, lat2_dev, n2, d);
+    ++e->launches;
+    cudaError_t le = cudaGetLastError();
+    if (le == cudaSuccess) le = cudaMemcpyAsync(out4_host, d, 4 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (le == cudaSuccess) le = cudaStreamSynchronize(st);
+    cudaFree(d);
+    CK(le);
     return 0;
 }
 

@@ -97,6 +97,17 @@ SAID_DEVINL void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+// Column count as an IMMEDIATE: with a register operand the tool chain cannot know how much tensor memory a CTA takes and admits
+// one CTA per SM (measured: occupancy 1 for a 256-column kernel); with an immediate two 256-column CTAs can share an SM.
+template <uint32_t NCOLS>
+SAID_DEVINL void tmem_alloc_imm(uint32_t dst_smem) {   // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS>
+SAID_DEVINL void tmem_dealloc_imm(uint32_t taddr) {    // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
 SAID_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {    // whole warp
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }

@@ -176,7 +176,9 @@ class SAID(ABC, nn.Module):
         # "fp16x3" (tcgen05 over fp16 hi/lo operand pairs loaded by TMA: same accuracy class at twice the tensor-core rate),
         # "tf32" (tcgen05, single pass) or "fp32" (FFMA); GEMMs below tc_min_rows rows stay on the FFMA kernel
         self.precision = "fp16x3"
-        self.encoder_precision = "fp32"   # the audio encoder runs once per clip: IEEE fp32 unless asked otherwise
+        # the audio encoder's dense contractions: "fp16x3" (tensor cores, split-K for the long ones: 6e-5 from the reference, 4x faster)
+        # at batch scale, the IEEE fp32 kernels below tc_min_rows frames (single short clips) or when set to "fp32"
+        self.encoder_precision = "fp16x3"
         self.tc_min_rows = 0
 
     # ------------------------------------------------------------------ state dict compatibility

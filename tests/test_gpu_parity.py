@@ -180,13 +180,15 @@ def test_audio_encoder_tensor_core_mode(golden_dir, gpu_model):
 
     m = gpu_model()
     wave = synthetic_batch(8, 1.0).to(DEV)
+    default = m.encoder_precision
+    m.encoder_precision = "fp32"
     ref = m.get_audio_embedding(wave, 60)
     m.encoder_precision, m.tc_min_rows = "tf32x3", 1
     try:
         got = m.get_audio_embedding(wave, 60)
     finally:
-        m.encoder_precision, m.tc_min_rows = "fp32", 0
-        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, "fp32")
+        m.encoder_precision, m.tc_min_rows = default, 0
+        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, default)
     e = maxdiff(got, ref)
     print("encoder tf32x3 vs fp32", e)
     assert 0 < e < 1e-3
@@ -207,7 +209,7 @@ def test_chain_1000_steps_tensor_core_mode(golden_dir, gpu_model, pt):
         out = run(m, wave, gd["noise"], steps=1000)
     finally:
         m.tc_min_rows, m.precision = 0, default
-        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, "fp32")
+        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, m.encoder_precision)
     e32, e64 = maxdiff(out.result, gd["result"]), maxdiff(out.result, gd["result64"])
     print("tensor-core chain", pt, e32, e64)
     assert e32 < 1e-3 and e64 < 1e-3
