@@ -492,6 +492,41 @@ def main():
                 "workload": "BASELINE configs[0]: 1 x 1 s clip, 10 DDIM steps, CFG 2.0, incl. audio encoder, host waveform in / host result out",
                 "ms_per_call": ms0 / 20, "clips_per_s": 1000.0 / (ms0 / 20),
                 "cpu_oracle_ms_per_call": cpu0 * 1000.0, "cpu_cores": os.cpu_count()}
+            # ---- the caller pattern of script/test_inference.py:148-202 for one utterance: the clip repeated over the batch, 72
+            #      generations in chunks of 64, every result cut to window_len frames and written to its own CSV
+            import tempfile
+
+            from said_b200.util.audio import fit_audio_unet
+            from said_b200.util.blendshape import DEFAULT_BLENDSHAPE_CLASSES, save_blendshape_coeffs, save_blendshape_coeffs_batch
+
+            raw = torch.from_numpy(synthetic_waveform(0, SECONDS))[: int(SECONDS * SR) - 123]      # not a multiple of the 800-sample hop
+            with torch.no_grad(), tempfile.TemporaryDirectory() as td:
+                def utterance(writer):
+                    t0 = time.perf_counter()
+                    fit = fit_audio_unet(raw.to(dev), SR, FPS, 1)
+                    wp = model.process_audio_device(fit.waveform)
+                    wb = wp.repeat(64, 1)
+                    torch.manual_seed(0)
+                    chunks = []
+                    for cs in (64, 8):
+                        o = model.inference(waveform_processed=wb[:cs], num_inference_steps=NUM_STEPS, guidance_scale=GUIDANCE)
+                        chunks.append(o.result[:, : fit.window_size].cpu().numpy())
+                    t1 = time.perf_counter()
+                    res = np.concatenate(chunks, 0)
+                    paths = [os.path.join(td, f"u-{i}.csv") for i in range(res.shape[0])]
+                    if writer == "batched":
+                        save_blendshape_coeffs_batch(res, DEFAULT_BLENDSHAPE_CLASSES, paths)
+                    else:
+                        for i, pth in enumerate(paths):
+                            save_blendshape_coeffs(res[i], DEFAULT_BLENDSHAPE_CLASSES, pth)
+                    return t1 - t0, time.perf_counter() - t1
+                utterance("batched")
+                g_b, h_b = utterance("batched")
+                g_p, h_p = utterance("pandas")
+            line["caller_test_inference"] = {
+                "workload": "script/test_inference.py:148-202 for one 5 s utterance: clip repeated x64 (encoded once), 72 generations in chunks "
+                            "of 64 + 8, 1000 steps, results cut to window_len and written as 72 CSV files",
+                "gpu_s": g_b, "csv_s_batched_writer": h_b, "csv_s_pandas_per_file": h_p, "generations_per_s": 72 / (g_b + h_b)}
             # ---- the reference's algorithm in PyTorch eager ON THIS B200 (oracle with device tensors): SURVEY 8(d) comparator
             try:
                 sdg = {k: v.to(dev) for k, v in sd.items()}

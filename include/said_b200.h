@@ -64,6 +64,13 @@ SAID_API int said_encode_audio(said_engine* e, const float* wave_dev, int B, int
  * on the device.  wave_dev (B, T_a) -> out_dev (B, T_a); in place allowed.   */
 SAID_API int said_normalize_audio(said_engine* e, const float* wave_dev, int B, int T_a, float* out_dev, void* stream);
 
+/* Device-side tail of load_audio (reference said/util/audio.py:35-38): torchaudio.functional.resample (polyphase windowed-sinc FIR)
+ * per channel followed by the mean over channels.  wave_dev (channels, n_in); the rates are given reduced by their gcd (orig, nw);
+ * bank_dev (nw, 2 * width + orig) is the filter bank, built by the host with torchaudio's published formula; out_dev (n_out),
+ * n_out = ceil(nw * n_in / orig).   */
+SAID_API int said_resample_mono(said_engine* e, const float* wave_dev, int channels, int n_in, int orig, int nw, int width,
+                                const float* bank_dev, float* out_dev, int n_out, void* stream);
+
 /* Hoist of everything the step loop needs from the audio features: cross-attention keys/values of all
  * four transformer blocks (reference said/model/ldm/attention.py:90-91 evaluates them on every step)
  * and, when with_uncond != 0, the constant value vector of the null-condition branch

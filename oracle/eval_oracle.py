@@ -99,7 +99,7 @@ def frechet_distance(lat1: np.ndarray, lat2: np.ndarray) -> float:
     mu1, mu2 = np.mean(lat1, axis=0), np.mean(lat2, axis=0)
     s1, s2 = np.cov(lat1, rowvar=False), np.cov(lat2, rowvar=False)
     diff = mu1 - mu2
-    covmean, _ = linalg.sqrtm(s1.dot(s2), disp=False)
+    covmean = linalg.sqrtm(s1.dot(s2))
     if not np.isfinite(covmean).all():
         off = np.eye(s1.shape[0]) * 1e-6
         covmean = linalg.sqrtm((s1 + off).dot(s2 + off))

@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "said_get_config",
     "said_encode_audio",
     "said_normalize_audio",
+    "said_resample_mono",
     "said_prepare_context",
     "said_denoise",
     "said_denoiser_forward",
@@ -109,6 +110,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_get_config.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.said_encode_audio.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.said_normalize_audio.argtypes = [vp, vp, ci, ci, vp, vp]
+    lib.said_resample_mono.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, ci, vp]
     lib.said_prepare_context.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.said_denoise.argtypes = [vp, ctypes.POINTER(DenoiseArgs), vp]
     lib.said_denoiser_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, vp, vp]
@@ -236,6 +238,34 @@ class Engine:
         out = torch.empty_like(wave)
         with torch.cuda.device(self.device):
             self._call(self.lib.said_normalize_audio(self._h, wave.data_ptr(), B, T_a, out.data_ptr(), self._stream()))
+        return out
+
+    def resample_mono(self, wave: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
+        """(channels, n) waveform on the device at ``orig_freq`` -> mono (n_out,) at ``new_freq``: torchaudio.functional.resample
+        (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99 -- its defaults, which the reference uses) + mean over channels."""
+        import math
+
+        wave = _check_dev(wave, self.device, "waveform")
+        channels, n_in = wave.shape
+        g = math.gcd(int(orig_freq), int(new_freq))
+        orig, nw = int(orig_freq) // g, int(new_freq) // g
+        # filter bank: torchaudio/functional/functional.py::_get_sinc_resample_kernel, evaluated in float32 as resample() does
+        lpw, rolloff = 6, 0.99
+        base = min(orig, nw) * rolloff
+        width = math.ceil(lpw * orig / base)
+        idx = torch.arange(-width, width + orig, dtype=torch.float32)[None] / orig
+        t = torch.arange(0, -nw, -1, dtype=torch.float32)[:, None] / nw + idx
+        t = (t * base).clamp_(-lpw, lpw)
+        window = torch.cos(t * math.pi / lpw / 2) ** 2
+        t = t * math.pi
+        bank = torch.where(t == 0, torch.tensor(1.0), t.sin() / t) * window * (base / orig)
+        bank = bank.to(torch.float32).contiguous().to(self.device)
+        n_out = int(math.ceil(nw * n_in / orig))
+        out = torch.empty((n_out,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_resample_mono(self._h, wave.data_ptr(), channels, n_in, orig, nw, width, bank.data_ptr(),
+                                                   out.data_ptr(), n_out, self._stream()))
+        self._keep_aux = [wave, bank]
         return out
 
     def prepare_context(self, emb: torch.Tensor, with_uncond: bool) -> None:

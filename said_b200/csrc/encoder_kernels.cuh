@@ -162,6 +162,32 @@ conv0_apply_kernel(const float* __restrict__ wave, int T_a, int L0, const float*
     }
 }
 
+// Device-side load_audio tail (reference said/util/audio.py:35-38): torchaudio.functional.resample (polyphase windowed-sinc FIR:
+// output j = i * new + p uses filter bank row p on the input window starting at i * orig - width) applied per channel, then the
+// mean over channels.  wave: (channels, n_in); bank: (new, K = 2 width + orig), built by the host exactly as torchaudio builds it;
+// out: (n_out).  One thread per output sample.
+__global__ void __launch_bounds__(256)
+resample_mono_kernel(const float* __restrict__ wave, int channels, int n_in, int orig, int nw, int width, const float* __restrict__ bank,
+                     float* __restrict__ out, int n_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    const int i = j / nw, p = j - i * nw;
+    const int K = 2 * width + orig;
+    const float* f = bank + (long long)p * K;
+    const int x0 = i * orig - width;
+    float mix = 0.f;
+    for (int c = 0; c < channels; ++c) {
+        const float* x = wave + (long long)c * n_in;
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const int xi = x0 + k;
+            if (xi >= 0 && xi < n_in) acc = fmaf(__ldg(f + k), __ldg(x + xi), acc);
+        }
+        mix += acc;
+    }
+    out[j] = mix / (float)channels;
+}
+
 // Positional conv embedding input: (B, T, H) -> zero-padded, group-major (B, G, T + KP, H/G) so that
 // the grouped Conv1d(H, H, k=KP, pad=KP/2, groups=G) becomes, per (clip, group), a GEMM whose row t is
 // the contiguous run of KP*(H/G) floats starting at padded frame t (row stride = H/G floats).

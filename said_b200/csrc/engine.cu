@@ -2072,6 +2072,18 @@ int said_normalize_audio(said_engine* e, const float* wave_dev, int B, int T_a, 
     return 0;
 }
 
+int said_resample_mono(said_engine* e, const float* wave_dev, int channels, int n_in, int orig, int nw, int width, const float* bank_dev,
+                       float* out_dev, int n_out, void* stream) {
+    if (!e) return fail("null engine");
+    if (!wave_dev || !bank_dev || !out_dev || channels <= 0 || n_in <= 0 || orig <= 0 || nw <= 0 || width < 0 || n_out <= 0)
+        return fail("said_resample_mono: bad arguments");
+    CK(cudaSetDevice(e->device));
+    resample_mono_kernel<<<(n_out + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wave_dev, channels, n_in, orig, nw, width, bank_dev, out_dev, n_out);
+    ++e->launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int said_encode_audio(said_engine* e, const float* wave_dev, int B, int T_a, int T, float* emb_out_dev, void* stream) {
     if (!e) return fail("null engine");
     CK(cudaSetDevice(e->device));
@@ -2328,6 +2340,17 @@ int said_op_self_attention_h(said_engine* e, const float* qkv_dev, int B, int T,
         cudaFuncGetAttributes(&fa, hx::self_attention_h_kernel);
         fprintf(stderr, "[said] self_attention_h_kernel: T=%d smem=%zu B, %d regs, resident CTAs per SM = %d\n", T, hx::attention_h_smem_bytes(T),
                 fa.numRegs, nb);
+        int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, hx::self_attention_h_kernel, 256, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, hx::self_attention_h_kernel, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, hx::self_attention_h_kernel, 64, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, hx::self_attention_h_kernel, 256, 16384);
+        cudaDeviceProp pr;
+        cudaGetDeviceProperties(&pr, e->device);
+        fprintf(stderr, "[said]   occupancy probes: (256 thr, 0 smem) %d, (128, 0) %d, (64, 0) %d, (256, 16 KB) %d; static smem %zu, maxDyn %d, "
+                "regsPerSM %d, smemPerSM %zu, reserved %zu, maxBlocksPerSM %d, maxThreadsPerSM %d\n", o1, o2, o3, o4, fa.sharedSizeBytes,
+                fa.maxDynamicSharedSizeBytes, pr.regsPerMultiprocessor, pr.sharedMemPerMultiprocessor, pr.reservedSharedMemPerBlock,
+                pr.maxBlocksPerMultiProcessor, pr.maxThreadsPerMultiProcessor);
     }
     hx::self_attention_h_kernel<<<dim3(heads, B), hx::AH_THREADS, hx::attention_h_smem_bytes(T), st>>>(
         qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr);

@@ -52,19 +52,38 @@ def load_audio(audio_path: str, sampling_rate: int) -> torch.FloatTensor:
     return torch.mean(waveform, dim=0)
 
 
+def load_audio_device(audio_path: str, sampling_rate: int, device) -> torch.FloatTensor:
+    """``load_audio`` with the resampling and the mono mix on the GPU: the file is decoded on the host (WAV
+    container parsing is not device work), uploaded as stored, and resampled / averaged over channels by ``said_resample_mono``
+    (torchaudio's algorithm, its default parameters).  Returns the mono waveform (T_a,) on ``device``."""
+    from .._lib import Engine
+
+    waveform, sr = _read_wav(audio_path)
+    eng = _engine_for(device)
+    wave_dev = waveform.to(eng.device, torch.float32).contiguous()
+    if sr != sampling_rate:
+        return eng.resample_mono(wave_dev, sr, sampling_rate)
+    return wave_dev.mean(dim=0)
+
+
+_ENGINES = {}
+
+
+def _engine_for(device):
+    from .._lib import Engine
+
+    d = torch.device(device)
+    key = d.index if d.index is not None else torch.cuda.current_device()
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(torch.device("cuda", key))
+    return _ENGINES[key]
+
+
 def fit_audio_unet(waveform: torch.FloatTensor, sampling_rate: int, fps: int, divisor_unet: int) -> FittedWaveform:
-    """Zero-pad the waveform so that the coefficient sequence length is divisible by ``divisor_unet``
-    (reference ``audio.py:42-75``)."""
-    gcd = math.gcd(sampling_rate, fps)
-    divisor_waveform = sampling_rate // gcd * divisor_unet
-
-    waveform_len = waveform.shape[0]
-    window_len = int(waveform_len / sampling_rate * fps)
-    waveform_len_fit = math.ceil(waveform_len / divisor_waveform) * divisor_waveform
-
-    if waveform_len_fit > waveform_len:
-        tmp = torch.zeros(waveform_len_fit)
-        tmp[:waveform_len] = waveform[:]
-        waveform = tmp
-
-    return FittedWaveform(waveform=waveform, window_size=window_len)
+    """Zero-pad the mono waveform (host or device tensor) up to the next multiple of the hop that makes the coefficient sequence
+    length divisible by ``divisor_unet``; ``window_size`` is the frame count of the UNPADDED audio (reference ``audio.py:42-75``)."""
+    hop = sampling_rate // math.gcd(sampling_rate, fps) * divisor_unet      # samples per `divisor_unet` coefficient frames
+    n = int(waveform.shape[0])
+    deficit = -n % hop
+    fitted = torch.nn.functional.pad(waveform, (0, deficit)) if deficit else waveform
+    return FittedWaveform(waveform=fitted, window_size=int(n / sampling_rate * fps))

@@ -67,3 +67,30 @@ def test_frechet_between_precision_modes(gpu_model, state_dict):
     d_seeds = ev.frechet_distance(outs[("fp16x3", 0)], outs[("fp16x3", 1)], 20)
     print("frechet: fp16x3 vs fp32 (same noise)", d_modes, " different noise", d_seeds)
     assert d_modes < 0.05 * d_seeds
+
+
+@pytest.mark.parametrize("sr,channels", [(44100, 2), (48000, 1), (8000, 2), (22050, 1)])
+def test_resample_mono_vs_torchaudio(tmp_path, sr, channels):
+    """Device-side load_audio tail (resample to 16 kHz + mono mix, 8(f) rank 1) against torchaudio.functional.resample +
+    mean on the CPU -- what the reference's load_audio runs (said/util/audio.py:35-38)."""
+    import torchaudio
+    from scipy.io import wavfile
+
+    from said_b200.util.audio import fit_audio_unet, load_audio, load_audio_device
+
+    g = torch.Generator().manual_seed(sr + channels)
+    n = int(sr * 1.3) + 17
+    t = torch.arange(n, dtype=torch.float32) / sr
+    x = torch.stack([0.4 * torch.sin(6.2832 * (200 + 50 * c) * t) + 0.05 * torch.randn(n, generator=g) for c in range(channels)])
+    pcm = (x.clamp(-1, 1) * 32767).round().to(torch.int16)
+    path = os.path.join(tmp_path, "a.wav")
+    wavfile.write(path, sr, pcm.T.contiguous().numpy() if channels > 1 else pcm[0].numpy())
+    want = load_audio(path, 16000)                      # host: torchaudio resample + mean
+    got = load_audio_device(path, 16000, DEV)
+    ref = torchaudio.functional.resample(pcm.float() / 32768.0, sr, 16000).mean(dim=0)
+    err, err2 = float((got.cpu() - want).abs().max()), float((got.cpu() - ref).abs().max())
+    print("resample", sr, channels, tuple(got.shape), err, err2)
+    assert got.device.type == "cuda" and got.shape == want.shape
+    assert err < 2e-6 and err2 < 2e-6
+    fit = fit_audio_unet(got, 16000, 60, 1)             # zero-padding to the 800-sample hop also runs on the device tensor
+    assert fit.waveform.device.type == "cuda" and fit.waveform.shape[0] % 800 == 0 and fit.window_size == int(got.shape[0] / 16000 * 60)
