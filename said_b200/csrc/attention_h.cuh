@@ -2,8 +2,11 @@
 //
 //   out = softmax(q k^T * scale) v          (CrossAttention.forward with context=None, ldm/attention.py:86-128)
 //
-// One CTA per (head, sample), TWO CTAs resident per SM (256 TMEM columns and ~99 KB of shared memory each at T = 300): the kernel is
-// a chain of short dependent phases (MMA -> softmax -> MMA), so the second CTA fills the first one's latency bubbles.
+// One CTA per (pair of heads, sample): the kernel is a chain of short dependent phases (MMA -> softmax -> MMA), so two independent
+// groups of 8 warps -- one head each, with their own 256 tensor-memory columns, ~99 KB of shared memory (T = 300) and barriers --
+// share the SM and fill each other's latency bubbles.  (Two CTAs per SM would do the same, but a kernel that uses tensor memory
+// is admitted one CTA per SM: measured with the occupancy API for every block size / shared-memory size.)  Sequences whose
+// operands do not fit twice (T > ~340) run one head per CTA.
 //   * K and V^T of the head are staged once: fp32 -> fp16 hi/lo, each row [hi(32 dims) | lo(32 dims)] = one 128-byte
 //     SWIZZLE_128B row, so the three passes of the split product (hi*hi + lo*hi + hi*lo) are just different 32-byte K-slices of
 //     the same tiles; V^T per 64 keys is a 64-row tile [hi dims | lo dims] x 64 keys.
@@ -21,19 +24,12 @@ namespace hx {
 
 constexpr int AH_HD = 32;
 constexpr int AH_SM_THREADS = 256;                 // 8 warps: staging / softmax / epilogue, two threads per query row
-constexpr int AH_THREADS = AH_SM_THREADS;          // thread 0 also issues the MMAs: with a ninth warp one SM sub-partition would host 3 warps
-                                                   // per CTA and its 16 K registers could not hold two CTAs (measured: 1 CTA per SM)
+constexpr int AH_THREADS = AH_SM_THREADS;          // threads per group (= per head); thread 0 of the group also issues its MMAs
 constexpr int AH_KB = 128;                         // keys per block
 constexpr int AH_S_COL = 0;                        // TMEM columns [0, 128): scores, then P_hi (cols 0-63) | P_lo (cols 64-127) packed 2 per column
 constexpr int AH_O_COL = 128;                      // TMEM columns [128, 192): output accumulators
 constexpr int AH_TMEM_COLS = 256;
 constexpr int AH_MAXT = 512;
-
-inline size_t attention_h_smem_bytes(int T) {
-    const int Tkp = (T + 15) / 16 * 16;
-    const int nch = (T + 63) / 64;
-    return (size_t)Tkp * 128 + 1024 /*V tile alignment*/ + (size_t)nch * 8192 + 16384 /*Q*/ + 2 * AH_SM_THREADS * 4 + 64 + 1024;
-}
 
 SAID_DEVINL void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -80,26 +76,42 @@ SAID_DEVINL void sts16(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(AH_THREADS, 2)
+// Per-group shared memory (one group = 8 warps = one head): K, V^T, Q, exchange floats, barriers.
+inline size_t attention_h_group_bytes(int T) {
+    const int Tkp = (T + 15) / 16 * 16;
+    const int nch = (T + 63) / 64;
+    const size_t raw = (size_t)Tkp * 128 + 1024 /*V tile alignment*/ + (size_t)nch * 8192 + 16384 /*Q*/ + 2 * AH_SM_THREADS * 4 + 64;
+    return (raw + 1023) / 1024 * 1024;
+}
+inline size_t attention_h_smem_bytes(int T, int groups) { return attention_h_group_bytes(T) * groups + 1024; }
+// two heads per CTA whenever their operands fit one SM's shared memory together (T <= ~340)
+inline int attention_h_groups(int T, int heads) { return (heads % 2 == 0 && attention_h_smem_bytes(T, 2) <= 227 * 1024) ? 2 : 1; }
+
+// grid (heads / groups, samples), block 256 * groups: group g (threads [256 g, 256 g + 256)) processes head blockIdx.x * groups + g with
+// its own shared memory, tensor-memory columns [256 g, 256 g + 192) and barriers; the two groups only meet at the TMEM allocation.
+__global__ void __launch_bounds__(2 * AH_THREADS, 1)
 self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int T, float scale,
                         float* __restrict__ out, int ldo, int Tstr /*rows per sample in qkv / out*/,
                         __half* __restrict__ out_pair /*non-null: write the pair tensor (ldo columns) instead of fp32*/,
-                        int* __restrict__ flag) {
+                        int* __restrict__ flag, uint32_t group_bytes) {
     extern __shared__ uint8_t smem_raw[];
     const int Tkp = (T + 15) / 16 * 16;
     const int nch = (T + 63) / 64;                    // 64-key chunks of V^T
     const int nkb = (T + AH_KB - 1) / AH_KB;          // 128-key blocks
-    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int grp = threadIdx.x >> 8, groups = blockDim.x >> 8;
+    const int tid = threadIdx.x & 255, warp = tid >> 5, lane = tid & 31;     // (within the group)
+    const uint32_t base0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t base = base0 + (uint32_t)grp * group_bytes;
     const uint32_t k_sm = base;                                            // [Tkp rows][hi 64 B | lo 64 B]
     const uint32_t v_sm = (k_sm + (uint32_t)Tkp * 128u + 1023u) & ~1023u;  // per 64-key chunk: [32 hi-dim rows | 32 lo-dim rows] x 128 B
     const uint32_t q_sm = v_sm + (uint32_t)nch * 8192u;                    // [128 rows][hi | lo]
     const uint32_t xch = q_sm + 16384u;                                    // float[2][AH_SM_THREADS]
     const uint32_t bars = xch + 2u * AH_SM_THREADS * 4u;
     const uint32_t bar_q = bars, bar_s = bars + 8u, bar_p = bars + 16u, bar_o = bars + 24u;
-    const uint32_t tmem_slot = bars + 32u;
+    const uint32_t tmem_slot = base0 + group_bytes - 8u;                   // (last bytes of group 0's region: shared by both groups)
+    const int nbar = 1 + grp;                                              // named barrier of this group
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int h = blockIdx.x, b = blockIdx.y;
+    const int h = blockIdx.x * groups + grp, b = blockIdx.y;
     const float* gbase = qkv + (long long)b * Tstr * ld + h * AH_HD;
 
     if (tid == 0) {
@@ -110,12 +122,14 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
         fence_mbar_init();
     }
     __syncwarp();
-    if (warp == 0) tc::tmem_alloc_imm<AH_TMEM_COLS>(tmem_slot);
+    if (threadIdx.x < 32) tmem_alloc(tmem_slot, groups == 2 ? 512u : 256u);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const uint32_t tmem_cta = tmem_base;
+    tmem_base += (uint32_t)grp * 256u;                                     // this group's columns
     pdl_wait();
     pdl_trigger();
     const int n_qtiles = (T + 127) / 128;
@@ -256,7 +270,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                     }
                 }
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)tid * 4u), "f"(mx) : "memory");
-                asm volatile("bar.sync 1, %0;" ::"n"(AH_SM_THREADS) : "memory");   // also: every thread holds its scores in registers now
+                asm volatile("bar.sync %0, %1;" ::"r"(nbar), "n"(AH_SM_THREADS) : "memory");   // also: every thread holds its scores in registers now
                 float other;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch + (uint32_t)(tid ^ 128) * 4u));
                 const float m_new = fmaxf(m_run, fmaxf(mx, other));
@@ -310,7 +324,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             mbar_wait(bar_o, n_o & 1u);
             ++n_o;
             tc_fence_after();
-            asm volatile("bar.sync 1, %0;" ::"n"(AH_SM_THREADS) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(nbar), "n"(AH_SM_THREADS) : "memory");
             float l_other;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xch + (uint32_t)(AH_SM_THREADS + (tid ^ 128)) * 4u));
             const float inv = 1.0f / (l_part + l_other);
@@ -342,9 +356,9 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (threadIdx.x < 32) {
         tc_fence_after();
-        tc::tmem_dealloc_imm<AH_TMEM_COLS>(tmem_base);
+        tmem_dealloc(tmem_cta, groups == 2 ? 512u : 256u);
     }
 }
 

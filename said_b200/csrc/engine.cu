@@ -78,6 +78,7 @@ struct DevBuf {
         if (n <= cap) return cudaSuccess;
         cudaError_t e = ensure(n);
         if (e == cudaSuccess) e = cudaMemset(p, 0, cap * sizeof(float));
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the memset runs on the legacy stream; the engine's streams do not wait for it
         return e;
     }
     ~DevBuf() {
@@ -901,10 +902,13 @@ int said_engine::encode_audio(const float* wave, int B, int T_a, int T, float* e
         int& p; int saved;
         PrecisionScope(int& p_, int v) : p(p_), saved(p_) { p = v; }
         ~PrecisionScope() { p = saved; }
-    } scope(precision, enc_precision);
+    } scope(precision, enc_precision == 3 ? 0 : enc_precision);   // fp16x3 encoder below its row threshold: the IEEE fp32 kernels throughout
     if (!ready) return fail("weights not committed");
     if (B <= 0 || T <= 0) return fail("encode_audio: empty batch");
-    if (enc_precision == 3 && (long long)B * T >= tc_min_rows) return encode_audio_h(wave, B, T_a, T, emb_out, st);
+    if (enc_precision == 3 && (long long)B * T >= tc_min_rows) {
+        scope.p = 3;
+        return encode_audio_h(wave, B, T_a, T, emb_out, st);
+    }
     int L[8];
     L[0] = (T_a - conv_k[0]) / conv_s[0] + 1;
     if (T_a < conv_k[0]) return fail("encode_audio: waveform shorter than the first conv kernel");
@@ -1447,12 +1451,9 @@ int said_engine::ensure_denoiser_ws(int Bp, int T) {
     if (T <= tc::ATC_MAXKEYS)
         CK(cudaFuncSetAttribute(tc::self_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)tc::attention_tc_smem_bytes(T)));
-    if (T <= hx::AH_MAXT) {
+    if (T <= hx::AH_MAXT)
         CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)hx::attention_h_smem_bytes(T)));
-        // two CTAs per SM need ~200 KB of the SM's unified L1 / shared memory: ask for the largest shared-memory carve-out
-        CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
+                                (int)hx::attention_h_smem_bytes(T, hx::attention_h_groups(T, HEADS))));
     return 0;
 }
 
@@ -1795,8 +1796,10 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
         }
         cur_tag = TAG_ATTN;
         if (T <= hx::AH_MAXT && attn_h) {
-            CK(launch_ex(hx::self_attention_h_kernel, dim3(HEADS, h_nb), dim3(hx::AH_THREADS), hx::attention_h_smem_bytes(T), st, pdl, 1,
-                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag));
+            const int ag = hx::attention_h_groups(T, HEADS);
+            CK(launch_ex(hx::self_attention_h_kernel, dim3(HEADS / ag, h_nb), dim3(hx::AH_THREADS * ag), hx::attention_h_smem_bytes(T, ag), st, pdl, 1,
+                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag,
+                         (uint32_t)hx::attention_h_group_bytes(T)));
         } else if (T <= tc::ATC_MAXKEYS) {
             CK(launch_ex(tc::self_attention_tc_kernel, dim3(HEADS, h_nb), dim3(tc::ATC_THREADS), tc::attention_tc_smem_bytes(T), st, pdl, 1,
                          (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag));
@@ -2331,29 +2334,11 @@ int said_op_self_attention_h(said_engine* e, const float* qkv_dev, int B, int T,
     CK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int Cw = heads * 32;
-    CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hx::attention_h_smem_bytes(T)));
-    CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (getenv("SAID_DEBUG")) {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hx::self_attention_h_kernel, hx::AH_THREADS, hx::attention_h_smem_bytes(T));
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, hx::self_attention_h_kernel);
-        fprintf(stderr, "[said] self_attention_h_kernel: T=%d smem=%zu B, %d regs, resident CTAs per SM = %d\n", T, hx::attention_h_smem_bytes(T),
-                fa.numRegs, nb);
-        int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, hx::self_attention_h_kernel, 256, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, hx::self_attention_h_kernel, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, hx::self_attention_h_kernel, 64, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o4, hx::self_attention_h_kernel, 256, 16384);
-        cudaDeviceProp pr;
-        cudaGetDeviceProperties(&pr, e->device);
-        fprintf(stderr, "[said]   occupancy probes: (256 thr, 0 smem) %d, (128, 0) %d, (64, 0) %d, (256, 16 KB) %d; static smem %zu, maxDyn %d, "
-                "regsPerSM %d, smemPerSM %zu, reserved %zu, maxBlocksPerSM %d, maxThreadsPerSM %d\n", o1, o2, o3, o4, fa.sharedSizeBytes,
-                fa.maxDynamicSharedSizeBytes, pr.regsPerMultiprocessor, pr.sharedMemPerMultiprocessor, pr.reservedSharedMemPerBlock,
-                pr.maxBlocksPerMultiProcessor, pr.maxThreadsPerMultiProcessor);
-    }
-    hx::self_attention_h_kernel<<<dim3(heads, B), hx::AH_THREADS, hx::attention_h_smem_bytes(T), st>>>(
-        qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr);
+    const int ag = hx::attention_h_groups(T, heads);
+    const size_t smem = hx::attention_h_smem_bytes(T, ag);
+    CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hx::self_attention_h_kernel<<<dim3(heads / ag, B), hx::AH_THREADS * ag, smem, st>>>(
+        qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr, (uint32_t)hx::attention_h_group_bytes(T));
     ++e->launches;
     CK(cudaGetLastError());
     return 0;
