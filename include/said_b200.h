@@ -100,6 +100,12 @@ typedef struct said_denoise_args {
     int scheduler;                  /* 0 DDIMScheduler.step; 1 DDPMScheduler.step (ancestral sampling, reference diffusion.py:55,404:
                                        table slots 2..4 then hold pred_original_sample_coeff, current_sample_coeff, sqrt(variance)
                                        and eta_noise_dev the per-step variance noise) */
+    int resume;                     /* 1: this call continues a loop started by an earlier call (chunked loops: the per-step
+                                       variance noise of eta > 0 / DDPM is then drawn and held chunk by chunk instead of for all
+                                       steps): init_src_dev holds the latents the previous call returned in latents_out_dev, no
+                                       scaling / noising is applied and the engine keeps its copy of the un-noised init_samples */
+    int more;                       /* 1: another chunk follows: the last iteration of this call is NOT the loop's last (no final
+                                       un-noised blend, no result); result_dev may be NULL */
 } said_denoise_args;
 SAID_API int said_denoise(said_engine* e, const said_denoise_args* args, void* stream);
 

@@ -76,6 +76,8 @@ class DenoiseArgs(ctypes.Structure):
         ("latents_out_dev", ctypes.c_void_p),
         ("use_graph", ctypes.c_int),
         ("scheduler", ctypes.c_int),
+        ("resume", ctypes.c_int),
+        ("more", ctypes.c_int),
     ]
 
 
@@ -294,6 +296,8 @@ class Engine:
         latents_out: Optional[torch.Tensor] = None,
         use_graph: bool = True,
         scheduler: int = 0,
+        resume: bool = False,
+        more: bool = False,
     ) -> torch.Tensor:
         init_src = _check_dev(init_src, self.device, "initial latents")
         B, T, C = init_src.shape
@@ -319,6 +323,7 @@ class Engine:
             mask_dev=_ptr(opt["mask"]), eta_noise_dev=_ptr(opt["eta_noise"]),
             intermediates_dev=_ptr(intermediates), result_dev=result.data_ptr(),
             latents_out_dev=_ptr(latents_out), use_graph=int(bool(use_graph)), scheduler=int(scheduler),
+            resume=int(bool(resume)), more=int(bool(more)),
         )
         with torch.cuda.device(self.device):
             self._call(self.lib.said_denoise(self._h, ctypes.byref(a), self._stream()))

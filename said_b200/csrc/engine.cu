@@ -1906,8 +1906,12 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
     CK(cudaEventRecord(ev_in, user));
     CK(cudaStreamWaitEvent(st, ev_in, 0));
 
-    prepare_latents_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a.init_src_dev, a.init_scale, a.edit_noise_dev, a.edit_sqrt_a,
-                                                                         a.edit_sqrt_b, lat.p, init_lat.p, tot);
+    if (a.resume) {   // continuation of a chunked loop: the latents come back as they were returned; init_lat keeps the first call's copy
+        prepare_latents_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a.init_src_dev, 1.0f, nullptr, 1.0f, 0.0f, lat.p, nullptr, tot);
+    } else {
+        prepare_latents_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a.init_src_dev, a.init_scale, a.edit_noise_dev, a.edit_sqrt_a,
+                                                                             a.edit_sqrt_b, lat.p, init_lat.p, tot);
+    }
     LAUNCH_CHECK();
     if (a.n_steps == 0) {
         finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(lat.p, a.latent_scale, a.result_dev, tot);
@@ -1936,7 +1940,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         sp.pred_type = a.prediction_type;
         sp.table = step_tab.p;
         sp.step_ptr = step_ctr;
-        sp.n_steps = a.n_steps;
+        sp.n_steps = a.more ? a.n_steps + 1 : a.n_steps;   // "last iteration" (un-noised blend, result) only in the loop's final chunk
         sp.eta_noise = a.eta_noise_dev;
         sp.scheduler = a.scheduler;
         sp.init_latents = init_lat.p;
@@ -1961,7 +1965,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         if (a.use_graph && a.n_steps > 1) {
             GraphKey key;
             memset(&key, 0, sizeof(key));
-            key.B = B; key.T = T; key.Tc = ctx_T; key.do_cfg = a.do_cfg; key.n_steps = a.n_steps; key.pred_type = a.prediction_type;
+            key.B = B; key.T = T; key.Tc = ctx_T; key.do_cfg = a.do_cfg; key.n_steps = sp.n_steps; key.pred_type = a.prediction_type;
             key.scheduler = a.scheduler; key.precision = precision; key.tc_min_rows = tc_min_rows;
             key.gscale = a.guidance_scale; key.grescale = a.guidance_rescale; key.latent_scale = a.latent_scale;
             key.eta_noise = a.eta_noise_dev; key.edit_noise = a.edit_noise_dev; key.mask = a.mask_dev;
@@ -1994,7 +1998,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         } else {
             for (int s = 0; s < a.n_steps; ++s) CKI(one_step());
         }
-        CK(cudaMemcpyAsync(a.result_dev, result_buf.p, (size_t)tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (!a.more && a.result_dev) CK(cudaMemcpyAsync(a.result_dev, result_buf.p, (size_t)tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     if (a.latents_out_dev)
         CK(cudaMemcpyAsync(a.latents_out_dev, lat.p, (size_t)tot * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -172,6 +172,7 @@ class SAID(ABC, nn.Module):
         self._engine_keys: Dict[int, tuple] = {}
         self.use_cuda_graph = True
         self.dedup_audio = True           # a batch that repeats one clip (script/test_inference.py:167) is encoded once
+        self.eta_chunk_bytes = 256 << 20  # resident per-step variance noise (eta > 0 / DDPMScheduler): the loop runs in chunks of this much
         # contraction precision of the denoiser GEMMs: "tf32x3" (tcgen05, 3xTF32 split: fp32-level accuracy),
         # "fp16x3" (tcgen05 over fp16 hi/lo operand pairs loaded by TMA: same accuracy class at twice the tensor-core rate),
         # "tf32" (tcgen05, single pass) or "fp32" (FFMA); GEMMs below tc_min_rows rows stay on the FFMA kernel
@@ -324,20 +325,24 @@ class SAID(ABC, nn.Module):
         # the latents keep init_samples' own length in the editing mode (reference diffusion.py:366); only the audio features
         # are resampled to window_size frames
         n_frames = window_size if init_samples is None else int(init_samples.shape[1])
+        # Per-step variance noise (eta > 0: DDIMScheduler.step draws randn(model_output.shape) once per iteration; DDPMScheduler.step in
+        # every iteration whose timestep is > 0).  It is drawn lazily, in loop order, by the chunked loop of _run -- the same
+        # torch.randn calls as the reference, but only a bounded number of steps' worth is ever resident (the reference holds one
+        # step's noise at a time; n_loop x B x T x C up front would be 2.5 GB at batch 64 x 1000 steps).
         eta_noise = None
+        shape = (batch_size, n_frames, in_channels)
         if eta > 0 and n_loop > 0 and self._scheduler_has_eta():
-            # DDIMScheduler.step draws randn(model_output.shape) once per iteration
-            eta_noise = torch.stack(
-                [torch.randn(batch_size, n_frames, in_channels, device=device) for _ in range(n_loop)]
-            )
+            def eta_noise(i: int, out: torch.Tensor) -> None:
+                torch.randn(shape, device=device, out=out)
         elif self._scheduler_is_ddpm() and n_loop > 0:
-            # DDPMScheduler.step draws randn(model_output.shape) in every iteration whose timestep is > 0
             self.noise_scheduler.set_timesteps(num_inference_steps, device=device)
-            loop_ts = [int(t) for t in self.noise_scheduler.timesteps.detach().cpu().numpy()][num_inference_steps - n_loop:]
-            eta_noise = torch.stack(
-                [torch.randn(batch_size, n_frames, in_channels, device=device) if t > 0
-                 else torch.zeros(batch_size, n_frames, in_channels, device=device) for t in loop_ts]
-            )
+            ddpm_ts = [int(t) for t in self.noise_scheduler.timesteps.detach().cpu().numpy()][num_inference_steps - n_loop:]
+
+            def eta_noise(i: int, out: torch.Tensor) -> None:
+                if ddpm_ts[i] > 0:
+                    torch.randn(shape, device=device, out=out)
+                else:
+                    out.zero_()
         return self._run(
             waveform_processed, noise, init_samples, mask, num_inference_steps, strength, guidance_scale,
             guidance_rescale, eta, window_size, save_intermediate, show_process, eta_noise,
@@ -445,16 +450,37 @@ class SAID(ABC, nn.Module):
         inter = None
         if save_intermediate and n_loop > 0:
             inter = torch.empty((n_loop, batch_size, n_frames, in_channels), dtype=torch.float32, device=device)
-        latents_out = torch.empty_like(src) if return_latents else None
         if getattr(self, "_profile_loop", False):   # bench.py: per-kernel timing of the loop only
             eng.profile_begin()
-        result = eng.denoise(
-            src, loop_ts, table, ns_prediction_code(ns), do_cfg, guidance_scale, guidance_rescale,
-            float(self.latent_scale), float(self.latent_scale) * float(ns.init_noise_sigma),
-            edit_noise=edit_noise, edit_coefs=edit_coefs, mask=mask if use_mask else None,
-            eta_noise=eta_noise, intermediates=inter, latents_out=latents_out, use_graph=self.use_cuda_graph,
-            scheduler=1 if is_ddpm else 0,
-        )
+        # The loop runs as one device program; when per-step variance noise is drawn lazily it runs in chunks of at most
+        # `eta_chunk_bytes` of noise (one reused buffer), the latents carried from chunk to chunk.
+        lazy = callable(eta_noise)
+        chunk = n_loop
+        if lazy and n_loop > 0:
+            chunk = max(1, min(n_loop, int(self.eta_chunk_bytes) // (src[0].numel() * batch_size * 4)))
+        noise_buf = torch.empty((chunk,) + tuple(src.shape), dtype=torch.float32, device=device) if lazy and n_loop > 0 else None
+        n_chunks = max(1, -(-n_loop // max(chunk, 1)))
+        latents_out = torch.empty_like(src) if (return_latents or n_chunks > 1) else None
+        carry, result = src, None
+        for ci in range(n_chunks):
+            c0, c1 = ci * chunk, min(n_loop, (ci + 1) * chunk)
+            en = eta_noise
+            if lazy and n_loop > 0:
+                for i in range(c0, c1):
+                    eta_noise(i, noise_buf[i - c0])
+                en = noise_buf[: c1 - c0]
+            elif eta_noise is not None:
+                en = eta_noise[c0:c1]
+            result = eng.denoise(
+                carry, loop_ts[c0:c1], table[c0:c1], ns_prediction_code(ns), do_cfg, guidance_scale, guidance_rescale,
+                float(self.latent_scale), float(self.latent_scale) * float(ns.init_noise_sigma),
+                edit_noise=edit_noise, edit_coefs=edit_coefs, mask=mask if use_mask else None,
+                eta_noise=en, intermediates=None if inter is None else inter[c0:c1], latents_out=latents_out,
+                use_graph=self.use_cuda_graph, scheduler=1 if is_ddpm else 0, resume=ci > 0, more=ci < n_chunks - 1,
+            )
+            carry = latents_out
+        if not return_latents:
+            latents_out = None
         eng.check_status()     # synchronises; raises if the fp16x3 path met an activation beyond fp16's range
         if show_process:
             from tqdm import tqdm
