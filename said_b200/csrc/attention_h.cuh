@@ -233,7 +233,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             tc::fence_proxy_async();
             mbar_arrive(bar_q);
             if (tid == 0) {
-                mbar_wait(bar_q, n_q & 1u);
+                tc::mbar_wait_tight(bar_q, n_q & 1u);
                 ++n_q;
                 tc_fence_after();
                 issue_s(0);
@@ -243,7 +243,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             for (int kb = 0; kb < nkb; ++kb) {
                 const int nvalid = min(AH_KB, T - kb * AH_KB);         // valid keys of this block
                 const int my0 = part * 64;                              // first column of this thread
-                mbar_wait(bar_s, n_s & 1u);
+                tc::mbar_wait_tight(bar_s, n_s & 1u);
                 ++n_s;
                 tc_fence_after();
                 float s[4][16];
@@ -310,7 +310,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 tc_fence_before();
                 mbar_arrive(bar_p);
                 if (tid == 0) {
-                    mbar_wait(bar_p, n_p & 1u);
+                    tc::mbar_wait_tight(bar_p, n_p & 1u);
                     ++n_p;
                     tc_fence_after();
                     issue_pv(kb);
@@ -321,7 +321,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             }
             // ---------------- O / rowsum -> global ----------------
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(AH_SM_THREADS + tid) * 4u), "f"(l_part) : "memory");
-            mbar_wait(bar_o, n_o & 1u);
+            tc::mbar_wait_tight(bar_o, n_o & 1u);
             ++n_o;
             tc_fence_after();
             asm volatile("bar.sync %0, %1;" ::"r"(nbar), "n"(AH_SM_THREADS) : "memory");

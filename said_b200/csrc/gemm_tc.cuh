@@ -88,6 +88,14 @@ SAID_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
         if (spins > 8) __nanosleep(40);          // long waits (epilogue, idle roles) must not burn issue slots
     }
 }
+// Latency-critical hand-offs (attention: MMA <-> softmax every few hundred cycles): mbarrier.try_wait already suspends the thread in
+// hardware until the phase completes or a time limit expires, so no __nanosleep (whose granularity is of the order of the waits).
+SAID_DEVINL void mbar_wait_tight(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
 SAID_DEVINL void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 SAID_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 SAID_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
