@@ -93,7 +93,11 @@ __global__ void __launch_bounds__(2 * AH_THREADS, 1)
 self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int T, float scale,
                         float* __restrict__ out, int ldo, int Tstr /*rows per sample in qkv / out*/,
                         __half* __restrict__ out_pair /*non-null: write the pair tensor (ldo columns) instead of fp32*/,
-                        int* __restrict__ flag, uint32_t group_bytes) {
+                        int* __restrict__ flag, uint32_t group_bytes, long long* __restrict__ trace = nullptr /*diagnostics: clock64 stamps of CTA (0,0) group 0 thread 0*/) {
+    int tr_n = 0;
+    const bool tr_on = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    auto stamp = [&]() { if (tr_on && tr_n < 62) trace[tr_n++] = clock64(); };
+    stamp();
     extern __shared__ uint8_t smem_raw[];
     const int Tkp = (T + 15) / 16 * 16;
     const int nch = (T + 63) / 64;                    // 64-key chunks of V^T
@@ -163,22 +167,29 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
     uint32_t n_q = 0, n_p = 0;
 
     {
-        // ---------------- stage K: row = key, [hi dims | lo dims] ----------------
-        for (int i = tid; i < Tkp * 4; i += AH_SM_THREADS) {
-            const int key = i >> 2, c2 = i & 3;                  // dims 8 c2 .. 8 c2 + 7
-            float x[8];
-            if (key < T) {
-                const float4 a = ldg4(gbase + (long long)key * ld + k_off + c2 * 8), c = ldg4(gbase + (long long)key * ld + k_off + c2 * 8 + 4);
-                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
-            } else {
+        // ---------------- stage K: row = key, [hi dims | lo dims]; two items (four 16-byte loads) in flight per thread ----------------
+        for (int i0 = tid; i0 < Tkp * 4; i0 += 2 * AH_SM_THREADS) {
+            float4 ld_[2][2];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = 0.f;
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + u * AH_SM_THREADS, key = i >> 2, c2 = i & 3;
+                const bool ok = i < Tkp * 4 && key < T;
+                const float* src = gbase + (long long)(ok ? key : 0) * ld + k_off + c2 * 8;
+                ld_[u][0] = ok ? ldg4(src) : zero4();
+                ld_[u][1] = ok ? ldg4(src + 4) : zero4();
             }
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const uint32_t row = k_sm + (uint32_t)key * 128u;
-            sts16(row + (uint32_t)((c2 ^ (key & 7)) << 4), hi);
-            sts16(row + (uint32_t)(((4 + c2) ^ (key & 7)) << 4), lo);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + u * AH_SM_THREADS, key = i >> 2, c2 = i & 3;
+                if (i < Tkp * 4) {
+                    const float x[8] = {ld_[u][0].x, ld_[u][0].y, ld_[u][0].z, ld_[u][0].w, ld_[u][1].x, ld_[u][1].y, ld_[u][1].z, ld_[u][1].w};
+                    uint4 hi, lo;
+                    split8(x, hi, lo);
+                    const uint32_t row = k_sm + (uint32_t)key * 128u;
+                    sts16(row + (uint32_t)((c2 ^ (key & 7)) << 4), hi);
+                    sts16(row + (uint32_t)(((4 + c2) ^ (key & 7)) << 4), lo);
+                }
+            }
         }
         // ---------------- stage V^T: per 64-key chunk, row = dim (hi rows 0-31, lo rows 32-63), 8 keys per 16-byte store ----------------
         for (int i = tid; i < nch * 8 * 8; i += AH_SM_THREADS) {
@@ -204,31 +215,38 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 sts16(tile + (uint32_t)(32 + dd) * 128u + (uint32_t)((kq ^ ((32 + dd) & 7)) << 4), lo);
             }
         }
+        stamp();                                               // K / V^T staged
         const int row = tid & 127, part = tid >> 7;            // two threads per query row: 64 of the 128 score columns each
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const float qscale = scale * 1.4426950408889634f;       // softmax in base 2
         uint32_t n_s = 0, n_o = 0;
+        // raw Q rows of the next query tile, prefetched into registers while the current tile is processed
+        float4 qreg[2][2];
+        auto load_q = [&](int qt) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = tid + u * AH_SM_THREADS, r = i >> 2, c2 = i & 3;
+                const bool ok = qt * 128 + r < T;
+                const float* src = gbase + (long long)(ok ? qt * 128 + r : 0) * ld + q_off + c2 * 8;
+                qreg[u][0] = ok ? ldg4(src) : zero4();
+                qreg[u][1] = ok ? ldg4(src + 4) : zero4();
+            }
+        };
+        load_q(0);
         for (int qt = 0; qt < n_qtiles; ++qt) {
             // ---------------- Q tile: 128 rows x [hi | lo], pre-scaled ----------------
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int i = tid + u * AH_SM_THREADS, r = i >> 2, c2 = i & 3;
-                float x[8];
-                if (qt * 128 + r < T) {
-                    const float* src = gbase + (long long)(qt * 128 + r) * ld + q_off + c2 * 8;
-                    const float4 a = ldg4(src), c = ldg4(src + 4);
-                    x[0] = a.x * qscale; x[1] = a.y * qscale; x[2] = a.z * qscale; x[3] = a.w * qscale;
-                    x[4] = c.x * qscale; x[5] = c.y * qscale; x[6] = c.z * qscale; x[7] = c.w * qscale;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = 0.f;
-                }
+                const float x[8] = {qreg[u][0].x * qscale, qreg[u][0].y * qscale, qreg[u][0].z * qscale, qreg[u][0].w * qscale,
+                                    qreg[u][1].x * qscale, qreg[u][1].y * qscale, qreg[u][1].z * qscale, qreg[u][1].w * qscale};
                 uint4 hi, lo;
                 split8(x, hi, lo);
                 const uint32_t ra = q_sm + (uint32_t)r * 128u;
                 sts16(ra + (uint32_t)((c2 ^ (r & 7)) << 4), hi);
                 sts16(ra + (uint32_t)(((4 + c2) ^ (r & 7)) << 4), lo);
             }
+            if (qt + 1 < n_qtiles) load_q(qt + 1);             // in flight during this tile's MMAs and softmax
             tc_fence_before();                                 // (TMEM reads of the previous tile's O are complete)
             tc::fence_proxy_async();
             mbar_arrive(bar_q);
@@ -243,31 +261,38 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             for (int kb = 0; kb < nkb; ++kb) {
                 const int nvalid = min(AH_KB, T - kb * AH_KB);         // valid keys of this block
                 const int my0 = part * 64;                              // first column of this thread
+                stamp();                                                // (waiting for S)
                 tc::mbar_wait_tight(bar_s, n_s & 1u);
                 ++n_s;
                 tc_fence_after();
+                stamp();                                                // S ready
                 float s[4][16];
-                const bool have = my0 < nvalid;                         // warp-uniform (part is)
+                // warp-uniform: this thread has valid score columns in this block, and its warp has at least one valid query row
+                const bool have = my0 < nvalid && qt * 128 + (warp & 3) * 32 < T;
+                const bool full = my0 + 64 <= nvalid;                   // no key mask needed (all blocks but the last)
                 if (have) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) tc::tmem_ld16_issue(trow + AH_S_COL + my0 + 16 * u, s[u]);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) tc::tmem_ld_wait16(s[u]);
-                }
-                float mx = -INFINITY;
-                if (have) {
-                    if (my0 + 64 <= nvalid) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, s[u][e]);
-                    } else {
+                    if (!full) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
 #pragma unroll
                             for (int e = 0; e < 16; ++e)
-                                if (my0 + 16 * u + e < nvalid) mx = fmaxf(mx, s[u][e]);
+                                if (my0 + 16 * u + e >= nvalid) s[u][e] = -INFINITY;     // masked keys: exp2(-inf) = 0 below
                     }
+                }
+                float mx = -INFINITY;
+                if (have) {
+                    float m4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        m4[u] = fmaxf(s[u][0], s[u][1]);
+#pragma unroll
+                        for (int e = 2; e < 16; e += 2) m4[u] = fmaxf(m4[u], fmaxf(s[u][e], s[u][e + 1]));
+                    }
+                    mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                 }
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)tid * 4u), "f"(mx) : "memory");
                 asm volatile("bar.sync %0, %1;" ::"r"(nbar), "n"(AH_SM_THREADS) : "memory");   // also: every thread holds its scores in registers now
@@ -278,21 +303,23 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 m_run = m_new;
                 // P = 2^(s - m) as packed fp16 hi / lo, written over the score columns
                 uint32_t ph[32], pl[32];
-                float ls = 0.f;
+                float ls0 = 0.f, ls1 = 0.f;
+                if (have) {
 #pragma unroll
-                for (int w = 0; w < 32; ++w) {
-                    float p0 = 0.f, p1 = 0.f;
-                    if (have) {
-                        p0 = (my0 + 2 * w < nvalid) ? ex2f(s[w >> 3][(2 * w) & 15] - m_new) : 0.f;
-                        p1 = (my0 + 2 * w + 1 < nvalid) ? ex2f(s[w >> 3][(2 * w + 1) & 15] - m_new) : 0.f;
+                    for (int w = 0; w < 32; ++w) {
+                        const float p0 = ex2f(s[w >> 3][(2 * w) & 15] - m_new), p1 = ex2f(s[w >> 3][(2 * w + 1) & 15] - m_new);
+                        ls0 += p0;
+                        ls1 += p1;
+                        const __half2 hh = __floats2half2_rn(p0, p1);
+                        const float2 hf = __half22float2(hh);
+                        ph[w] = *reinterpret_cast<const uint32_t*>(&hh);
+                        pl[w] = pack_h2(p0 - hf.x, p1 - hf.y);
                     }
-                    ls += p0 + p1;
-                    const __half2 hh = __floats2half2_rn(p0, p1);
-                    const float2 hf = __half22float2(hh);
-                    ph[w] = *reinterpret_cast<const uint32_t*>(&hh);
-                    pl[w] = pack_h2(p0 - hf.x, p1 - hf.y);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 32; ++w) { ph[w] = 0u; pl[w] = 0u; }
                 }
-                l_part = l_part * alpha + ls;
+                l_part = l_part * alpha + (ls0 + ls1);
                 tmem_st32u(trow + AH_S_COL + part * 32, ph);
                 tmem_st32u(trow + AH_S_COL + 64 + part * 32, pl);
                 // rescale the running output when the maximum moved (warp-uniform decision: tcgen05.ld/st are warp-wide)
@@ -309,6 +336,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 tc::tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar_p);
+                stamp();                                                // softmax of this thread done
                 if (tid == 0) {
                     tc::mbar_wait_tight(bar_p, n_p & 1u);
                     ++n_p;
@@ -321,7 +349,9 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             }
             // ---------------- O / rowsum -> global ----------------
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(AH_SM_THREADS + tid) * 4u), "f"(l_part) : "memory");
+            stamp();
             tc::mbar_wait_tight(bar_o, n_o & 1u);
+            stamp();                                                    // O ready
             ++n_o;
             tc_fence_after();
             asm volatile("bar.sync %0, %1;" ::"r"(nbar), "n"(AH_SM_THREADS) : "memory");
@@ -353,6 +383,8 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             }
         }
     }
+    stamp();
+    if (tr_on) trace[63] = tr_n;
     __syncwarp();
     tc_fence_before();
     __syncthreads();

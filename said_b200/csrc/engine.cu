@@ -1799,7 +1799,7 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
             const int ag = hx::attention_h_groups(T, HEADS);
             CK(launch_ex(hx::self_attention_h_kernel, dim3(HEADS / ag, h_nb), dim3(hx::AH_THREADS * ag), hx::attention_h_smem_bytes(T, ag), st, pdl, 1,
                          (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag,
-                         (uint32_t)hx::attention_h_group_bytes(T)));
+                         (uint32_t)hx::attention_h_group_bytes(T), (long long*)nullptr));
         } else if (T <= tc::ATC_MAXKEYS) {
             CK(launch_ex(tc::self_attention_tc_kernel, dim3(HEADS, h_nb), dim3(tc::ATC_THREADS), tc::attention_tc_smem_bytes(T), st, pdl, 1,
                          (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag));
@@ -2341,10 +2341,24 @@ int said_op_self_attention_h(said_engine* e, const float* qkv_dev, int B, int T,
     const int ag = hx::attention_h_groups(T, heads);
     const size_t smem = hx::attention_h_smem_bytes(T, ag);
     CK(cudaFuncSetAttribute(hx::self_attention_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long* tr = nullptr;
+    if (getenv("SAID_ATTN_TRACE")) {
+        CK(cudaMalloc((void**)&tr, 64 * sizeof(long long)));
+        CK(cudaMemset(tr, 0, 64 * sizeof(long long)));
+    }
     hx::self_attention_h_kernel<<<dim3(heads / ag, B), hx::AH_THREADS * ag, smem, st>>>(
-        qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr, (uint32_t)hx::attention_h_group_bytes(T));
+        qkv_dev, 3 * Cw, 0, Cw, 2 * Cw, T, 1.0f / sqrtf(32.0f), out_dev, Cw, T, nullptr, nullptr, (uint32_t)hx::attention_h_group_bytes(T), tr);
     ++e->launches;
     CK(cudaGetLastError());
+    if (tr) {   // diagnostics: phase time line of CTA (0, 0), group 0, thread 0 (cycles since kernel entry)
+        long long h[64];
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(h, tr, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(tr);
+        fprintf(stderr, "[said] attention_h trace T=%d B=%d groups=%d:", T, B, ag);
+        for (int i = 1; i < (int)h[63] && i < 62; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+        fprintf(stderr, "\n");
+    }
     return 0;
 }
 

@@ -265,18 +265,18 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                 if (a_first) sa0 = sa;
                 const uint32_t idesc = make_idesc_f16(HBM, it_.nw);
                 const uint32_t boff = (uint32_t)it_.n0 * HROW;               // n0 is a multiple of 16 rows: whole swizzle atoms
-                tc::mbar_wait_tight(acce_bar(buf), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_wait(acce_bar(buf), ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::ACC_STRIDE);
                 for (int kc = 0; kc < nk; ++kc) {
                     int sa_use = sa;
                     if (a_first) {
-                        tc::mbar_wait_tight(fulla_bar(sa), pa);
+                        mbar_wait(fulla_bar(sa), pa);
                     } else {
                         sa_use = sa0 + kc;
                         if (sa_use >= AS) sa_use -= AS;
                     }
-                    tc::mbar_wait_tight(fullb_bar(sb), pb);
+                    mbar_wait(fullb_bar(sb), pb);
                     tc_fence_after();
                     const uint64_t dah = make_desc(a_st(sa_use)), dal = make_desc(a_st(sa_use) + A_PLANE);
                     const uint64_t dbh = make_desc(b_st(sb) + boff), dbl = make_desc(b_st(sb) + Cfg::B_PLANE + boff);
@@ -308,7 +308,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                     const HSeg sg = p.seg[s];
                     const CUtensorMap* map = &p.maps[sg.map];
                     for (int j = 0; j < sg.nchunks; ++j) {
-                        tc::mbar_wait_tight(emptya_bar(sa), pa ^ 1u);
+                        mbar_wait(emptya_bar(sa), pa ^ 1u);
                         if (p.dbg & 1) {
                             mbar_arrive(fulla_bar(sa));
                         } else {
@@ -332,7 +332,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                 const Item it_ = item(i);
                 const uint8_t* wsrc = Wimg + ((size_t)it_.nt * p.w_nk_total + p.w_kc0) * p.w_block_bytes;
                 for (int kc = 0; kc < nk; ++kc) {
-                    tc::mbar_wait_tight(emptyb_bar(sb), pb ^ 1u);
+                    mbar_wait(emptyb_bar(sb), pb ^ 1u);
                     const uint8_t* blk = wsrc + (size_t)kc * p.w_block_bytes;
                     if (p.dbg & 2) {
                         mbar_arrive(fullb_bar(sb));
