@@ -437,7 +437,8 @@ class Engine:
             self._call(self.lib.said_op_gemm_h(self._h, a.data_ptr(), M, Cin, taps, w.ctypes.data, N, _ptr(b), out.data_ptr(), self._stream()))
         return out
 
-    def op_gemm_h_bench(self, M: int, Cin: int, taps: int = 1, N: int = 192, with_residual: bool = True, dbg: int = 0, iters: int = 10) -> float:
+    def op_gemm_h_bench(self, M: int, Cin: int, taps: int = 1, N: int = 192, with_residual: int = 1, dbg: int = 0, iters: int = 10) -> float:
+        """with_residual: 0 plain store, 1 residual add, 2 the GEGLU epilogue with pair output"""
         ms = ctypes.c_float()
         with torch.cuda.device(self.device):
             self._call(self.lib.said_op_gemm_h_bench(self._h, M, Cin, taps, N, int(with_residual), dbg, iters, ctypes.byref(ms)))

@@ -2149,14 +2149,22 @@ int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int N, int wi
     e->hmap[key] = said_engine::HW{wd, K, N, 192, 0};
     const said_engine::HSrc src{reinterpret_cast<const __half*>(a.p), Cin, M};
     EpiStd ep = mk_epi(o.p, N, N);
-    if (with_residual) { ep.res = r.p; ep.ldr = N; }
+    if (with_residual == 1) { ep.res = r.p; ep.ldr = N; }
+    static DevBuf gb;
+    CK(gb.ensure_zero((size_t)N));
+    if (!e->status_flag) {
+        CK(cudaMalloc((void**)&e->status_flag, sizeof(int)));
+        CK(cudaMemset(e->status_flag, 0, sizeof(int)));
+    }
+    const EpiGegluPair eg{reinterpret_cast<__half*>(o.p), N / 2, N, gb.p, 1.0f, e->status_flag};   // with_residual == 2: the GEGLU epilogue (pair output)
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     int rc = 0;
     for (int it = -2; it < iters && rc == 0; ++it) {
         if (it == 0) CK(cudaEventRecord(e0, 0));
-        if (taps == 1) rc = e->gemm_h((cudaStream_t)0, M, N, {{src, 0, Cin, 0}}, key, ep, said_engine::TAG_GEMM_PLAIN, dbg);
+        if (with_residual == 2) rc = e->gemm_h((cudaStream_t)0, M, N, {{src, 0, Cin, 0}}, key, eg, said_engine::TAG_GEMM_PLAIN, dbg);
+        else if (taps == 1) rc = e->gemm_h((cudaStream_t)0, M, N, {{src, 0, Cin, 0}}, key, ep, said_engine::TAG_GEMM_PLAIN, dbg);
         else rc = e->gemm_h((cudaStream_t)0, M, N, {{src, 0, Cin, -1}, {src, 0, Cin, 0}, {src, 0, Cin, 1}}, key, ep, said_engine::TAG_GEMM_CONV, dbg);
     }
     cudaError_t se = cudaEventRecord(e1, 0);

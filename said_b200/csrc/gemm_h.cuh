@@ -220,6 +220,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
             for (int jj = 0; jj < MYCH; ++jj) {
                 const int j = H_EPI_PARTS * jj + half;
                 if (j < nch_i) {                           // warp-uniform
+                    const typename EP::ColCtx cc = ep.tc_col(ncol0 + j * 16 + lq * 4);   // bias: in flight while the accumulator is read
                     float v[16];
                     tmem_ld16(taddr + j * 16, v);
 #pragma unroll
@@ -237,7 +238,7 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                         float4 acc;
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "r"(a));
                         const int m = mrow0 + 8 * ii;
-                        if (m < p.M && !(p.dbg & 4)) ep.store4(rc[ii], m, n, acc, pf[jj % EPI_PF][ii]);
+                        if (m < p.M && !(p.dbg & 4)) ep.store4(rc[ii], cc, m, n, acc, pf[jj % EPI_PF][ii]);
                     }
                     __syncwarp();
                     const int jn = j + H_EPI_PARTS * EPI_PF;

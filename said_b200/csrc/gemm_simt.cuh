@@ -393,7 +393,12 @@ struct EpiStd {
         return c;
     }
     SAID_DEVINL float4 tc_prefetch4(const RowCtx& c, int n) const { return ldg4_l2pf(c.res + (n < N ? n : 0)); }
-    SAID_DEVINL void store4(const RowCtx& c, int m, int n, float4 a, float4 r) const {
+    // everything that depends only on the COLUMN (the bias), loaded once per 16-column chunk before the accumulator is waited for:
+    // a load inside store4 sits behind the shared-memory transpose and its latency is exposed four times per chunk
+    struct ColCtx { float4 bias; };
+    SAID_DEVINL ColCtx tc_col(int n) const { return ColCtx{bias ? ldg4(bias + (n < N ? n : 0)) : zero4()}; }
+    SAID_DEVINL void store4(const RowCtx& c, int m, int n, float4 a, float4 r) const { store4(c, tc_col(n), m, n, a, r); }
+    SAID_DEVINL void store4(const RowCtx& c, const ColCtx& cc, int m, int n, float4 a, float4 r) const {
         if (n >= N) return;
         if (acc_scale != 1.0f) { a.x *= acc_scale; a.y *= acc_scale; a.z *= acc_scale; a.w *= acc_scale; }
         if (acc_in != nullptr) {
@@ -405,10 +410,7 @@ struct EpiStd {
             if (t >= out_valid) return;
             m = b * out_valid + t;
         }
-        if (bias) {
-            const float4 bq = ldg4(bias + n);
-            a.x += bq.x; a.y += bq.y; a.z += bq.z; a.w += bq.w;
-        }
+        a.x += cc.bias.x; a.y += cc.bias.y; a.z += cc.bias.z; a.w += cc.bias.w;
         if (act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
         if (emb) {
             const float4 q = ldg4(c.emb_row + n);
@@ -504,6 +506,9 @@ struct EpiGeglu {
     SAID_DEVINL bool tc_has_res() const { return false; }
     SAID_DEVINL RowCtx tc_row(int, int) const { return RowCtx{}; }
     SAID_DEVINL float4 tc_prefetch4(const RowCtx&, int) const { return zero4(); }
+    struct ColCtx { float4 bias; };
+    SAID_DEVINL ColCtx tc_col(int n) const { return ColCtx{ldg4(bias + (n < N ? n : 0))}; }
+    SAID_DEVINL void store4(const RowCtx& c, const ColCtx&, int m, int n, float4 a, float4 r) const { store4(c, m, n, a, r); }
     SAID_DEVINL void store4(const RowCtx&, int m, int n, float4 a, float4) const {
         if (n >= N) return;
         const float4 bq = ldg4(bias + n);
@@ -542,9 +547,11 @@ struct EpiGegluPair {
     SAID_DEVINL bool tc_has_res() const { return false; }
     SAID_DEVINL RowCtx tc_row(int, int) const { return RowCtx{}; }
     SAID_DEVINL float4 tc_prefetch4(const RowCtx&, int) const { return zero4(); }
-    SAID_DEVINL void store4(const RowCtx&, int m, int n, float4 a, float4) const {
+    struct ColCtx { float4 bias; };
+    SAID_DEVINL ColCtx tc_col(int n) const { return ColCtx{ldg4(bias + (n < N ? n : 0))}; }
+    SAID_DEVINL void store4(const RowCtx&, const ColCtx& cc, int m, int n, float4 a, float4) const {
         if (n >= N) return;
-        const float4 bq = ldg4(bias + n);
+        const float4 bq = cc.bias;
         const float o0 = (a.x * acc_scale + bq.x) * gelu_erf_fast(a.y * acc_scale + bq.y);
         const float o1 = (a.z * acc_scale + bq.z) * gelu_erf_fast(a.w * acc_scale + bq.w);
         const __half2 h = __floats2half2_rn(o0, o1);
