@@ -28,6 +28,7 @@
 #include "eval_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_h.cuh"
+#include "ffn_h.cuh"
 #include "gemm_tc.cuh"
 #include "norm_kernels.cuh"
 #include "pair_kernels.cuh"
@@ -151,16 +152,60 @@ struct said_engine {
         float* d = nullptr;
         CKI(upload(img, &d));
         tcmap[key] = TcW{d, K, N, bn};
-        if (reg_h && K % hx::HBK == 0) {
-            std::vector<uint16_t> himg;
-            const int e = hx::pack_weights_h(host_wt, K, N, ldw, bn, himg);
-            uint8_t* hd = nullptr;
-            CK(cudaMalloc((void**)&hd, himg.size() * sizeof(uint16_t)));
-            arena.push_back(reinterpret_cast<float*>(hd));
-            CK(cudaMemcpy(hd, himg.data(), himg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-            hmap[key] = HW{hd, K, N, bn, e};
-        }
+        if (reg_h && K % hx::HBK == 0) CKI(register_h(key, host_wt, K, N, ldw, bn));
         return 0;
+    }
+    int register_h(const float* key, const float* host_wt, int K, int N, int ldw, int bn) {
+        std::vector<uint16_t> himg;
+        const int e = hx::pack_weights_h(host_wt, K, N, ldw, bn, himg);
+        uint8_t* hd = nullptr;
+        CK(cudaMalloc((void**)&hd, himg.size() * sizeof(uint16_t)));
+        arena.push_back(reinterpret_cast<float*>(hd));
+        CK(cudaMemcpy(hd, himg.data(), himg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        hmap[key] = HW{hd, K, N, bn, e};
+        return 0;
+    }
+    // The fused feed-forward (ffn_h.cuh): out = [geglu(ln W1 + b1) | x2] Wffp + bias + residual of `ep`.  W1's image for this
+    // kernel has 256-column n-tiles and is registered under the GEGLU bias pointer.
+    // workspace of the fused feed-forward's split leftover tiles (ffn_h.cuh): partial accumulators + counters
+    DevBuf ffn_part, ffn_sync;
+    bool ffn_split = getenv("SAID_FFN_NOSPLIT") == nullptr;
+    int ensure_ffn_split(size_t M) {
+        const int tiles = (int)((M + hx::HBM - 1) / hx::HBM), grid = tiles < num_sms ? tiles : num_sms;
+        const int left = tiles - (tiles / grid) * grid;
+        CK(ffn_sync.ensure_zero(64));
+        if (left > 0) CK(ffn_part.ensure((size_t)left * hx::FFN_NP * hx::HBM * hx::FFN_C));
+        return 0;
+    }
+    template <class EP>
+    int ffn_h(cudaStream_t st, int M, const __half* pln, const __half* px2, const float* w1key, const float* bias1, const float* wffp,
+              EP ep, int tag, int dbg = 0, long long* trace = nullptr) {
+        auto i1 = hmap.find(w1key), i2 = hmap.find(wffp);
+        if (i1 == hmap.end() || i2 == hmap.end()) return fail("fused feed-forward: weight images not registered");
+        const HW &w1 = i1->second, &w2 = i2->second;
+        if (w1.K != hx::FFN_C || w1.N != 2 * hx::FFN_NJ * hx::FFN_JC || w1.bn != 256 || w2.K != hx::FFN_NJ * hx::FFN_JC + hx::FFN_C ||
+            w2.N != hx::FFN_C || w2.bn != 192)
+            return fail("fused feed-forward: unexpected weight geometry");
+        hx::FfnParams p;
+        memset(&p, 0, sizeof(p));
+        if (!hx::make_pair_map(&p.map_ln, pln, hx::FFN_C, M) || !hx::make_pair_map(&p.map_x2, px2, hx::FFN_C, M))
+            return fail("cuTensorMapEncodeTiled failed (driver entry point unavailable or bad tensor geometry)");
+        p.M = M;
+        p.scale1 = std::ldexp(1.0f, -w1.exp);
+        p.dbg = trace ? dbg : (dbg & ~16);
+        p.trace = trace;
+        {
+            const int tiles = (M + hx::HBM - 1) / hx::HBM, grid = tiles < num_sms ? tiles : num_sms;
+            const size_t need = (size_t)(tiles - (tiles / grid) * grid) * hx::FFN_NP * hx::HBM * hx::FFN_C;
+            p.split = (ffn_split && ffn_sync.p != nullptr && ffn_part.cap >= need && need > 0) ? 1 : 0;
+            p.part = ffn_part.p;
+            p.sync = reinterpret_cast<int*>(ffn_sync.p);
+        }
+        ep.acc_scale = std::ldexp(1.0f, -w2.exp);
+        cur_tag = tag;
+        cudaError_t e = hx::launch_ffn_h(st, num_sms, p, w1.img, w2.img, bias1, status_flag, ep, pdl);
+        if (e != cudaSuccess) return fail(std::string("fused feed-forward launch failed: ") + cudaGetErrorString(e));
+        return after_launch(st);
     }
     // One contraction on the fp16x3 path.  The K dimension is the concatenation of `segs`: columns [col0, col0 + ncols) of
     // the pair tensor `src` (C columns, `rows` rows), rows shifted by row_shift (Conv1d taps).  Weight = the image of `wkey`.
@@ -430,6 +475,7 @@ struct said_engine {
     int forward_h(cudaStream_t st, const float* x, int src_batch, int Bp, int n_uncond, int T, const float* emb_table,
                   const int* step_ptr, float* eps_out, float* taps);
     bool enc_split_k = getenv("SAID_ENC_NO_SPLITK") == nullptr;   // fp16x3 encoder: contractions longer than 768 run as split-K launches (accuracy)
+    bool fused_ffn = getenv("SAID_NO_FUSED_FFN") == nullptr;   // fp16x3 path: GEGLU + ff2 + proj_out as one kernel (ffn_h.cuh); the env switch keeps the two-GEMM form for A/B runs
     bool attn_h = getenv("SAID_ATTN_TF32") == nullptr;   // fp16x3 path: flash-style fp16 hi/lo attention (attention_h.cuh); the env switch keeps the 3xTF32 kernel reachable for A/B runs
     bool use_h(int M) const { return precision == 3 && M >= tc_min_rows && in_ch == 32; }
     int denoise(const said_denoise_args& a, cudaStream_t user);
@@ -580,6 +626,7 @@ int said_engine::commit_denoiser() {
         CKI(need(b + "ff.net.0.proj.bias", {2 * FF}, &t));
         for (int o = 0; o < 2 * FF; ++o) bff1[o < FF ? 2 * o : 2 * (o - FF) + 1] = t->data[o];
         CKI(upload(bff1, &s.bff1));
+        if (reg_h && C == hx::FFN_C && FF == hx::FFN_NJ * hx::FFN_JC) CKI(register_h(s.bff1, wff1.data(), C, 2 * FF, 2 * FF, 256));
         CKI(need(b + "ff.net.2.weight", {C, FF}, &t));
         std::vector<float> wff2((size_t)FF * C);
         pack_w(*t, C, FF, 1, wff2, C, 0, 0);
@@ -1433,6 +1480,7 @@ int said_engine::ensure_denoiser_ws(int Bp, int T) {
         CK(p_raw.ensure_zero(M * 2 * C));
         CK(p_ln.ensure_zero(M * C));
         CK(p_x2.ensure_zero(M * C));
+        CKI(ensure_ffn_split(M));
     }
     if (!status_flag) {
         CK(cudaMalloc((void**)&status_flag, sizeof(int)));
@@ -1843,6 +1891,15 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
             CKI(gemm_h(st, Mcp, C, {{psrc(pao + r0 * 2 * C, C, Mcp), 0, C, 0}}, W.wo2, ep, TAG_GEMM_PLAIN));
         }
         CKI(ln_pair(x2, Mp, nullptr, nullptr, W.ln3_g, W.ln3_b, pln, px2));
+        if (fused_ffn) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
+            EpiStd ep = mk_epi(out, C, C);
+            ep.bias = W.bffp;
+            ep.res = h;
+            ep.ldr = C;
+            ep.res_mod = mh;
+            CKI(ffn_h(st, Mp, pln, px2, W.bff1, W.bff1, W.wffp, ep, TAG_GEMM_PLAIN));
+            return 0;
+        }
         {   // GEGLU
             EpiGegluPair ep{pff, FF, 2 * FF, W.bff1, 1.0f, status_flag};
             CKI(gemm_h(st, Mp, 2 * FF, {{psrc(pln, C, Mp), 0, C, 0}}, W.wff1, ep, TAG_GEMM_PLAIN));
@@ -2137,6 +2194,69 @@ int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int N, int wi
     if (!(taps == 1 || taps == 3) || Cin % hx::HBK != 0 || N % 192 != 0) return fail("said_op_gemm_h_bench: unsupported shape");
     CK(cudaSetDevice(e->device));
     static DevBuf a, o, r;
+    if (with_residual == 3) {   // the fused feed-forward (M rows; Cin, taps, N ignored) on zero operands
+        constexpr int C = hx::FFN_C, FF = hx::FFN_NJ * hx::FFN_JC;
+        CK(a.ensure_zero((size_t)M * C * 2));     // two pair tensors (ln, x2) of 2 * C halves per row
+        CK(o.ensure_zero((size_t)M * C));
+        CK(r.ensure_zero((size_t)M * C));
+        static DevBuf b1;
+        CK(b1.ensure_zero((size_t)2 * FF));
+        const size_t w1b = (size_t)hx::FFN_NP * 6 * hx::FFN_W1_PLANE, w2b = (size_t)(hx::FFN_NJ + 3) * 2 * hx::FFN_W2_PLANE;
+        uint8_t* wd = nullptr;
+        CK(cudaMalloc((void**)&wd, w1b + w2b));
+        CK(cudaMemset(wd, 0, w1b + w2b));
+        const float *k1 = reinterpret_cast<const float*>(wd), *k2 = reinterpret_cast<const float*>(wd + w1b);
+        e->hmap[k1] = said_engine::HW{wd, C, 2 * FF, 256, 0};
+        e->hmap[k2] = said_engine::HW{wd + w1b, FF + C, C, 192, 0};
+        if (!e->status_flag) {
+            CK(cudaMalloc((void**)&e->status_flag, sizeof(int)));
+            CK(cudaMemset(e->status_flag, 0, sizeof(int)));
+        }
+        EpiStd ep = mk_epi(o.p, C, C);
+        ep.res = r.p;
+        ep.ldr = C;
+        CKI(e->ensure_ffn_split((size_t)M));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        int rc = 0;
+        const __half* pa = reinterpret_cast<const __half*>(a.p);
+        long long* trace_dev = nullptr;
+        if (dbg & 16) {
+            CK(cudaMalloc((void**)&trace_dev, 256 * sizeof(long long)));
+            CK(cudaMemset(trace_dev, 0, 256 * sizeof(long long)));
+        }
+        for (int it = -2; it < iters && rc == 0; ++it) {
+            if (it == 0) CK(cudaEventRecord(e0, 0));
+            rc = e->ffn_h((cudaStream_t)0, M, pa, pa + (size_t)M * 2 * C, k1, b1.p, k2, ep, said_engine::TAG_GEMM_PLAIN, dbg, trace_dev);
+        }
+        if (trace_dev) {
+            long long h[256];
+            cudaDeviceSynchronize();
+            cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaFree(trace_dev);
+            const long long t0 = h[60];
+            fprintf(stderr, "[ffn trace] tile start 0, g4(0) issued %lld, tile issued %lld; epilogue: wait %lld, acc5 ready %lld, done %lld\n", h[61] - t0,
+                    h[62] - t0, h[130] - t0, h[131] - t0, h[132] - t0);
+            for (int j = 0; j < hx::FFN_NJ; ++j)
+                fprintf(stderr, "[ffn trace] j=%2d  mma: g4(j+1) issued %6lld, ff_full %6lld, g5 issued %6lld | geglu: acc4_full %6lld, loaded %6lld, math done %6lld, ff_empty %6lld, arrived %6lld\n",
+                        j, h[j * 4] - t0, h[j * 4 + 1] - t0, h[j * 4 + 2] - t0, h[64 + j * 5] - t0, h[64 + j * 5 + 1] - t0, h[64 + j * 5 + 2] - t0,
+                        h[64 + j * 5 + 3] - t0, h[64 + j * 5 + 4] - t0);
+        }
+        cudaError_t se = cudaEventRecord(e1, 0);
+        if (se == cudaSuccess) se = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (se == cudaSuccess) se = cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        e->hmap.erase(k1);
+        e->hmap.erase(k2);
+        cudaFree(wd);
+        if (rc != 0) return rc;
+        CK(se);
+        *ms_out = ms / iters;
+        return 0;
+    }
     CK(a.ensure_zero((size_t)M * Cin));
     CK(o.ensure_zero((size_t)M * N));
     CK(r.ensure_zero((size_t)M * N));

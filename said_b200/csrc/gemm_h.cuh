@@ -29,6 +29,7 @@
 namespace said {
 namespace hx {
 
+using tc::elect_one;
 using tc::fence_mbar_init;
 using tc::make_desc;
 using tc::mbar_arrive;

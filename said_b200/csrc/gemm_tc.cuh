@@ -133,6 +133,16 @@ SAID_DEVINL void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uin
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one lane of a converged warp (the issuing lane of tcgen05.mma / commit in warp-uniform code)
+SAID_DEVINL bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 SAID_DEVINL void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
