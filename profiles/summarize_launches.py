@@ -21,22 +21,41 @@ def main():
     rows = []
     with open(path) as f:
         lines = [ln for ln in f if not ln.startswith("==")]
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0}
+    by_id = OrderedDict()
     for r in csv.DictReader(lines):
-        if r.get("Metric Name") == "gpu__time_duration.sum":
-            rows.append((short(r["Kernel Name"]), float(r["Metric Value"]) / 1e6))
-    split = max((i for i, (k, _) in enumerate(rows) if "prepare_latents_kernel" in k), default=-1)
+        m = r.get("Metric Name")
+        if m in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"):
+            e = by_id.setdefault(r["ID"], [short(r["Kernel Name"]), 0.0, 0.0, False])
+            v = float(r["Metric Value"].replace(",", "")) * unit.get(r.get("Metric Unit", "ns"), 1e-6 if m.startswith("gpu") else 1.0)
+            if m.startswith("gpu"):
+                e[1] = v
+            else:
+                e[2] += v
+                e[3] = True
+    rows = [(e[0], e[1], e[2]) for e in by_id.values()]
+    have_dram = any(e[3] for e in by_id.values())
+    split = max((i for i, (k, _, _) in enumerate(rows) if "prepare_latents_kernel" in k), default=-1)
     pre, loop = rows[: split + 1], rows[split + 1:]
     print(f"# {title}\n\nCommand: `{cmd}`\n(cold-cache, serialised launches: compare shares, not absolutes.)\n")
     for head, part in (("Loop iterations", loop), ("Once per batch: audio encoder + K/V hoist + tables", pre)):
         agg = OrderedDict()
-        for k, ms in part:
-            a = agg.setdefault(k, [0.0, 0])
+        for k, ms, by in part:
+            a = agg.setdefault(k, [0.0, 0, 0.0])
             a[0] += ms
             a[1] += 1
+            a[2] += by
         tot = sum(v[0] for v in agg.values())
-        print(f"## {head}\n\n{len(part)} launches, {tot:.2f} ms.\n\n| ms | share | launches | us / launch | kernel |\n|---:|---:|---:|---:|---|")
-        for k, (ms, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-            print(f"| {ms:.3f} | {100 * ms / tot:.1f}% | {n} | {1000 * ms / n:.1f} | `{k}` |")
+        totb = sum(v[2] for v in agg.values())
+        extra = f", {totb / 1e6:.0f} MB of DRAM traffic (read + write)" if have_dram else ""
+        print(f"## {head}\n\n{len(part)} launches, {tot:.2f} ms{extra}.\n")
+        if have_dram:
+            print("| ms | share | launches | us / launch | DRAM MB / launch | kernel |\n|---:|---:|---:|---:|---:|---|")
+        else:
+            print("| ms | share | launches | us / launch | kernel |\n|---:|---:|---:|---:|---|")
+        for k, (ms, n, by) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            mid = f" {by / n / 1e6:.1f} |" if have_dram else ""
+            print(f"| {ms:.3f} | {100 * ms / tot:.1f}% | {n} | {1000 * ms / n:.1f} |{mid} `{k}` |")
         print()
 
 

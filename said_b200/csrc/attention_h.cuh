@@ -102,8 +102,9 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
     const int Tkp = (T + 15) / 16 * 16;
     const int nch = (T + 63) / 64;                    // 64-key chunks of V^T
     const int nkb = (T + AH_KB - 1) / AH_KB;          // 128-key blocks
-    const int grp = threadIdx.x >> 8, groups = blockDim.x >> 8;
-    const int tid = threadIdx.x & 255, warp = tid >> 5, lane = tid & 31;     // (within the group)
+    const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);    // provably warp-uniform (the MMA-issuing warp keeps its
+    const int grp = wg >> 3, groups = blockDim.x >> 8;                      //  descriptors in uniform registers)
+    const int tid = threadIdx.x & 255, warp = wg & 7;                        // (within the group)
     const uint32_t base0 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t base = base0 + (uint32_t)grp * group_bytes;
     const uint32_t k_sm = base;                                            // [Tkp rows][hi 64 B | lo 64 B]
@@ -132,13 +133,14 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t tmem_cta = tmem_base;
     tmem_base += (uint32_t)grp * 256u;                                     // this group's columns
     pdl_wait();
     pdl_trigger();
     const int n_qtiles = (T + 127) / 128;
 
-    // ---------------- MMA issue (thread 0 only, between its softmax duties) ----------------
+    // ---------------- MMA issue (warp 0 of the group between its softmax duties: all lanes run the bookkeeping, one elected lane issues) ----------------
     const uint64_t dq = make_desc(q_sm);
     const uint32_t id64 = make_idesc_f16(128, 64), id32 = make_idesc_f16(128, 32);
     auto issue_s = [&](int kb) {     // S = Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T: hi / lo are the 32-byte K-slices 0,1 / 2,3 of the same 128-byte rows
@@ -250,11 +252,11 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
             tc_fence_before();                                 // (TMEM reads of the previous tile's O are complete)
             tc::fence_proxy_async();
             mbar_arrive(bar_q);
-            if (tid == 0) {
+            if (warp == 0) {
                 tc::mbar_wait_tight(bar_q, n_q & 1u);
                 ++n_q;
                 tc_fence_after();
-                issue_s(0);
+                if (tc::elect_one()) issue_s(0);
             }
             __syncwarp();
             float m_run = -INFINITY, l_part = 0.f;
@@ -337,13 +339,15 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 tc_fence_before();
                 mbar_arrive(bar_p);
                 stamp();                                                // softmax of this thread done
-                if (tid == 0) {
+                if (warp == 0) {
                     tc::mbar_wait_tight(bar_p, n_p & 1u);
                     ++n_p;
                     tc_fence_after();
-                    issue_pv(kb);
-                    if (kb == nkb - 1) mma_commit(bar_o);
-                    else issue_s(kb + 1);                      // executes after the P V MMAs above (tcgen05.mma runs in issue order)
+                    if (tc::elect_one()) {
+                        issue_pv(kb);
+                        if (kb == nkb - 1) mma_commit(bar_o);
+                        else issue_s(kb + 1);                  // executes after the P V MMAs above (tcgen05.mma runs in issue order)
+                    }
                 }
                 __syncwarp();
             }

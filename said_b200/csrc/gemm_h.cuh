@@ -127,7 +127,8 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
     auto a_st = [&](int s) { return smem_base + s * A_STAGE; };
     auto b_st = [&](int s) { return b_base + s * Cfg::B_STAGE; };
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // provably warp-uniform: role branches do not diverge
     const int nk = p.nk;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int total_tiles = ((p.M + HBM - 1) / HBM) * n_tiles;
@@ -254,7 +255,11 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
         }
     } else if (warp == H_EPI_WARPS) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp runs the loop (state and descriptors stay in uniform registers); one elected lane issues.  From a
+        // single-lane branch every tcgen05.mma cost a divergence loop plus register -> uniform-register moves, which at N <= 192
+        // (96 tensor cycles per MMA) made the issue stream the limiter (profiles/r2_mma_rate.md).
+        {
+            const bool do_mma = !(p.dbg & 8);
             int sa = 0, sb = 0, sa0 = 0;
             uint32_t pa = 0, pb = 0;
             for (int i = 0; i < my_tiles; ++i) {
@@ -282,19 +287,24 @@ gemm_h_kernel(const __grid_constant__ HParams p, const uint8_t* __restrict__ Wim
                     tc_fence_after();
                     const uint64_t dah = make_desc(a_st(sa_use)), dal = make_desc(a_st(sa_use) + A_PLANE);
                     const uint64_t dbh = make_desc(b_st(sb) + boff), dbl = make_desc(b_st(sb) + Cfg::B_PLANE + boff);
+                    if (elect_one()) {
+                        if (do_mma) {
 #pragma unroll
-                    for (int k4 = 0; k4 < ((p.dbg & 8) ? 0 : HBK / 16); ++k4) {
-                        const uint64_t adv = (uint64_t)(k4 * 2);   // 16 fp16 = 32 bytes = 2 x 16-byte units along K
-                        mma_f16(tacc, dah + adv, dbh + adv, idesc, (kc | k4) != 0 ? 1u : 0u);
-                        mma_f16(tacc, dal + adv, dbh + adv, idesc, 1u);
-                        mma_f16(tacc, dah + adv, dbl + adv, idesc, 1u);
+                            for (int k4 = 0; k4 < HBK / 16; ++k4) {
+                                const uint64_t adv = (uint64_t)(k4 * 2);   // 16 fp16 = 32 bytes = 2 x 16-byte units along K
+                                mma_f16(tacc, dah + adv, dbh + adv, idesc, (kc | k4) != 0 ? 1u : 0u);
+                                mma_f16(tacc, dal + adv, dbh + adv, idesc, 1u);
+                                mma_f16(tacc, dah + adv, dbl + adv, idesc, 1u);
+                            }
+                        }
+                        if (a_last) mma_commit(emptya_bar(sa_use));      // the stage is free once the LAST n-tile's MMAs have read it
+                        mma_commit(emptyb_bar(sb));
+                        if (kc == nk - 1) mma_commit(accf_bar(buf));
                     }
-                    if (a_last) mma_commit(emptya_bar(sa_use));      // the stage is free once the LAST n-tile's MMAs have read it
-                    mma_commit(emptyb_bar(sb));
+                    __syncwarp();
                     if (a_first && ++sa == AS) { sa = 0; pa ^= 1u; }
                     if (++sb == BS) { sb = 0; pb ^= 1u; }
                 }
-                mma_commit(accf_bar(buf));
             }
         }
         __syncwarp();

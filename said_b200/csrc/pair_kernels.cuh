@@ -52,14 +52,17 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
         const int t = t0 + ph + PH * i;
         v[i] = t < t1 ? ldg4(xb + (long long)t * C) : zero4();
     }
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+    // per-thread partial sums over its <= 10 frames in fp32 (the kernel is issue-bound and fp64 adds cost two slots each); everything
+    // across threads, CTAs and the variance itself stay in fp64
+    float fs0 = 0.f, fs1 = 0.f, fs2 = 0.f, fs3 = 0.f, fq0 = 0.f, fq1 = 0.f, fq2 = 0.f, fq3 = 0.f;
 #pragma unroll
     for (int i = 0; i < GNF_MAXR; ++i) {
-        s0 += (double)v[i].x; q0 += (double)v[i].x * (double)v[i].x;
-        s1 += (double)v[i].y; q1 += (double)v[i].y * (double)v[i].y;
-        s2 += (double)v[i].z; q2 += (double)v[i].z * (double)v[i].z;
-        s3 += (double)v[i].w; q3 += (double)v[i].w * (double)v[i].w;
+        fs0 += v[i].x; fq0 = fmaf(v[i].x, v[i].x, fq0);
+        fs1 += v[i].y; fq1 = fmaf(v[i].y, v[i].y, fq1);
+        fs2 += v[i].z; fq2 = fmaf(v[i].z, v[i].z, fq2);
+        fs3 += v[i].w; fq3 = fmaf(v[i].w, v[i].w, fq3);
     }
+    const double s0 = fs0, s1 = fs1, s2 = fs2, s3 = fs3, q0 = fq0, q1 = fq1, q2 = fq2, q3 = fq3;
     s_red[ph][0][q * 4 + 0] = s0; s_red[ph][0][q * 4 + 1] = s1; s_red[ph][0][q * 4 + 2] = s2; s_red[ph][0][q * 4 + 3] = s3;
     s_red[ph][1][q * 4 + 0] = q0; s_red[ph][1][q * 4 + 1] = q1; s_red[ph][1][q * 4 + 2] = q2; s_red[ph][1][q * 4 + 3] = q3;
     __syncthreads();
@@ -113,8 +116,8 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
         const int t = t0 + ph + PH * i;
         if (t < t1) {
             if (act_pair != nullptr) {
-                const float4 a = make_float4(silu(v[i].x * sc.x + sh.x), silu(v[i].y * sc.y + sh.y), silu(v[i].z * sc.z + sh.z),
-                                             silu(v[i].w * sc.w + sh.w));
+                const float4 a = make_float4(silu_fast(fmaf(v[i].x, sc.x, sh.x)), silu_fast(fmaf(v[i].y, sc.y, sh.y)),
+                                             silu_fast(fmaf(v[i].z, sc.z, sh.z)), silu_fast(fmaf(v[i].w, sc.w, sh.w)));
                 amax = amax4(amax, a);
                 store_pair4(act_pair, row0 + t, act_C, act_off + q * 4, a);
             }
