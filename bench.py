@@ -377,7 +377,7 @@ def main():
                 tj = json.load(f)
             if tj.get("precision", "tf32x3") == precision:
                 traffic = tj["dram_bytes_per_launch"]
-                traffic_src = f"profiles/{name} (DRAM bytes per launch, ncu --set full capture of the same kernels)"
+                traffic_src = f"profiles/{name} (DRAM bytes per launch, ncu dram__bytes capture of the same kernels, see the file)"
                 break
     roofline = {
         "kernel": f"tcgen05 GEMM family ({precision}): every Linear/Conv1d of the UNet" if precision != "fp32"
