@@ -881,6 +881,7 @@ int said_engine::commit_bcvae() {
     CKI(raw_t("fc_layers.6.weight", {BCV_Z, 128}, &bcv.f3w));      CKI(raw_t("fc_layers.6.bias", {BCV_Z}, &bcv.f3b));
     CKI(raw_t("fc_mu.weight", {BCV_Z, BCV_Z}, &bcv.muw));          CKI(raw_t("fc_mu.bias", {BCV_Z}, &bcv.mub));
     bcv_ready = true;
+    for (auto it = raw.begin(); it != raw.end();) it = it->first.compare(0, 6, "bcvae.") == 0 ? raw.erase(it) : std::next(it);
     return 0;
 }
 
@@ -904,6 +905,7 @@ int said_engine::commit() {
     if (enc_out != ctx_dim)
         return fail("audio feature width " + std::to_string(enc_out) + " != denoiser context dim " + std::to_string(ctx_dim));
     ready = true;
+    raw.clear();    // the host staging copies are consumed: a later load of a shallower model must not see this one's layers
     return 0;
 }
 

@@ -143,8 +143,9 @@ class SAID(ABC, nn.Module):
     ):
         super().__init__()
         # Audio-related
-        self.audio_config = audio_config
         self._audio_dims = Wav2Vec2Dims(audio_config)
+        # the reference stores Wav2Vec2Config() when none is given (diffusion.py:83-86): keep `model.audio_config.hidden_size` etc. readable
+        self.audio_config = audio_config if audio_config is not None else self._audio_dims.as_config()
         self._audio_dims.check_supported()
         self.audio_encoder = ParamTree(audio_encoder_spec(self._audio_dims))
         self.audio_processor = audio_processor if audio_processor is not None else AudioProcessor()

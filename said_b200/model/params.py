@@ -164,6 +164,17 @@ class Wav2Vec2Dims:
         self.output_hidden = int(g("output_hidden_size", self.hidden))
         self.add_adapter = bool(g("add_adapter", False))
 
+    def as_config(self):
+        """A config-like namespace with the transformers ``Wav2Vec2Config`` attribute names of these dimensions."""
+        import types
+
+        return types.SimpleNamespace(
+            hidden_size=self.hidden, num_hidden_layers=self.layers, num_attention_heads=self.heads, intermediate_size=self.ffn,
+            conv_dim=self.conv_dim, conv_kernel=self.conv_kernel, conv_stride=self.conv_stride, conv_bias=self.conv_bias,
+            feat_extract_norm=self.feat_extract_norm, num_conv_pos_embeddings=self.pos_kernel,
+            num_conv_pos_embedding_groups=self.pos_groups, do_stable_layer_norm=self.stable_layer_norm,
+            layer_norm_eps=self.layer_norm_eps, output_hidden_size=self.output_hidden, add_adapter=self.add_adapter)
+
     def check_supported(self) -> None:
         """Fail loudly on configurations the sm_100a kernels do not implement."""
         bad = []
@@ -173,6 +184,8 @@ class Wav2Vec2Dims:
             bad.append("feat_extract_norm='layer' without conv_bias=True (or the reverse)")
         if self.add_adapter:
             bad.append("add_adapter=True")
+        if abs(self.layer_norm_eps - 1e-5) > 1e-12:
+            bad.append(f"layer_norm_eps={self.layer_norm_eps} (the encoder kernels use 1e-5)")
         if len(set(self.conv_dim)) != 1:
             bad.append("non-uniform conv_dim")
         if self.hidden % self.heads or self.hidden // self.heads != 64:

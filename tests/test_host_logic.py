@@ -306,3 +306,37 @@ def test_gemm_tile_and_sliver_decomposition_covers_output_once(M, N):
     assert len(seen) == rows * cols * 12
     total = rows * cols
     assert max(len(i) for i in per_cta) <= -(-total // min(G, total))
+
+
+def test_compat_diffusers_defers_to_an_installed_package(tmp_path):
+    """compat/ first on the path must not shadow a real `diffusers` further down: the stand-in hands the import over."""
+    import subprocess
+
+    fake = tmp_path / "site" / "diffusers"
+    fake.mkdir(parents=True)
+    (fake / "__init__.py").write_text("MARK = 'real'\nclass DDIMScheduler:\n    origin = 'real'\n")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from diffusers import DDIMScheduler; import diffusers\n"
+            "print(DDIMScheduler.origin, diffusers.MARK)") % (ROOT, str(tmp_path / "site"), os.path.join(ROOT, "compat"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["real", "real"]
+    # without another diffusers on the path the restated scheduler is exported
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from diffusers import DDIMScheduler; print(DDIMScheduler.__module__)") % (ROOT, os.path.join(ROOT, "compat"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "said_b200.scheduler"
+
+
+def test_audio_config_defaults_and_eps_check():
+    from said_b200.model.params import Wav2Vec2Dims
+    import types
+
+    d = Wav2Vec2Dims(None)
+    cfg = d.as_config()
+    assert cfg.hidden_size == 768 and cfg.num_hidden_layers == 12 and cfg.conv_kernel[0] == 10
+    d.check_supported()
+    bad = Wav2Vec2Dims(types.SimpleNamespace(layer_norm_eps=1e-6))
+    with pytest.raises(NotImplementedError):
+        bad.check_supported()
