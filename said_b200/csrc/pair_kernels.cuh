@@ -30,7 +30,8 @@ f32_to_pair_kernel(const float* __restrict__ x, long long rows, int C, __half* _
 //   raw_pair        x itself as a pair tensor, same geometry                          (1x1 skip_connection operand; optional)
 // and a zero row at frame T of the pair outputs when Tstr > T.  x is read once.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GNF_THREADS)
+template <int MAXR>   // frames per thread: 10 (clusters of 4 CTAs per sample) or 5 (clusters of 8: half the registers, twice the resident warps)
+__global__ void __launch_bounds__(GNF_THREADS, MAXR <= 5 ? 3 : 2)
 gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, int cpg, float eps, const float* __restrict__ gamma,
                const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int out_ld, int out_off,
                __half* __restrict__ act_pair, __half* __restrict__ raw_pair, int act_C, int act_off, int* __restrict__ flag) {
@@ -46,9 +47,9 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
     const int rows = (T + nsp - 1) / nsp;
     const int t0 = sp * rows, t1 = min(T, t0 + rows);
     const float* xb = x + (long long)(b % src_samples) * Tstr * C + q * 4;
-    float4 v[GNF_MAXR];
+    float4 v[MAXR];
 #pragma unroll
-    for (int i = 0; i < GNF_MAXR; ++i) {
+    for (int i = 0; i < MAXR; ++i) {
         const int t = t0 + ph + PH * i;
         v[i] = t < t1 ? ldg4(xb + (long long)t * C) : zero4();
     }
@@ -56,7 +57,7 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
     // across threads, CTAs and the variance itself stay in fp64
     float fs0 = 0.f, fs1 = 0.f, fs2 = 0.f, fs3 = 0.f, fq0 = 0.f, fq1 = 0.f, fq2 = 0.f, fq3 = 0.f;
 #pragma unroll
-    for (int i = 0; i < GNF_MAXR; ++i) {
+    for (int i = 0; i < MAXR; ++i) {
         fs0 += v[i].x; fq0 = fmaf(v[i].x, v[i].x, fq0);
         fs1 += v[i].y; fq1 = fmaf(v[i].y, v[i].y, fq1);
         fs2 += v[i].z; fq2 = fmaf(v[i].z, v[i].z, fq2);
@@ -112,7 +113,7 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
     const long long row0 = (long long)b * Tstr;
     float amax = 0.f;
 #pragma unroll
-    for (int i = 0; i < GNF_MAXR; ++i) {
+    for (int i = 0; i < MAXR; ++i) {
         const int t = t0 + ph + PH * i;
         if (t < t1) {
             if (act_pair != nullptr) {
