@@ -36,7 +36,9 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
                const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int out_ld, int out_off,
                __half* __restrict__ act_pair, __half* __restrict__ raw_pair, int act_C, int act_off, int* __restrict__ flag) {
     constexpr int C = 192, Q = C / 4, PH = GNF_THREADS / Q;
-    __shared__ double s_red[PH][2][C];
+    static_assert(GNF_THREADS == 2 * C, "one (statistic, channel) per thread in the block reduction");
+    __shared__ float4 s_redf[PH][2][Q];
+    __shared__ double s_ch[2][C];
     __shared__ double s_part[2][32];
     __shared__ float s_mean[32], s_rstd[32];
     cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
@@ -63,21 +65,25 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
         fs2 += v[i].z; fq2 = fmaf(v[i].z, v[i].z, fq2);
         fs3 += v[i].w; fq3 = fmaf(v[i].w, v[i].w, fq3);
     }
-    const double s0 = fs0, s1 = fs1, s2 = fs2, s3 = fs3, q0 = fq0, q1 = fq1, q2 = fq2, q3 = fq3;
-    s_red[ph][0][q * 4 + 0] = s0; s_red[ph][0][q * 4 + 1] = s1; s_red[ph][0][q * 4 + 2] = s2; s_red[ph][0][q * 4 + 3] = s3;
-    s_red[ph][1][q * 4 + 0] = q0; s_red[ph][1][q * 4 + 1] = q1; s_red[ph][1][q * 4 + 2] = q2; s_red[ph][1][q * 4 + 3] = q3;
+    // block reduction, every thread busy and no long serial chain (the CTA's critical path is load -> reduce -> cluster barrier ->
+    // exchange -> cluster barrier -> store, twice per SM at batch 64): phase partials in fp32, one (sum | sum of squares, channel)
+    // per thread summed over the 8 phases in fp64, then one (sum | sum of squares, group) per thread over its <= 12 channels
+    s_redf[ph][0][q] = make_float4(fs0, fs1, fs2, fs3);
+    s_redf[ph][1][q] = make_float4(fq0, fq1, fq2, fq3);
+    __syncthreads();
+    {
+        const int w = threadIdx.x / C, c = threadIdx.x - w * C;      // GNF_THREADS == 2 * C
+        double cs = 0.0;
+#pragma unroll
+        for (int p2 = 0; p2 < PH; ++p2) cs += (double)reinterpret_cast<const float*>(&s_redf[p2][w][0])[c];
+        s_ch[w][c] = cs;
+    }
     __syncthreads();
     const int ng = C / cpg;
     if ((int)threadIdx.x < 2 * ng) {
         const int g = threadIdx.x % ng, w = threadIdx.x / ng;
         double a = 0.0;
-        for (int j = 0; j < cpg; ++j) {
-            const int c = g * cpg + j;
-            double cs = 0.0;
-#pragma unroll
-            for (int p2 = 0; p2 < PH; ++p2) cs += s_red[p2][w][c];
-            a += cs;
-        }
+        for (int j = 0; j < cpg; ++j) a += s_ch[w][g * cpg + j];
         s_part[w][g] = a;
     }
     cluster.sync();
