@@ -50,11 +50,10 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
     const int t0 = sp * rows, t1 = min(T, t0 + rows);
     const float* xb = x + (long long)(b % src_samples) * Tstr * C + q * 4;
     float4 v[MAXR];
+    const int mine = t1 - t0 - ph;                       // frames t0 + ph + PH i with PH i < mine are this thread's
+    const float* xp = xb + (long long)(t0 + ph) * C;
 #pragma unroll
-    for (int i = 0; i < MAXR; ++i) {
-        const int t = t0 + ph + PH * i;
-        v[i] = t < t1 ? ldg4(xb + (long long)t * C) : zero4();
-    }
+    for (int i = 0; i < MAXR; ++i) v[i] = PH * i < mine ? ldg4(xp + i * (PH * C)) : zero4();
     // per-thread partial sums over its <= 10 frames in fp32 (the kernel is issue-bound and fp64 adds cost two slots each); everything
     // across threads, CTAs and the variance itself stay in fp64
     float fs0 = 0.f, fs1 = 0.f, fs2 = 0.f, fs3 = 0.f, fq0 = 0.f, fq1 = 0.f, fq2 = 0.f, fq3 = 0.f;
@@ -118,21 +117,37 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
     if (act_pair == nullptr && raw_pair == nullptr) return;
     const long long row0 = (long long)b * Tstr;
     float amax = 0.f;
+    // output pointers advanced by a precomputed stride (the row * pitch products in 64 bits were a third of the store loop)
+    const long long first = (row0 + t0 + ph) * (2LL * act_C) + act_off + q * 4;
+    const int step = PH * 2 * act_C;                     // halfs between this thread's consecutive frames
+    __half* pa = act_pair != nullptr ? act_pair + first : nullptr;
+    __half* pr = raw_pair != nullptr ? raw_pair + first : nullptr;
+    auto act4 = [&](const float4& x) {
+        return make_float4(silu_fast(fmaf(x.x, sc.x, sh.x)), silu_fast(fmaf(x.y, sc.y, sh.y)), silu_fast(fmaf(x.z, sc.z, sh.z)),
+                           silu_fast(fmaf(x.w, sc.w, sh.w)));
+    };
+    auto put = [&](__half* p, const float4& x) {
+        amax = amax4(amax, x);
+        uint2 hi, lo;
+        split_pair4(x, hi, lo);
+        *reinterpret_cast<uint2*>(p) = hi;
+        *reinterpret_cast<uint2*>(p + act_C) = lo;
+    };
+    if (pa != nullptr && pr != nullptr) {                // (one loop per output combination: no per-frame pointer tests)
 #pragma unroll
-    for (int i = 0; i < MAXR; ++i) {
-        const int t = t0 + ph + PH * i;
-        if (t < t1) {
-            if (act_pair != nullptr) {
-                const float4 a = make_float4(silu_fast(fmaf(v[i].x, sc.x, sh.x)), silu_fast(fmaf(v[i].y, sc.y, sh.y)),
-                                             silu_fast(fmaf(v[i].z, sc.z, sh.z)), silu_fast(fmaf(v[i].w, sc.w, sh.w)));
-                amax = amax4(amax, a);
-                store_pair4(act_pair, row0 + t, act_C, act_off + q * 4, a);
+        for (int i = 0; i < MAXR; ++i)
+            if (PH * i < mine) {
+                put(pa + (long long)i * step, act4(v[i]));
+                put(pr + (long long)i * step, v[i]);
             }
-            if (raw_pair != nullptr) {
-                amax = amax4(amax, v[i]);
-                store_pair4(raw_pair, row0 + t, act_C, act_off + q * 4, v[i]);
-            }
-        }
+    } else if (pa != nullptr) {
+#pragma unroll
+        for (int i = 0; i < MAXR; ++i)
+            if (PH * i < mine) put(pa + (long long)i * step, act4(v[i]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < MAXR; ++i)
+            if (PH * i < mine) put(pr + (long long)i * step, v[i]);
     }
     if (Tstr > T && sp == nsp - 1 && ph == 0) {      // the zero row between clips (Conv1d padding)
         for (int t = T; t < Tstr; ++t) {
