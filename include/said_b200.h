@@ -137,6 +137,15 @@ SAID_API int said_op_self_attention(said_engine* e, const float* qkv_dev, int B,
 SAID_API int said_op_gemm_h(said_engine* e, const float* a_dev, int M, int Cin, int taps, const float* wt_host, int N,
                             const float* bias_dev, float* out_dev, void* stream);
 
+/* Unit entry point of the fused feed-forward kernel (ffn_h.cuh; reference said/model/ldm/attention.py:25-51 FeedForward with GEGLU,
+ * :232-234 proj_out + residual, as folded at load): out (M,192) = [geglu(ln . W1 + b1) | x2] . W2 + b2 + res, where
+ * geglu(v | g) = v * gelu(g).  ln_dev, x2_dev, res_dev (optional) (M,192) fp32 on the device; w1_host (192, 1536) K-major with
+ * value / gate columns interleaved (column 2j = value j, 2j+1 = gate j), b1_dev (1536) interleaved alike; w2_host (960, 192)
+ * K-major (rows 0..767 multiply the GEGLU output, rows 768..959 multiply x2); b2_dev (192) or NULL.  Synchronises. */
+SAID_API int said_op_ffn_h(said_engine* e, const float* ln_dev, const float* x2_dev, const float* res_dev, int M,
+                           const float* w1_host, const float* b1_dev, const float* w2_host, const float* b2_dev, float* out_dev,
+                           void* stream);
+
 /* Diagnostics: average milliseconds of the fp16x3 GEMM (M rows, K = taps * Cin, N a multiple of 192) over `iters` launches on
  * zero-filled scratch operands; dbg bits disable parts of the kernel (1 activation TMA loads, 2 weight copies, 4 epilogue I/O,
  * 8 MMAs) to attribute time.  Synchronises. */

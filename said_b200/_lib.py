@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "said_eval_bcvae_latents",
     "said_eval_frechet",
     "said_op_gemm_h",
+    "said_op_ffn_h",
     "said_op_gemm_h_bench",
     "said_op_ddim_step",
     "said_op_self_attention",
@@ -121,6 +122,7 @@ def load_library() -> ctypes.CDLL:
     lib.said_eval_bcvae_latents.argtypes = [vp, vp, ci, ci, ci, vp, vp]
     lib.said_eval_frechet.argtypes = [vp, vp, ci, vp, ci, ctypes.POINTER(ctypes.c_double), vp]
     lib.said_op_gemm_h.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, vp, vp]
+    lib.said_op_ffn_h.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     lib.said_op_gemm_h_bench.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(cf)]
     lib.said_op_ddim_step.argtypes = [vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, ci, vp]
     lib.said_op_self_attention.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp]
@@ -435,6 +437,24 @@ class Engine:
         out = torch.empty((M, N), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._call(self.lib.said_op_gemm_h(self._h, a.data_ptr(), M, Cin, taps, w.ctypes.data, N, _ptr(b), out.data_ptr(), self._stream()))
+        return out
+
+    def op_ffn_h(self, ln: torch.Tensor, x2: torch.Tensor, res: Optional[torch.Tensor], w1: torch.Tensor, b1: torch.Tensor,
+                 w2: torch.Tensor, b2: Optional[torch.Tensor]) -> torch.Tensor:
+        """fused feed-forward unit op (see said_op_ffn_h): ln, x2, res (M, 192) on the device; w1 (192, 1536) / w2 (960, 192) on the host."""
+        ln = _check_dev(ln, self.device, "ln")
+        x2 = _check_dev(x2, self.device, "x2")
+        r = None if res is None else _check_dev(res, self.device, "res")
+        M = ln.shape[0]
+        w1h = np.ascontiguousarray(w1.detach().to("cpu", torch.float32).numpy())
+        w2h = np.ascontiguousarray(w2.detach().to("cpu", torch.float32).numpy())
+        assert w1h.shape == (192, 1536) and w2h.shape == (960, 192) and tuple(ln.shape) == (M, 192) == tuple(x2.shape)
+        b1d = _check_dev(b1, self.device, "b1")
+        b2d = None if b2 is None else _check_dev(b2, self.device, "b2")
+        out = torch.empty((M, 192), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.said_op_ffn_h(self._h, ln.data_ptr(), x2.data_ptr(), _ptr(r), M, w1h.ctypes.data, b1d.data_ptr(),
+                                              w2h.ctypes.data, _ptr(b2d), out.data_ptr(), self._stream()))
         return out
 
     def op_gemm_h_bench(self, M: int, Cin: int, taps: int = 1, N: int = 192, with_residual: int = 1, dbg: int = 0, iters: int = 10) -> float:

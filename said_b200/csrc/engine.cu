@@ -2198,6 +2198,53 @@ int said_denoiser_forward(said_engine* e, const float* x_dev, const float* times
     return 0;
 }
 
+int said_op_ffn_h(said_engine* e, const float* ln_dev, const float* x2_dev, const float* res_dev, int M, const float* w1_host,
+                  const float* b1_dev, const float* w2_host, const float* b2_dev, float* out_dev, void* stream) {
+    // unit test of the fused feed-forward (ffn_h.cuh): out = [geglu(ln W1 + b1) | x2] W2 + b2 + res, W1 (192, 1536) K-major with
+    // value / gate columns interleaved (the layout commit_denoiser builds), b1 (1536) interleaved alike, W2 (960, 192), all fp32;
+    // ln and x2 are converted to the pair format first
+    if (!e) return fail("null engine");
+    if (M <= 0 || !ln_dev || !x2_dev || !w1_host || !b1_dev || !w2_host || !out_dev) return fail("said_op_ffn_h: bad arguments");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int Cc = hx::FFN_C, FFc = hx::FFN_NJ * hx::FFN_JC;
+    static DevBuf pairs;
+    CK(pairs.ensure((size_t)M * Cc * 2));
+    if (!e->status_flag) {
+        CK(cudaMalloc((void**)&e->status_flag, sizeof(int)));
+        CK(cudaMemset(e->status_flag, 0, sizeof(int)));
+    }
+    CKI(e->ensure_ffn_split((size_t)M));
+    __half* pl = reinterpret_cast<__half*>(pairs.p);
+    __half* px = pl + (size_t)M * 2 * Cc;
+    const long long nq = (long long)M * (Cc / 4);
+    f32_to_pair_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(ln_dev, M, Cc, pl, e->status_flag);
+    f32_to_pair_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(x2_dev, M, Cc, px, e->status_flag);
+    CK(cudaGetLastError());
+    std::vector<uint16_t> i1, i2;
+    const int e1 = hx::pack_weights_h(w1_host, Cc, 2 * FFc, 2 * FFc, 256, i1);
+    const int e2 = hx::pack_weights_h(w2_host, FFc + Cc, Cc, Cc, 192, i2);
+    uint8_t* wd = nullptr;
+    const size_t b1s = i1.size() * sizeof(uint16_t), b2s = i2.size() * sizeof(uint16_t);
+    CK(cudaMalloc((void**)&wd, b1s + b2s));
+    CK(cudaMemcpyAsync(wd, i1.data(), b1s, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(wd + b1s, i2.data(), b2s, cudaMemcpyHostToDevice, st));
+    const float *k1 = reinterpret_cast<const float*>(wd), *k2 = reinterpret_cast<const float*>(wd + b1s);
+    e->hmap[k1] = said_engine::HW{wd, Cc, 2 * FFc, 256, e1};
+    e->hmap[k2] = said_engine::HW{wd + b1s, FFc + Cc, Cc, 192, e2};
+    EpiStd ep = mk_epi(out_dev, Cc, Cc);
+    ep.bias = b2_dev;
+    if (res_dev) { ep.res = res_dev; ep.ldr = Cc; }
+    const int rc = e->ffn_h(st, M, pl, px, k1, b1_dev, k2, ep, said_engine::TAG_GEMM_PLAIN);
+    cudaError_t se = cudaStreamSynchronize(st);
+    e->hmap.erase(k1);
+    e->hmap.erase(k2);
+    cudaFree(wd);
+    if (rc != 0) return rc;
+    CK(se);
+    return 0;
+}
+
 int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int N, int with_residual, int dbg, int iters, float* ms_out) {
     // diagnostics: average milliseconds of the fp16x3 GEMM on scratch (zero) operands, with parts of it disabled by dbg
     if (!e || !ms_out) return fail("said_op_gemm_h_bench: bad arguments");

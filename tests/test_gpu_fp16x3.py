@@ -257,3 +257,34 @@ def test_large_family_encoder_fp16x3(golden_dir, large_family):
     e32, e64 = maxdiff(emb, gd["emb"]), maxdiff(emb, gd["emb64"])
     print("fp16x3 large-family encoder", e32, e64)
     assert e32 < 2e-4 and e64 < 2e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [1000, 19264, 38528])
+def test_fused_feed_forward_vs_fp64(gpu_model, M):
+    """The fused GEGLU feed-forward kernel against fp64 math (reference ``ldm/attention.py:25-51, 232-234`` as folded at load):
+    M = 1000 (8 whole tiles, the last one partial), 19264 (151 tiles: one round + 3 leftover tiles split across CTAs) and 38528
+    (the bench's 301 tiles: two rounds + 5 split tiles, reduced in a fixed order)."""
+    eng = _engine(gpu_model)
+    g = torch.Generator(device="cpu").manual_seed(7 + M)
+    ln = torch.randn(M, 192, generator=g)
+    x2 = torch.randn(M, 192, generator=g) * 2.0
+    res = torch.randn(M, 192, generator=g)
+    w1 = torch.randn(192, 1536, generator=g) / 192 ** 0.5
+    b1 = torch.randn(1536, generator=g) * 0.1
+    w2 = torch.randn(960, 192, generator=g) / 960 ** 0.5
+    b2 = torch.randn(192, generator=g) * 0.1
+    dev = eng.device
+    out = eng.op_ffn_h(ln.to(dev), x2.to(dev), res.to(dev), w1, b1.to(dev), w2, b2.to(dev)).cpu().double()
+    # fp64 reference on a sample of rows (all rows of the split tiles' region included)
+    rows = torch.unique(torch.cat([torch.arange(0, min(M, 300)), torch.arange(max(0, M - 700), M), torch.randint(0, M, (400,), generator=g)]))
+    a = ln[rows].double() @ w1.double() + b1.double()
+    val, gate = a[:, 0::2], a[:, 1::2]
+    ff = val * (0.5 * gate * (1.0 + torch.erf(gate / 2 ** 0.5)))
+    ref = torch.cat([ff, x2[rows].double()], dim=1) @ w2.double() + b2.double() + res[rows].double()
+    err = float((out[rows] - ref).abs().max())
+    print(f"fused feed-forward M={M}: max err {err:.3e} (|ref| max {float(ref.abs().max()):.2f})")
+    assert err < 4e-5
+    # run to run bit-identical (the split tiles are reduced in a fixed order)
+    out2 = eng.op_ffn_h(ln.to(dev), x2.to(dev), res.to(dev), w1, b1.to(dev), w2, b2.to(dev)).cpu().double()
+    assert torch.equal(out, out2)
