@@ -186,8 +186,11 @@ SAID_API int said_op_gemm_tc_bench(said_engine* e, int M, int K, int nsplit, int
  *   3  tcgen05 tensor cores, fp16 hi/lo operand pairs, three passes (hi*hi + lo*hi + hi*lo, fp32 accumulate), operands
  *      pre-split by their producers and loaded by TMA: the accuracy of mode 1 at twice its tensor-core rate; activations
  *      must stay below fp16's range (65504), checked on the device (said_check_status).
- * GEMMs with fewer than tc_min_rows rows (<= 0: keep the current threshold) stay on the FFMA kernel, so results
- * are bit-reproducible across batch sizes only within one regime (mode 0 is reproducible across all sizes).
+ * GEMMs with fewer rows than a threshold stay on the FFMA kernel, so results are bit-reproducible across batch sizes only within
+ * one regime (mode 0 is reproducible across all sizes).  Defaults: 512 rows for the mode-3 denoiser (one 5 s clip under
+ * guidance is 602 rows: its 32-column weight tile images keep the tensor-core path ahead of the FFMA kernels from there), 2048
+ * rows for modes 1 / 2 and for the encoder.  tc_min_rows > 0 sets every threshold to that value, 0 keeps the current ones,
+ * < 0 restores the defaults.
  * encoder_mode: the same choice for the Wav2Vec2 encoder's GEMMs (default 0: the encoder runs once per clip, and
  * its long contractions (K up to 3072) lose about a decimal digit under the tensor cores' truncating accumulation). */
 SAID_API int said_set_precision(said_engine* e, int mode, int tc_min_rows, int encoder_mode);

@@ -1,0 +1,32 @@
+"""Single-clip latency (BASELINE configs[1]) with the FFMA kernels (engine default below tc_min_rows) and with every contraction on
+the tensor-core path (32-column tile images for small row counts), plus batch 2 and 4."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from said_b200.model.diffusion import SAID_UNet1D  # noqa: E402
+from said_b200.synth import synthetic_batch, synthetic_state_dict  # noqa: E402
+
+m = SAID_UNet1D()
+m.load_state_dict(synthetic_state_dict(0))
+m.to("cuda:0").eval()
+for B in (1, 2, 4, 8):
+    wave = synthetic_batch(B, 5.0).to("cuda:0")
+    res = {}
+    for name, rows in (("ffma", 1 << 30), ("tensor-core", 1)):
+        m.tc_min_rows = rows
+        outs = None
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                torch.manual_seed(0)
+                outs = m.inference(wave, num_inference_steps=1000, guidance_scale=2.0)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        res[name] = (dt, outs.result.clone())
+    d = float((res["ffma"][1] - res["tensor-core"][1]).abs().max())
+    print(f"batch {B}: ffma {res['ffma'][0] * 1e3 / 1000:.3f} ms/step, tensor-core {res['tensor-core'][0] * 1e3 / 1000:.3f} ms/step, max |diff| {d:.2e}", flush=True)

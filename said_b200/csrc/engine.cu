@@ -143,7 +143,9 @@ struct said_engine {
     // ---- fp16x3 path (gemm_h.cuh): per GEMM weight, an fp16 hi/lo tile image pre-scaled by 2^exp
     struct HW { uint8_t* img; int K, N, bn, exp; };
     std::map<const float*, HW> hmap;     // keyed like tcmap
-    bool reg_h = false;                  // register_tc also builds the fp16 image (denoiser weights only)
+    std::map<const float*, HW> hmap32;   // the same weights as 32-column tile images: small row counts (single clips) get 6x the CTAs
+    bool reg_h = false;                  // register_tc also builds the fp16 image
+    bool reg_h32 = false;                // ... and the 32-column image (denoiser weights only)
     int register_tc(const float* key, const float* host_wt, int K, int N, int ldw) {
         const int bn = (N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : (N == 32 ? 32 : 0));
         if (bn == 0 || K % tc::BK != 0) return 0;
@@ -152,19 +154,24 @@ struct said_engine {
         float* d = nullptr;
         CKI(upload(img, &d));
         tcmap[key] = TcW{d, K, N, bn};
-        if (reg_h && K % hx::HBK == 0) CKI(register_h(key, host_wt, K, N, ldw, bn));
+        if (reg_h && K % hx::HBK == 0) {
+            CKI(register_h(key, host_wt, K, N, ldw, bn));
+            if (reg_h32 && bn != 32 && N % 32 == 0) CKI(register_h(key, host_wt, K, N, ldw, 32, &hmap32));
+        }
         return 0;
     }
-    int register_h(const float* key, const float* host_wt, int K, int N, int ldw, int bn) {
+    int register_h(const float* key, const float* host_wt, int K, int N, int ldw, int bn, std::map<const float*, HW>* into = nullptr) {
         std::vector<uint16_t> himg;
         const int e = hx::pack_weights_h(host_wt, K, N, ldw, bn, himg);
         uint8_t* hd = nullptr;
         CK(cudaMalloc((void**)&hd, himg.size() * sizeof(uint16_t)));
         arena.push_back(reinterpret_cast<float*>(hd));
         CK(cudaMemcpy(hd, himg.data(), himg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-        hmap[key] = HW{hd, K, N, bn, e};
+        (into ? *into : hmap)[key] = HW{hd, K, N, bn, e};
         return 0;
     }
+    // few row tiles (single clips: 5 tiles of 128 rows): tile N by 32 instead of 192 so that the launch has 6x the CTAs
+    bool small_rows(int M) const { return ((M + hx::HBM - 1) / hx::HBM) * 6 <= num_sms; }   // (N = 32 MMAs cost 68 cycles against 96 for N = 192: only worth it while the 6x CTAs still fit one wave)
     // The fused feed-forward (ffn_h.cuh): out = [geglu(ln W1 + b1) | x2] Wffp + bias + residual of `ep`.  W1's image for this
     // kernel has 256-column n-tiles and is registered under the GEGLU bias pointer.
     // workspace of the fused feed-forward's split leftover tiles (ffn_h.cuh): partial accumulators + counters
@@ -216,6 +223,10 @@ struct said_engine {
                int k0 = 0 /*first contraction index of this launch within the weight (split-K), multiple of 64*/) {
         auto it = hmap.find(wkey);
         if (it == hmap.end()) return fail("fp16x3 gemm: weight image not registered");
+        if (small_rows(M) && it->second.bn != 32) {
+            auto it32 = hmap32.find(wkey);
+            if (it32 != hmap32.end()) it = it32;
+        }
         const HW& w = it->second;
         hx::HParams p;
         memset(&p, 0, sizeof(p));
@@ -329,7 +340,10 @@ struct said_engine {
     }
     int enc_precision = 0;               // audio encoder GEMMs: IEEE fp32 FFMA by default (exact parity with the goldens)
     int a_in_tmem = 0;                   // 1: activations through TMEM (TS MMA, gemm_tca_kernel) -- measured slower, kept for study
-    int tc_min_rows = 2048;              // below this many rows the small-tile FFMA kernel spreads better over the SMs
+    static constexpr int TC_MIN_ROWS_DEFAULT = 2048, H_MIN_ROWS_DEFAULT = 512;
+    int tc_min_rows = TC_MIN_ROWS_DEFAULT;   // 3xTF32 / TF32 denoiser and every tensor-core encoder: below this many rows the small-tile FFMA kernel spreads better over the SMs
+    int h_min_rows = H_MIN_ROWS_DEFAULT;     // fp16x3 denoiser: its 32-column tile images keep the tensor-core path ahead down to a single 5 s clip
+                                             // (602 rows: 0.54 vs 0.82 ms per step; two clips: 0.55 vs 1.06); shorter inputs stay on the IEEE fp32 kernels
     template <class AL, class EP>
     int gemm(cudaStream_t st, int M, int N, int K, const AL& al, const float* Wt, int ldw, const EP& ep, int batch = 1,
              int wz_mod = 1, long long w_zstride = 0) {
@@ -477,7 +491,7 @@ struct said_engine {
     bool enc_split_k = getenv("SAID_ENC_NO_SPLITK") == nullptr;   // fp16x3 encoder: contractions longer than 768 run as split-K launches (accuracy)
     bool fused_ffn = getenv("SAID_NO_FUSED_FFN") == nullptr;   // fp16x3 path: GEGLU + ff2 + proj_out as one kernel (ffn_h.cuh); the env switch keeps the two-GEMM form for A/B runs
     bool attn_h = getenv("SAID_ATTN_TF32") == nullptr;   // fp16x3 path: flash-style fp16 hi/lo attention (attention_h.cuh); the env switch keeps the 3xTF32 kernel reachable for A/B runs
-    bool use_h(int M) const { return precision == 3 && M >= tc_min_rows && in_ch == 32; }
+    bool use_h(int M) const { return precision == 3 && M >= h_min_rows && in_ch == 32; }
     int denoise(const said_denoise_args& a, cudaStream_t user);
 };
 
@@ -563,13 +577,8 @@ int said_engine::commit_denoiser() {
         if (r.skip) CKI(register_tc(r.w2 + (size_t)3 * C * C, w2.data() + (size_t)3 * C * C, r.cin, C, C));
         CKI(upload(b2, &r.b2));
         if (r.skip) {   // fp16x3 path: second conv + 1x1 skip as one K = 576 + 384 contraction; image keyed by the (unique) bias pointer
-            std::vector<uint16_t> himg;
-            const int e = hx::pack_weights_h(w2.data(), r.k2, C, C, 192, himg);
-            uint8_t* hd = nullptr;
-            CK(cudaMalloc((void**)&hd, himg.size() * sizeof(uint16_t)));
-            arena.push_back(reinterpret_cast<float*>(hd));
-            CK(cudaMemcpy(hd, himg.data(), himg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-            hmap[r.b2] = HW{hd, r.k2, C, 192, e};
+            CKI(register_h(r.b2, w2.data(), r.k2, C, C, 192));
+            CKI(register_h(r.b2, w2.data(), r.k2, C, C, 32, &hmap32));
         }
     }
     // ---- SpatialTransformers in execution order
@@ -893,10 +902,13 @@ int said_engine::commit() {
     arena.clear();
     tcmap.clear();
     hmap.clear();
+    hmap32.clear();
     ready = false;
     ctx_B = ctx_T = 0;
     reg_h = true;
+    reg_h32 = true;
     const int rc_d = commit_denoiser();
+    reg_h32 = false;
     const int rc_e = rc_d == 0 ? commit_encoder() : 0;
     reg_h = false;
     CKI(rc_d);
@@ -1854,7 +1866,7 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
         }
         cur_tag = TAG_ATTN;
         if (T <= hx::AH_MAXT && attn_h) {
-            const int ag = hx::attention_h_groups(T, HEADS);
+            const int ag = (h_nb * HEADS / 2 >= num_sms) ? hx::attention_h_groups(T, HEADS) : 1;   // few samples: one head per CTA, twice the CTAs
             CK(launch_ex(hx::self_attention_h_kernel, dim3(HEADS / ag, h_nb), dim3(hx::AH_THREADS * ag), hx::attention_h_smem_bytes(T, ag), st, pdl, 1,
                          (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag,
                          (uint32_t)hx::attention_h_group_bytes(T), (long long*)nullptr));
@@ -1901,7 +1913,7 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
             CKI(gemm_h(st, Mcp, C, {{psrc(pao + r0 * 2 * C, C, Mcp), 0, C, 0}}, W.wo2, ep, TAG_GEMM_PLAIN));
         }
         CKI(ln_pair(x2, Mp, nullptr, nullptr, W.ln3_g, W.ln3_b, pln, px2));
-        if (fused_ffn) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
+        if (fused_ffn && !small_rows(Mp)) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
             EpiStd ep = mk_epi(out, C, C);
             ep.bias = W.bffp;
             ep.res = h;
@@ -2033,7 +2045,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
             GraphKey key;
             memset(&key, 0, sizeof(key));
             key.B = B; key.T = T; key.Tc = ctx_T; key.do_cfg = a.do_cfg; key.n_steps = sp.n_steps; key.pred_type = a.prediction_type;
-            key.scheduler = a.scheduler; key.precision = precision; key.tc_min_rows = tc_min_rows;
+            key.scheduler = a.scheduler; key.precision = precision; key.tc_min_rows = tc_min_rows * 100003 + h_min_rows;
             key.gscale = a.guidance_scale; key.grescale = a.guidance_rescale; key.latent_scale = a.latent_scale;
             key.eta_noise = a.eta_noise_dev; key.edit_noise = a.edit_noise_dev; key.mask = a.mask_dev;
             key.intermediates = a.intermediates_dev;
@@ -2248,7 +2260,7 @@ int said_op_ffn_h(said_engine* e, const float* ln_dev, const float* x2_dev, cons
 int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int N, int with_residual, int dbg, int iters, float* ms_out) {
     // diagnostics: average milliseconds of the fp16x3 GEMM on scratch (zero) operands, with parts of it disabled by dbg
     if (!e || !ms_out) return fail("said_op_gemm_h_bench: bad arguments");
-    if (!(taps == 1 || taps == 3) || Cin % hx::HBK != 0 || N % 192 != 0) return fail("said_op_gemm_h_bench: unsupported shape");
+    if (!(taps == 1 || taps == 3) || Cin % hx::HBK != 0 || (N % 192 != 0 && N != 32)) return fail("said_op_gemm_h_bench: unsupported shape");
     CK(cudaSetDevice(e->device));
     static DevBuf a, o, r;
     if (with_residual == 3) {   // the fused feed-forward (M rows; Cin, taps, N ignored) on zero operands
@@ -2318,12 +2330,13 @@ int said_op_gemm_h_bench(said_engine* e, int M, int Cin, int taps, int N, int wi
     CK(o.ensure_zero((size_t)M * N));
     CK(r.ensure_zero((size_t)M * N));
     const int K = taps * Cin;
-    const size_t wbytes = (size_t)(N / 192) * (K / hx::HBK) * 2 * 192 * hx::HROW;
+    const int bnb = N == 32 ? 32 : 192;
+    const size_t wbytes = (size_t)(N / bnb) * (K / hx::HBK) * 2 * bnb * hx::HROW;
     uint8_t* wd = nullptr;
     CK(cudaMalloc((void**)&wd, wbytes));
     CK(cudaMemset(wd, 0, wbytes));
     const float* key = reinterpret_cast<const float*>(wd);
-    e->hmap[key] = said_engine::HW{wd, K, N, 192, 0};
+    e->hmap[key] = said_engine::HW{wd, K, N, bnb, 0};
     const said_engine::HSrc src{reinterpret_cast<const __half*>(a.p), Cin, M};
     EpiStd ep = mk_epi(o.p, N, N);
     if (with_residual == 1) { ep.res = r.p; ep.ldr = N; }
@@ -2597,7 +2610,8 @@ int said_set_precision(said_engine* e, int mode, int tc_min_rows, int encoder_mo
     if (encoder_mode < 0 || encoder_mode > 3) return fail("said_set_precision: encoder_mode must be 0, 1, 2 or 3");
     e->precision = mode;
     e->enc_precision = encoder_mode;
-    if (tc_min_rows > 0) e->tc_min_rows = tc_min_rows;
+    if (tc_min_rows > 0) e->tc_min_rows = e->h_min_rows = tc_min_rows;
+    else if (tc_min_rows < 0) { e->tc_min_rows = said_engine::TC_MIN_ROWS_DEFAULT; e->h_min_rows = said_engine::H_MIN_ROWS_DEFAULT; }
     e->a_in_tmem = getenv("SAID_TC_TMEM_A") ? 1 : 0;   // study aid: SAID_TC_TMEM_A=1 selects the A-through-TMEM kernel
     return 0;
 }

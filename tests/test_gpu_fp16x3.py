@@ -120,7 +120,7 @@ def test_denoiser_forward_fp16x3_golden(golden_dir, gpu_model):
         out, taps = eng.denoiser_forward(torch.from_numpy(gd["x"]).to(DEV), torch.from_numpy(gd["t"]),
                                          torch.from_numpy(gd["ctx"]).to(DEV), taps=True)
     finally:
-        eng.set_precision(m.precision, 2048, m.encoder_precision)
+        eng.set_precision(m.precision, -1, m.encoder_precision)
     errs = {name: maxdiff(taps[i].transpose(1, 2), gd["act_" + name]) for i, name in enumerate(TAP_ORDER) if "act_" + name in gd.files}
     errs["out"] = maxdiff(out, gd["y64"])
     print("fp16x3", errs)
@@ -146,7 +146,7 @@ class _Mode:
 
     def __exit__(self, *a):
         self.m.precision, self.m.tc_min_rows = self.saved
-        self.m._engine(torch.device(DEV)).set_precision(self.m.precision, 2048, self.m.encoder_precision)
+        self.m._engine(torch.device(DEV)).set_precision(self.m.precision, -1, self.m.encoder_precision)
 
 
 def test_chain_1000_steps_fp16x3(golden_dir, gpu_model):
@@ -236,7 +236,7 @@ def test_audio_encoder_fp16x3(golden_dir, gpu_model):
         ref = m.get_audio_embedding(wave, 60)
     finally:
         m.encoder_precision, m.tc_min_rows = saved
-        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, m.encoder_precision)
+        m._engine(torch.device(DEV)).set_precision(m.precision, -1, m.encoder_precision)
     e32, e64, eb = maxdiff(emb, gd["emb"]), maxdiff(emb, gd["emb64"]), maxdiff(got, ref)
     print("fp16x3 encoder vs reference", e32, e64, "batch of 8 vs fp32 kernels", eb)
     assert e32 < 2e-4 and e64 < 2e-4 and eb < 2e-4
@@ -288,3 +288,35 @@ def test_fused_feed_forward_vs_fp64(gpu_model, M):
     # run to run bit-identical (the split tiles are reduced in a fixed order)
     out2 = eng.op_ffn_h(ln.to(dev), x2.to(dev), res.to(dev), w1, b1.to(dev), w2, b2.to(dev)).cpu().double()
     assert torch.equal(out, out2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 2])
+def test_small_batch_default_path_vs_oracle(gpu_model, state_dict, B):
+    """One and two 5 s clips at DEFAULT settings: 602 / 1204 denoiser rows are above the fp16x3 row threshold (512), so the
+    tensor-core kernels run with the 32-column weight tile images, the two-GEMM feed-forward and one head per attention CTA.
+    4 DDIM steps under CFG against the CPU oracle; and the same call on the FFMA kernels must differ in the last bits (proof that
+    the default did not take them)."""
+    from oracle import said_oracle as O
+    from said_b200.synth import synthetic_batch
+
+    wave = synthetic_batch(B, 5.0)
+    g = torch.Generator().manual_seed(23 + B)
+    noise = torch.randn(B, 300, 32, generator=g)
+    m = gpu_model("epsilon")
+    eng = m._engine(torch.device(DEV))
+    eng.set_precision(m.precision, -1, m.encoder_precision)
+    out = _run(m, wave, noise, steps=4)
+    res, lat = out.result.cpu(), out.latents.cpu()
+    m.tc_min_rows = 1 << 30
+    try:
+        lat_ffma = _run(m, wave, noise, steps=4).latents.cpu()
+    finally:
+        m.tc_min_rows = 0
+        eng.set_precision(m.precision, -1, m.encoder_precision)
+    with torch.no_grad():
+        ref, pre = O.inference(state_dict, wave, num_inference_steps=4, guidance_scale=2.0, noise=noise, return_preclamp=True)
+    e, ep, ef = maxdiff(res, ref), maxdiff(lat, pre[-1]), maxdiff(lat, lat_ffma)
+    print(f"small batch {B}: result vs oracle {e:.3e}, pre-clamp {ep:.3e}, vs FFMA kernels {ef:.3e}")
+    assert e < 5e-4 and ep < 1e-3
+    assert 0.0 < ef < 1e-3

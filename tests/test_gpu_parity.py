@@ -143,7 +143,7 @@ def test_denoiser_forward_precision_modes(golden_dir, gpu_model, mode, tol):
         out, taps = eng.denoiser_forward(torch.from_numpy(gd["x"]).to(DEV), torch.from_numpy(gd["t"]),
                                          torch.from_numpy(gd["ctx"]).to(DEV), taps=True)
     finally:
-        eng.set_precision(m.precision, 2048, m.encoder_precision)
+        eng.set_precision(m.precision, -1, m.encoder_precision)
     errs = {name: maxdiff(taps[i].transpose(1, 2), gd["act_" + name]) for i, name in enumerate(TAP_ORDER) if "act_" + name in gd.files}
     errs["out"] = maxdiff(out, gd["y64"])
     print(mode, errs)
@@ -188,7 +188,7 @@ def test_audio_encoder_tensor_core_mode(golden_dir, gpu_model):
         got = m.get_audio_embedding(wave, 60)
     finally:
         m.encoder_precision, m.tc_min_rows = default, 0
-        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, default)
+        m._engine(torch.device(DEV)).set_precision(m.precision, -1, default)
     e = maxdiff(got, ref)
     print("encoder tf32x3 vs fp32", e)
     assert 0 < e < 1e-3
@@ -209,7 +209,7 @@ def test_chain_1000_steps_tensor_core_mode(golden_dir, gpu_model, pt):
         out = run(m, wave, gd["noise"], steps=1000)
     finally:
         m.tc_min_rows, m.precision = 0, default
-        m._engine(torch.device(DEV)).set_precision(m.precision, 2048, m.encoder_precision)
+        m._engine(torch.device(DEV)).set_precision(m.precision, -1, m.encoder_precision)
     e32, e64 = maxdiff(out.result, gd["result"]), maxdiff(out.result, gd["result64"])
     print("tensor-core chain", pt, e32, e64)
     assert e32 < 1e-3 and e64 < 1e-3
@@ -668,7 +668,7 @@ def test_gemm_tail_slivers_match_fp32(gpu_model):
     t = torch.randint(0, 1000, (320,), generator=g)
     outs = {}
     for mode in ("tf32x3", "fp32"):
-        eng.set_precision(mode, 2048, "fp32")
+        eng.set_precision(mode, -1, "fp32")
         try:
             outs[mode] = eng.denoiser_forward(x, t, ctx).cpu()
         finally:
@@ -690,7 +690,7 @@ def test_full_size_forward_tc_vs_fp32(gpu_model):
     t = torch.randint(0, 1000, (128,), generator=g)
     outs = {}
     for mode in ("tf32x3", "fp32"):
-        eng.set_precision(mode, 2048, "fp32")
+        eng.set_precision(mode, -1, "fp32")
         try:
             outs[mode] = eng.denoiser_forward(x, t, ctx).cpu()
         finally:
