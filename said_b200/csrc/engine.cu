@@ -113,7 +113,11 @@ struct EncLayerW {
 struct said_engine {
     int device = 0;
     int num_sms = 0;
-    bool pdl = getenv("SAID_PDL") != nullptr;   // programmatic dependent launch for the step-loop kernels: measured slower, opt-in (common.cuh)
+    bool pdl = getenv("SAID_PDL") != nullptr;   // programmatic dependent launch for the step-loop kernels: measured slower at batch scale, opt-in (common.cuh)
+    // ... but ON for the small-row tensor-core path (single clips): its launches fill a fraction of the SMs, so the next kernel's
+    // CTAs really are resident early and their prologues (barrier init, TMEM allocation, descriptor prefetch) overlap the
+    // predecessor's tail: 0.54 -> 0.48 ms per step for one 5 s clip.  SAID_NO_PDL_SMALL switches it off.
+    bool pdl_small = getenv("SAID_NO_PDL_SMALL") == nullptr;
     bool gn_fused = getenv("SAID_GN_TWO_PASS") == nullptr;   // cluster GroupNorm (one launch); the env switch keeps the two-kernel version reachable for A/B timing
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -144,6 +148,7 @@ struct said_engine {
     struct HW { uint8_t* img; int K, N, bn, exp; };
     std::map<const float*, HW> hmap;     // keyed like tcmap
     std::map<const float*, HW> hmap32;   // the same weights as 32-column tile images: small row counts (single clips) get 6x the CTAs
+    std::map<const float*, HW> hmap64;   // ... and as 64-column images: 3x the CTAs for a handful of clips
     bool reg_h = false;                  // register_tc also builds the fp16 image
     bool reg_h32 = false;                // ... and the 32-column image (denoiser weights only)
     int register_tc(const float* key, const float* host_wt, int K, int N, int ldw) {
@@ -157,6 +162,7 @@ struct said_engine {
         if (reg_h && K % hx::HBK == 0) {
             CKI(register_h(key, host_wt, K, N, ldw, bn));
             if (reg_h32 && bn != 32 && N % 32 == 0) CKI(register_h(key, host_wt, K, N, ldw, 32, &hmap32));
+            if (reg_h32 && bn != 32 && N % 64 == 0) CKI(register_h(key, host_wt, K, N, ldw, 64, &hmap64));
         }
         return 0;
     }
@@ -174,6 +180,7 @@ struct said_engine {
     bool small_rows(int M) const { return ((M + hx::HBM - 1) / hx::HBM) * 6 <= num_sms; }   // (N = 32 MMAs cost 68 cycles against 96 for N = 192: only worth it while the 6x CTAs still fit one wave)
     // The fused feed-forward (ffn_h.cuh): out = [geglu(ln W1 + b1) | x2] Wffp + bias + residual of `ep`.  W1's image for this
     // kernel has 256-column n-tiles and is registered under the GEGLU bias pointer.
+    bool mid_rows(int M) const { return !small_rows(M) && ((M + hx::HBM - 1) / hx::HBM) * 3 <= num_sms; }   // 25..49 row tiles: 64-column tiles
     // workspace of the fused feed-forward's split leftover tiles (ffn_h.cuh): partial accumulators + counters
     DevBuf ffn_part, ffn_sync;
     bool ffn_split = getenv("SAID_FFN_NOSPLIT") == nullptr;
@@ -226,6 +233,9 @@ struct said_engine {
         if (small_rows(M) && it->second.bn != 32) {
             auto it32 = hmap32.find(wkey);
             if (it32 != hmap32.end()) it = it32;
+        } else if (mid_rows(M) && it->second.bn == 192) {
+            auto it64 = hmap64.find(wkey);
+            if (it64 != hmap64.end()) it = it64;
         }
         const HW& w = it->second;
         hx::HParams p;
@@ -266,6 +276,7 @@ struct said_engine {
         cudaError_t e = cudaErrorInvalidValue;
         if (w.bn == 192) e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, ep, pdl);
         else if (w.bn == 128) e = hx::launch_gemm_h<128>(st, num_sms, p, w.img, ep, pdl);
+        else if (w.bn == 64) e = hx::launch_gemm_h<64>(st, num_sms, p, w.img, ep, pdl);
         else if (w.bn == 32) e = hx::launch_gemm_h<32>(st, num_sms, p, w.img, ep, pdl);
         if (e != cudaSuccess) return fail(std::string("fp16x3 gemm launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
@@ -579,6 +590,7 @@ int said_engine::commit_denoiser() {
         if (r.skip) {   // fp16x3 path: second conv + 1x1 skip as one K = 576 + 384 contraction; image keyed by the (unique) bias pointer
             CKI(register_h(r.b2, w2.data(), r.k2, C, C, 192));
             CKI(register_h(r.b2, w2.data(), r.k2, C, C, 32, &hmap32));
+            CKI(register_h(r.b2, w2.data(), r.k2, C, C, 64, &hmap64));
         }
     }
     // ---- SpatialTransformers in execution order
@@ -903,6 +915,7 @@ int said_engine::commit() {
     tcmap.clear();
     hmap.clear();
     hmap32.clear();
+    hmap64.clear();
     ready = false;
     ctx_B = ctx_T = 0;
     reg_h = true;
@@ -1771,6 +1784,11 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
     const bool share = n_uncond > 0 && 2 * n_uncond == Bp && taps == nullptr;   // see forward(): shared guidance prefix
     const int Bs = share ? Bp - n_uncond : Bp;
     const int Msp = Bs * Tp;
+    struct PdlScope {
+        bool& p; bool saved;
+        PdlScope(bool& p_, bool v) : p(p_), saved(p_) { p = v; }
+        ~PdlScope() { p = saved; }
+    } pdl_scope(pdl, pdl || (pdl_small && (small_rows(Mp) || mid_rows(Mp))));
     float* h0 = act[0].p; float* h1 = act[1].p; float* A = act[2].p; float* Bb = act[3].p;
     float* t1 = act[4].p; float* x1 = act[5].p; float* x2 = act[6].p;
     float* sc_st = ss_st.p; float* sh_st = ss_st.p + (size_t)Bp * C;
@@ -1913,7 +1931,7 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
             CKI(gemm_h(st, Mcp, C, {{psrc(pao + r0 * 2 * C, C, Mcp), 0, C, 0}}, W.wo2, ep, TAG_GEMM_PLAIN));
         }
         CKI(ln_pair(x2, Mp, nullptr, nullptr, W.ln3_g, W.ln3_b, pln, px2));
-        if (fused_ffn && !small_rows(Mp)) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
+        if (fused_ffn && !small_rows(Mp) && !mid_rows(Mp)) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
             EpiStd ep = mk_epi(out, C, C);
             ep.bias = W.bffp;
             ep.res = h;

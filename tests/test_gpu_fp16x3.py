@@ -291,10 +291,11 @@ def test_fused_feed_forward_vs_fp64(gpu_model, M):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B", [1, 2])
+@pytest.mark.parametrize("B", [1, 2, 6])
 def test_small_batch_default_path_vs_oracle(gpu_model, state_dict, B):
-    """One and two 5 s clips at DEFAULT settings: 602 / 1204 denoiser rows are above the fp16x3 row threshold (512), so the
-    tensor-core kernels run with the 32-column weight tile images, the two-GEMM feed-forward and one head per attention CTA.
+    """One, two and six 5 s clips at DEFAULT settings: 602 / 1204 / 3612 denoiser rows are above the fp16x3 row threshold (512),
+    so the tensor-core kernels run with the 32-column (1, 2 clips) or 64-column (6 clips) weight tile images, the two-GEMM
+    feed-forward, one head per attention CTA and programmatic dependent launch.
     4 DDIM steps under CFG against the CPU oracle; and the same call on the FFMA kernels must differ in the last bits (proof that
     the default did not take them)."""
     from oracle import said_oracle as O
