@@ -149,6 +149,7 @@ struct said_engine {
     std::map<const float*, HW> hmap;     // keyed like tcmap
     std::map<const float*, HW> hmap32;   // the same weights as 32-column tile images: small row counts (single clips) get 6x the CTAs
     std::map<const float*, HW> hmap64;   // ... and as 64-column images: 3x the CTAs for a handful of clips
+    std::map<const float*, HW> hmap96;   // ... and as 96-column images: 2x the CTAs up to half a wave of row tiles
     bool reg_h = false;                  // register_tc also builds the fp16 image
     bool reg_h32 = false;                // ... and the 32-column image (denoiser weights only)
     int register_tc(const float* key, const float* host_wt, int K, int N, int ldw) {
@@ -163,6 +164,7 @@ struct said_engine {
             CKI(register_h(key, host_wt, K, N, ldw, bn));
             if (reg_h32 && bn != 32 && N % 32 == 0) CKI(register_h(key, host_wt, K, N, ldw, 32, &hmap32));
             if (reg_h32 && bn != 32 && N % 64 == 0) CKI(register_h(key, host_wt, K, N, ldw, 64, &hmap64));
+            if (reg_h32 && bn != 32 && N % 96 == 0) CKI(register_h(key, host_wt, K, N, ldw, 96, &hmap96));
         }
         return 0;
     }
@@ -181,6 +183,7 @@ struct said_engine {
     // The fused feed-forward (ffn_h.cuh): out = [geglu(ln W1 + b1) | x2] Wffp + bias + residual of `ep`.  W1's image for this
     // kernel has 256-column n-tiles and is registered under the GEGLU bias pointer.
     bool mid_rows(int M) const { return !small_rows(M) && ((M + hx::HBM - 1) / hx::HBM) * 3 <= num_sms; }   // 25..49 row tiles: 64-column tiles
+    bool half_rows(int M) const { return !small_rows(M) && !mid_rows(M) && ((M + hx::HBM - 1) / hx::HBM) * 2 <= num_sms; }   // 50..74 row tiles: 96-column tiles
     // workspace of the fused feed-forward's split leftover tiles (ffn_h.cuh): partial accumulators + counters
     DevBuf ffn_part, ffn_sync;
     bool ffn_split = getenv("SAID_FFN_NOSPLIT") == nullptr;
@@ -236,6 +239,9 @@ struct said_engine {
         } else if (mid_rows(M) && it->second.bn == 192) {
             auto it64 = hmap64.find(wkey);
             if (it64 != hmap64.end()) it = it64;
+        } else if (half_rows(M) && it->second.bn == 192) {
+            auto it96 = hmap96.find(wkey);
+            if (it96 != hmap96.end()) it = it96;
         }
         const HW& w = it->second;
         hx::HParams p;
@@ -276,6 +282,7 @@ struct said_engine {
         cudaError_t e = cudaErrorInvalidValue;
         if (w.bn == 192) e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, ep, pdl);
         else if (w.bn == 128) e = hx::launch_gemm_h<128>(st, num_sms, p, w.img, ep, pdl);
+        else if (w.bn == 96) e = hx::launch_gemm_h<96>(st, num_sms, p, w.img, ep, pdl);
         else if (w.bn == 64) e = hx::launch_gemm_h<64>(st, num_sms, p, w.img, ep, pdl);
         else if (w.bn == 32) e = hx::launch_gemm_h<32>(st, num_sms, p, w.img, ep, pdl);
         if (e != cudaSuccess) return fail(std::string("fp16x3 gemm launch failed: ") + cudaGetErrorString(e));
@@ -591,6 +598,7 @@ int said_engine::commit_denoiser() {
             CKI(register_h(r.b2, w2.data(), r.k2, C, C, 192));
             CKI(register_h(r.b2, w2.data(), r.k2, C, C, 32, &hmap32));
             CKI(register_h(r.b2, w2.data(), r.k2, C, C, 64, &hmap64));
+            CKI(register_h(r.b2, w2.data(), r.k2, C, C, 96, &hmap96));
         }
     }
     // ---- SpatialTransformers in execution order
@@ -916,6 +924,7 @@ int said_engine::commit() {
     hmap.clear();
     hmap32.clear();
     hmap64.clear();
+    hmap96.clear();
     ready = false;
     ctx_B = ctx_T = 0;
     reg_h = true;
@@ -1788,7 +1797,7 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
         bool& p; bool saved;
         PdlScope(bool& p_, bool v) : p(p_), saved(p_) { p = v; }
         ~PdlScope() { p = saved; }
-    } pdl_scope(pdl, pdl || (pdl_small && (small_rows(Mp) || mid_rows(Mp))));
+    } pdl_scope(pdl, pdl || (pdl_small && (small_rows(Mp) || mid_rows(Mp) || half_rows(Mp))));
     float* h0 = act[0].p; float* h1 = act[1].p; float* A = act[2].p; float* Bb = act[3].p;
     float* t1 = act[4].p; float* x1 = act[5].p; float* x2 = act[6].p;
     float* sc_st = ss_st.p; float* sh_st = ss_st.p + (size_t)Bp * C;
@@ -1931,7 +1940,7 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
             CKI(gemm_h(st, Mcp, C, {{psrc(pao + r0 * 2 * C, C, Mcp), 0, C, 0}}, W.wo2, ep, TAG_GEMM_PLAIN));
         }
         CKI(ln_pair(x2, Mp, nullptr, nullptr, W.ln3_g, W.ln3_b, pln, px2));
-        if (fused_ffn && !small_rows(Mp) && !mid_rows(Mp)) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
+        if (fused_ffn && !small_rows(Mp) && !mid_rows(Mp) && !half_rows(Mp)) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
             EpiStd ep = mk_epi(out, C, C);
             ep.bias = W.bffp;
             ep.res = h;

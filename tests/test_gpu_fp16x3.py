@@ -291,7 +291,7 @@ def test_fused_feed_forward_vs_fp64(gpu_model, M):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B", [1, 2, 6])
+@pytest.mark.parametrize("B", [1, 2, 6, 12])
 def test_small_batch_default_path_vs_oracle(gpu_model, state_dict, B):
     """One, two and six 5 s clips at DEFAULT settings: 602 / 1204 / 3612 denoiser rows are above the fp16x3 row threshold (512),
     so the tensor-core kernels run with the 32-column (1, 2 clips) or 64-column (6 clips) weight tile images, the two-GEMM
