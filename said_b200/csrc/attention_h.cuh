@@ -139,6 +139,8 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
     pdl_wait();
     pdl_trigger();
     const int n_qtiles = (T + 127) / 128;
+    // few samples: gridDim.z = n_qtiles spreads the query tiles of a head over CTAs (each stages K / V itself)
+    const int qt_begin = gridDim.z > 1 ? (int)blockIdx.z : 0, qt_end = gridDim.z > 1 ? qt_begin + 1 : n_qtiles;
 
     // ---------------- MMA issue (warp 0 of the group between its softmax duties: all lanes run the bookkeeping, one elected lane issues) ----------------
     const uint64_t dq = make_desc(q_sm);
@@ -234,8 +236,8 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 qreg[u][1] = ok ? ldg4(src + 4) : zero4();
             }
         };
-        load_q(0);
-        for (int qt = 0; qt < n_qtiles; ++qt) {
+        load_q(qt_begin);
+        for (int qt = qt_begin; qt < qt_end; ++qt) {
             // ---------------- Q tile: 128 rows x [hi | lo], pre-scaled ----------------
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -248,7 +250,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 sts16(ra + (uint32_t)((c2 ^ (r & 7)) << 4), hi);
                 sts16(ra + (uint32_t)(((4 + c2) ^ (r & 7)) << 4), lo);
             }
-            if (qt + 1 < n_qtiles) load_q(qt + 1);             // in flight during this tile's MMAs and softmax
+            if (qt + 1 < qt_end) load_q(qt + 1);               // in flight during this tile's MMAs and softmax
             tc_fence_before();                                 // (TMEM reads of the previous tile's O are complete)
             tc::fence_proxy_async();
             mbar_arrive(bar_q);

@@ -1894,7 +1894,9 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
         cur_tag = TAG_ATTN;
         if (T <= hx::AH_MAXT && attn_h) {
             const int ag = (h_nb * HEADS / 2 >= num_sms) ? hx::attention_h_groups(T, HEADS) : 1;   // few samples: one head per CTA, twice the CTAs
-            CK(launch_ex(hx::self_attention_h_kernel, dim3(HEADS / ag, h_nb), dim3(hx::AH_THREADS * ag), hx::attention_h_smem_bytes(T, ag), st, pdl, 1,
+            const int nqt = (T + 127) / 128;
+            const int zs = (ag == 1 && h_nb * HEADS * nqt <= num_sms) ? nqt : 1;                    // ... and one query tile per CTA while that fits a wave
+            CK(launch_ex(hx::self_attention_h_kernel, dim3(HEADS / ag, h_nb, zs), dim3(hx::AH_THREADS * ag), hx::attention_h_smem_bytes(T, ag), st, pdl, 1,
                          (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag,
                          (uint32_t)hx::attention_h_group_bytes(T), (long long*)nullptr));
         } else if (T <= tc::ATC_MAXKEYS) {
