@@ -187,6 +187,7 @@ struct said_engine {
     // workspace of the fused feed-forward's split leftover tiles (ffn_h.cuh): partial accumulators + counters
     DevBuf ffn_part, ffn_sync;
     bool ffn_split = getenv("SAID_FFN_NOSPLIT") == nullptr;
+    int ffn_min_tiles = getenv("SAID_FFN_MIN_TILES") ? atoi(getenv("SAID_FFN_MIN_TILES")) : 75;   // measured at 16 / 24 / 32 / 48 clips: 75 -> 0.95 / 1.06 / 1.43 / 1.78 ms per step, 148 -> 0.95 / 1.12 / 1.44 / 1.77, never -> 0.98 / 1.13 / 1.45 / 1.83
     int ensure_ffn_split(size_t M) {
         const int tiles = (int)((M + hx::HBM - 1) / hx::HBM), grid = tiles < num_sms ? tiles : num_sms;
         const int left = tiles - (tiles / grid) * grid;
@@ -1942,7 +1943,8 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
             CKI(gemm_h(st, Mcp, C, {{psrc(pao + r0 * 2 * C, C, Mcp), 0, C, 0}}, W.wo2, ep, TAG_GEMM_PLAIN));
         }
         CKI(ln_pair(x2, Mp, nullptr, nullptr, W.ln3_g, W.ln3_b, pln, px2));
-        if (fused_ffn && !small_rows(Mp) && !mid_rows(Mp) && !half_rows(Mp)) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
+        // (below half a wave of row tiles the fused kernel leaves most SMs idle for a whole tile time: two finer-tiled GEMMs spread better)
+        if (fused_ffn && (Mp + hx::HBM - 1) / hx::HBM >= ffn_min_tiles) {   // GEGLU, ff2 and proj_out in one kernel: the 768-wide intermediate stays in shared memory
             EpiStd ep = mk_epi(out, C, C);
             ep.bias = W.bffp;
             ep.res = h;
