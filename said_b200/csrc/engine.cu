@@ -1821,6 +1821,8 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
     // clusters of 4 CTAs per sample, 10 frames per thread at batch scale; 8 CTAs for long clips / few samples.  (8 CTAs x 5 frames
     // per thread at batch scale -- more resident warps -- measured slower: 0.58 vs 0.49 ms per step; SAID_GN_CL8 selects it.)
     static const bool gn_cl8 = getenv("SAID_GN_CL8") != nullptr;
+    static const int gn_two_env = getenv("SAID_GN_TWO") ? atoi(getenv("SAID_GN_TWO")) : 0;   // A/B: stats + apply as two plain launches, this many slabs per sample (<= 16)
+    const int gn_two = gn_two_env > GN_SPLIT_MAX ? GN_SPLIT_MAX : gn_two_env;
     const int gn_cl = (!gn_cl8 && T <= 320 && Bp * GN_SPLIT >= num_sms) ? GN_SPLIT : 8;
     const bool gn_r5 = gn_cl == 8 && ((T + 7) / 8 + 7) / 8 <= 5;
     if (((T + gn_cl - 1) / gn_cl + 7) / 8 > GNF_MAXR) return fail("fp16x3 path: at most 640 frames per clip");
@@ -1828,6 +1830,16 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
     auto gnp = [&](const float* src, int src_nb, int nb, int cpg, float eps_, const float* g, const float* b, float* osc, float* osh,
                    __half* act_pair, __half* raw_pair, int act_C, int act_off) -> int {
         cur_tag = TAG_GN;
+        if (gn_two) {
+            const int slabs = gn_two;
+            CK(launch_ex(gn_stats_kernel, dim3(slabs, nb), dim3(GN2_THREADS), 0, st, pdl, 1, src, src_nb, T, Tp, gn_partial));
+            LAUNCH_CHECK();
+            cur_tag = TAG_GN;
+            CK(launch_ex(gn_apply_kernel, dim3(slabs, nb), dim3(GN2_THREADS), 0, st, pdl, 1, src, src_nb, T, Tp, cpg, eps_,
+                         (const double*)gn_partial, g, b, osc, osh, C, 0, act_pair, raw_pair, act_C, act_off, status_flag));
+            LAUNCH_CHECK();
+            return 0;
+        }
         if (gn_r5)
             CK(launch_ex(gn_pair_kernel<5>, dim3(gn_cl, nb), dim3(GNF_THREADS), 0, st, pdl, gn_cl, src, src_nb, T, Tp, cpg, eps_, g, b, osc, osh,
                          C, 0, act_pair, raw_pair, act_C, act_off, status_flag));

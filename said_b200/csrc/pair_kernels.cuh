@@ -163,6 +163,140 @@ gn_pair_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, in
 // tensor:  y = LN(x * ps + pb) * gamma + beta   (attention.py:168-192 norm1 / norm2 / norm3); optionally also x itself as a
 // pair tensor (the residual stream as an operand of the folded ff.net.2 + proj_out GEMM).  16 lanes per row.
 // ------------------------------------------------------------------------------------------------
+// The same GroupNorm as two plain launches (no cluster, no barrier between the reduction and the stores):
+//   gn_stats_kernel   per-channel sum / sum of squares of a slab of frames -> fp64 partials (sample, slab, 2, 192)
+//   gn_apply_kernel   every CTA re-reduces its sample's partials (a few hundred loads), derives scale / shift and writes
+//                     silu(gn(x)) and / or x as operand pairs for its slab of frames (+ the zero pad row)
+// x is read twice (the second time from L2); in exchange neither kernel has a latency chain longer than load -> reduce -> store,
+// registers drop to a few frames per thread and the grids are many small CTAs.  MEASURED SLOWER at batch 64 (GroupNorm + LayerNorm
+// family per step: 0.60 / 0.65 / 0.72 ms with 4 / 8 / 12 slabs against 0.47 for the cluster kernel): every variant that reads x a
+// second time lost by about the cost of that read, occupancy and CTA count made no difference -- the family is bound by bytes
+// moved, not by the cluster barriers.  Kept behind SAID_GN_TWO=<slabs> for A/B runs.
+// ------------------------------------------------------------------------------------------------
+constexpr int GN2_THREADS = 384;   // 8 row phases x 48 channel quads
+__global__ void __launch_bounds__(GN2_THREADS)
+gn_stats_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, double* __restrict__ partial /*(B', slabs, 2, 192)*/) {
+    constexpr int C = 192, Q = C / 4, PH = GN2_THREADS / Q;
+    __shared__ float4 s_redf[PH][2][Q];
+    pdl_wait();
+    pdl_trigger();
+    const int nsp = gridDim.x, sp = blockIdx.x, b = blockIdx.y;
+    const int q = threadIdx.x % Q, ph = threadIdx.x / Q;
+    const int rows = (T + nsp - 1) / nsp;
+    const int t0 = sp * rows, t1 = min(T, t0 + rows);
+    const float* xp = x + ((long long)(b % src_samples) * Tstr + t0 + ph) * C + q * 4;
+    float4 fs = zero4(), fq = zero4();
+    for (int t = t0 + ph; t < t1; t += 2 * PH) {         // two independent loads in flight
+        const float4 a = ldg4(xp);
+        const float4 d = t + PH < t1 ? ldg4(xp + PH * C) : zero4();
+        xp += 2 * PH * C;
+        fs.x += a.x + d.x; fs.y += a.y + d.y; fs.z += a.z + d.z; fs.w += a.w + d.w;
+        fq.x = fmaf(a.x, a.x, fmaf(d.x, d.x, fq.x)); fq.y = fmaf(a.y, a.y, fmaf(d.y, d.y, fq.y));
+        fq.z = fmaf(a.z, a.z, fmaf(d.z, d.z, fq.z)); fq.w = fmaf(a.w, a.w, fmaf(d.w, d.w, fq.w));
+    }
+    s_redf[ph][0][q] = fs;
+    s_redf[ph][1][q] = fq;
+    __syncthreads();
+    const int w = threadIdx.x / C, c = threadIdx.x - w * C;          // GN2_THREADS == 2 * C
+    double cs = 0.0;
+#pragma unroll
+    for (int p2 = 0; p2 < PH; ++p2) cs += (double)reinterpret_cast<const float*>(&s_redf[p2][w][0])[c];
+    partial[(((long long)b * nsp + sp) * 2 + w) * C + c] = cs;
+}
+
+__global__ void __launch_bounds__(GN2_THREADS)
+gn_apply_kernel(const float* __restrict__ x, int src_samples, int T, int Tstr, int cpg, float eps, const double* __restrict__ partial,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
+                int out_ld, int out_off, __half* __restrict__ act_pair, __half* __restrict__ raw_pair, int act_C, int act_off,
+                int* __restrict__ flag) {
+    constexpr int C = 192, Q = C / 4, PH = GN2_THREADS / Q;
+    __shared__ double s_ch[2][C];
+    __shared__ float s_mean[32], s_rstd[32];
+    pdl_wait();
+    pdl_trigger();
+    const int nsp = gridDim.x, sp = blockIdx.x, b = blockIdx.y;
+    {
+        const int w = threadIdx.x / C, c = threadIdx.x - w * C;
+        double a = 0.0;
+        for (int k = 0; k < nsp; ++k) a += partial[(((long long)b * nsp + k) * 2 + w) * C + c];
+        s_ch[w][c] = a;
+    }
+    __syncthreads();
+    const int ng = C / cpg;
+    if ((int)threadIdx.x < ng) {
+        double gs = 0.0, gq = 0.0;
+        for (int j = 0; j < cpg; ++j) {
+            gs += s_ch[0][threadIdx.x * cpg + j];
+            gq += s_ch[1][threadIdx.x * cpg + j];
+        }
+        const double n = (double)cpg * T;
+        const double mean = gs / n;
+        double var = gq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int q = threadIdx.x % Q, ph = threadIdx.x / Q;
+    const float4 gm = ldg4(gamma + q * 4), bt = ldg4(beta + q * 4);
+    float4 sc, sh;
+    {
+        const int g0 = (q * 4) / cpg, g1 = (q * 4 + 1) / cpg, g2 = (q * 4 + 2) / cpg, g3 = (q * 4 + 3) / cpg;
+        sc.x = s_rstd[g0] * gm.x; sh.x = bt.x - s_mean[g0] * sc.x;
+        sc.y = s_rstd[g1] * gm.y; sh.y = bt.y - s_mean[g1] * sc.y;
+        sc.z = s_rstd[g2] * gm.z; sh.z = bt.z - s_mean[g2] * sc.z;
+        sc.w = s_rstd[g3] * gm.w; sh.w = bt.w - s_mean[g3] * sc.w;
+    }
+    if (sp == 0 && ph == 0 && scale != nullptr) {
+        st4(scale + (long long)b * out_ld + out_off + q * 4, sc);
+        st4(shift + (long long)b * out_ld + out_off + q * 4, sh);
+    }
+    if (act_pair == nullptr && raw_pair == nullptr) return;
+    const int rows = (T + nsp - 1) / nsp;
+    const int t0 = sp * rows, t1 = min(T, t0 + rows);
+    const long long row0 = (long long)b * Tstr;
+    const float* xp = x + ((long long)(b % src_samples) * Tstr + t0 + ph) * C + q * 4;
+    const long long first = (row0 + t0 + ph) * (2LL * act_C) + act_off + q * 4;
+    const int step = PH * 2 * act_C;
+    __half* pa = act_pair != nullptr ? act_pair + first : nullptr;
+    __half* pr = raw_pair != nullptr ? raw_pair + first : nullptr;
+    float amax = 0.f;
+    auto put = [&](__half* p, const float4& v) {
+        amax = amax4(amax, v);
+        uint2 hi, lo;
+        split_pair4(v, hi, lo);
+        *reinterpret_cast<uint2*>(p) = hi;
+        *reinterpret_cast<uint2*>(p + act_C) = lo;
+    };
+    for (int t = t0 + ph; t < t1; t += 2 * PH) {
+        const bool two = t + PH < t1;
+        const float4 a = ldg4(xp);
+        const float4 d = two ? ldg4(xp + PH * C) : zero4();
+        xp += 2 * PH * C;
+        if (pa != nullptr) {
+            put(pa, make_float4(silu_fast(fmaf(a.x, sc.x, sh.x)), silu_fast(fmaf(a.y, sc.y, sh.y)), silu_fast(fmaf(a.z, sc.z, sh.z)),
+                                silu_fast(fmaf(a.w, sc.w, sh.w))));
+            if (two)
+                put(pa + step, make_float4(silu_fast(fmaf(d.x, sc.x, sh.x)), silu_fast(fmaf(d.y, sc.y, sh.y)),
+                                           silu_fast(fmaf(d.z, sc.z, sh.z)), silu_fast(fmaf(d.w, sc.w, sh.w))));
+            pa += 2 * (long long)step;
+        }
+        if (pr != nullptr) {
+            put(pr, a);
+            if (two) put(pr + step, d);
+            pr += 2 * (long long)step;
+        }
+    }
+    if (Tstr > T && sp == nsp - 1 && ph == 0) {      // the zero row between clips (Conv1d padding)
+        for (int t = T; t < Tstr; ++t) {
+            if (act_pair != nullptr) store_pair4_zero(act_pair, row0 + t, act_C, act_off + q * 4);
+            if (raw_pair != nullptr) store_pair4_zero(raw_pair, row0 + t, act_C, act_off + q * 4);
+        }
+    }
+    if (amax > P16_LIMIT) atomicOr(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ln192_pair_kernel(const float* __restrict__ x, int M, int Tstr, const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ y_pair,
