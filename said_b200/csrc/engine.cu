@@ -120,6 +120,15 @@ struct said_engine {
     bool pdl_small = getenv("SAID_NO_PDL_SMALL") == nullptr;
     bool gn_fused = getenv("SAID_GN_TWO_PASS") == nullptr;   // cluster GroupNorm (one launch); the env switch keeps the two-kernel version reachable for A/B timing
     cudaStream_t own_stream = nullptr;
+    // Two half-batches on two streams (fp16x3 path, mid-size batches): layer L+1 of one half starts on the SMs that layer L of the
+    // other half has already left, which hides part of the row-tile quantisation.  Measured (ms per step, split / whole): 32 clips
+    // (151 row tiles) 1.36 / 1.43, 48 clips (226) 1.72 / 1.77, 64 clips (301) 2.41 / 2.26 -- so it is used between
+    // split_min_tiles and split_max_tiles only.  Workspaces are the same buffers, one row range per half.
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    struct HalfCtx { int row_base, samp_base, clip_base, half; } hctx{0, 0, 0, 0};
+    int split_min_tiles = getenv("SAID_SPLIT_MIN_TILES") ? atoi(getenv("SAID_SPLIT_MIN_TILES")) : 150;
+    int split_max_tiles = getenv("SAID_SPLIT_MAX_TILES") ? atoi(getenv("SAID_SPLIT_MAX_TILES")) : 260;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     long long launches = 0;
 
@@ -186,13 +195,13 @@ struct said_engine {
     bool half_rows(int M) const { return !small_rows(M) && !mid_rows(M) && ((M + hx::HBM - 1) / hx::HBM) * 2 <= num_sms; }   // 50..74 row tiles: 96-column tiles
     // workspace of the fused feed-forward's split leftover tiles (ffn_h.cuh): partial accumulators + counters
     DevBuf ffn_part, ffn_sync;
+    static constexpr int FFN_SPLIT_TILES = 16;
     bool ffn_split = getenv("SAID_FFN_NOSPLIT") == nullptr;
     int ffn_min_tiles = getenv("SAID_FFN_MIN_TILES") ? atoi(getenv("SAID_FFN_MIN_TILES")) : 75;   // measured at 16 / 24 / 32 / 48 clips: 75 -> 0.95 / 1.06 / 1.43 / 1.78 ms per step, 148 -> 0.95 / 1.12 / 1.44 / 1.77, never -> 0.98 / 1.13 / 1.45 / 1.83
     int ensure_ffn_split(size_t M) {
-        const int tiles = (int)((M + hx::HBM - 1) / hx::HBM), grid = tiles < num_sms ? tiles : num_sms;
-        const int left = tiles - (tiles / grid) * grid;
-        CK(ffn_sync.ensure_zero(64));
-        if (left > 0) CK(ffn_part.ensure((size_t)left * hx::FFN_NP * hx::HBM * hx::FFN_C));
+        (void)M;   // fixed size: room for FFN_SPLIT_TILES leftover tiles per half-batch (two halves may run at once)
+        CK(ffn_sync.ensure_zero(2 * 64));
+        CK(ffn_part.ensure((size_t)2 * FFN_SPLIT_TILES * hx::FFN_NP * hx::HBM * hx::FFN_C));
         return 0;
     }
     template <class EP>
@@ -214,10 +223,10 @@ struct said_engine {
         p.trace = trace;
         {
             const int tiles = (M + hx::HBM - 1) / hx::HBM, grid = tiles < num_sms ? tiles : num_sms;
-            const size_t need = (size_t)(tiles - (tiles / grid) * grid) * hx::FFN_NP * hx::HBM * hx::FFN_C;
-            p.split = (ffn_split && ffn_sync.p != nullptr && ffn_part.cap >= need && need > 0) ? 1 : 0;
-            p.part = ffn_part.p;
-            p.sync = reinterpret_cast<int*>(ffn_sync.p);
+            const int left = tiles - (tiles / grid) * grid;
+            p.split = (ffn_split && ffn_sync.p != nullptr && ffn_part.p != nullptr && left > 0 && left <= FFN_SPLIT_TILES) ? 1 : 0;
+            p.part = ffn_part.p + (size_t)hctx.half * FFN_SPLIT_TILES * hx::FFN_NP * hx::HBM * hx::FFN_C;
+            p.sync = reinterpret_cast<int*>(ffn_sync.p) + hctx.half * 64;
         }
         ep.acc_scale = std::ldexp(1.0f, -w2.exp);
         cur_tag = tag;
@@ -455,6 +464,9 @@ struct said_engine {
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
         if (own_stream) cudaStreamDestroy(own_stream);
+        if (stream2) cudaStreamDestroy(stream2);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
     }
 
     // ------------------------------------------------------------------ weights
@@ -1799,15 +1811,20 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
         PdlScope(bool& p_, bool v) : p(p_), saved(p_) { p = v; }
         ~PdlScope() { p = saved; }
     } pdl_scope(pdl, pdl || (pdl_small && (small_rows(Mp) || mid_rows(Mp) || half_rows(Mp))));
-    float* h0 = act[0].p; float* h1 = act[1].p; float* A = act[2].p; float* Bb = act[3].p;
-    float* t1 = act[4].p; float* x1 = act[5].p; float* x2 = act[6].p;
-    float* sc_st = ss_st.p; float* sh_st = ss_st.p + (size_t)Bp * C;
-    __half* pgn = reinterpret_cast<__half*>(gnbuf.p);     // conv operand: silu(gn(x)), 192 or 384 columns
-    __half* praw = reinterpret_cast<__half*>(p_raw.p);    // raw concat [h | skip] (1x1 skip_connection operand), 384 columns
-    __half* pln = reinterpret_cast<__half*>(p_ln.p);      // LayerNorm outputs
-    __half* pao = reinterpret_cast<__half*>(ao.p);        // attention outputs
-    __half* px2 = reinterpret_cast<__half*>(p_x2.p);      // residual stream before the feed-forward, as an operand
-    __half* pff = reinterpret_cast<__half*>(ffb.p);       // GEGLU output, 768 columns
+    // (a half-batch works in its own row range of every workspace: hctx, set by denoise())
+    const size_t rowb = (size_t)hctx.row_base;
+    float* h0 = act[0].p + rowb * C; float* h1 = act[1].p + rowb * C; float* A = act[2].p + rowb * C; float* Bb = act[3].p + rowb * C;
+    float* t1 = act[4].p + rowb * C; float* x1 = act[5].p + rowb * C; float* x2 = act[6].p + rowb * C;
+    float* sc_st = ss_st.p + (size_t)hctx.samp_base * 2 * C; float* sh_st = sc_st + (size_t)Bp * C;
+    float* const qkv_p = qkv.p + rowb * 3 * C;
+    float* const q2_p = q2.p + rowb * C;
+    const float* const kv_p = kv.p + (size_t)hctx.clip_base * ctx_T * 8 * C;
+    __half* pgn = reinterpret_cast<__half*>(gnbuf.p) + rowb * 4 * C;     // conv operand: silu(gn(x)), 192 or 384 columns
+    __half* praw = reinterpret_cast<__half*>(p_raw.p) + rowb * 4 * C;    // raw concat [h | skip] (1x1 skip_connection operand), 384 columns
+    __half* pln = reinterpret_cast<__half*>(p_ln.p) + rowb * 2 * C;      // LayerNorm outputs
+    __half* pao = reinterpret_cast<__half*>(ao.p) + rowb * 2 * C;        // attention outputs
+    __half* px2 = reinterpret_cast<__half*>(p_x2.p) + rowb * 2 * C;      // residual stream before the feed-forward, as an operand
+    __half* pff = reinterpret_cast<__half*>(ffb.p) + rowb * 2 * FF;      // GEGLU output, 768 columns
     const float att_scale = 1.0f / sqrtf((float)HD);
     int tap_idx = 0;
     auto tap = [&](const float* p) -> int {
@@ -1901,7 +1918,7 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
         CKI(gnp(h, h_nb, h_nb, 6, 1e-6f, W.gn_g, W.gn_b, sc_st, sh_st, nullptr, nullptr, C, 0));
         CKI(ln_pair(h, mh, sc_st, sh_st, W.ln1_g, W.ln1_b, pln, nullptr));
         {   // q,k,v = LN1(GN(h)) W   (no bias)
-            EpiStd ep = mk_epi(qkv.p, 3 * C, 3 * C);
+            EpiStd ep = mk_epi(qkv_p, 3 * C, 3 * C);
             CKI(gemm_h(st, mh, 3 * C, {{psrc(pln, C, mh), 0, C, 0}}, W.wqkv, ep, TAG_GEMM_PLAIN));
         }
         cur_tag = TAG_ATTN;
@@ -1910,14 +1927,14 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
             const int nqt = (T + 127) / 128;
             const int zs = (ag == 1 && h_nb * HEADS * nqt <= num_sms) ? nqt : 1;                    // ... and one query tile per CTA while that fits a wave
             CK(launch_ex(hx::self_attention_h_kernel, dim3(HEADS / ag, h_nb, zs), dim3(hx::AH_THREADS * ag), hx::attention_h_smem_bytes(T, ag), st, pdl, 1,
-                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag,
+                         (const float*)qkv_p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag,
                          (uint32_t)hx::attention_h_group_bytes(T), (long long*)nullptr));
         } else if (T <= tc::ATC_MAXKEYS) {
             CK(launch_ex(tc::self_attention_tc_kernel, dim3(HEADS, h_nb), dim3(tc::ATC_THREADS), tc::attention_tc_smem_bytes(T), st, pdl, 1,
-                         (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag));
+                         (const float*)qkv_p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp, pao, status_flag));
         } else {
             CK(launch_ex(self_attention_kernel<32>, dim3((T + ATT_QTILE - 1) / ATT_QTILE, HEADS, h_nb), dim3(ATT_THREADS),
-                         attention_smem_bytes<32>(), st, pdl, 1, (const float*)qkv.p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp,
+                         attention_smem_bytes<32>(), st, pdl, 1, (const float*)qkv_p, 3 * C, 0, C, 2 * C, T, att_scale, (float*)nullptr, C, Tp,
                          pao, status_flag));
         }
         LAUNCH_CHECK();
@@ -1936,14 +1953,14 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
         const size_t r0 = (size_t)n_uncond * Tp;                           // ... in the full-batch tensors
         if (Mcp > 0) {   // cross-attention queries, conditional samples only
             CKI(ln_pair(x1 + x1c, Mcp, nullptr, nullptr, W.ln2_g, W.ln2_b, pln, nullptr));
-            EpiStd ep = mk_epi(q2.p, C, C);
+            EpiStd ep = mk_epi(q2_p, C, C);
             CKI(gemm_h(st, Mcp, C, {{psrc(pln, C, Mcp), 0, C, 0}}, W.wq2, ep, TAG_GEMM_LN));
         }
         {
             const long long tot = (long long)Bp * T * HEADS * 8;   // 8 lanes per (frame, head)
             cur_tag = TAG_XATTN;
-            CK(launch_ex(cross_attention_band_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, pdl, 1, (const float*)q2.p,
-                         (const float*)kv.p, 8 * C, i * 2 * C, (const int2*)band_dev, (const float*)(cnull.p + i * C), (const float*)x1, x2,
+            CK(launch_ex(cross_attention_band_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, pdl, 1, (const float*)q2_p,
+                         kv_p, 8 * C, i * 2 * C, (const int2*)band_dev, (const float*)(cnull.p + i * C), (const float*)x1, x2,
                          mh, n_uncond, Bp, T, Tp, ctx_T, att_scale, (float*)nullptr, pao, status_flag));
             LAUNCH_CHECK();
         }
@@ -2074,7 +2091,51 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
         sp.result = result_buf.p;       // engine-owned so that the cached graph does not depend on the caller's output tensor
         if (sp.mask && !sp.edit_noise) return fail("denoise: mask given without edit noise");
 
+        // two half-batches on two streams (see `stream2`): plain generation only -- per-step user tensors (variance noise,
+        // intermediates, editing) are indexed by the full batch inside the step kernel
+        const bool halves = use_h(Bp * T) && !prof_on && B >= 2 && split_min_tiles > 0 &&
+                            (Bp * (T + 1) + hx::HBM - 1) / hx::HBM >= split_min_tiles &&
+                            (Bp * (T + 1) + hx::HBM - 1) / hx::HBM <= split_max_tiles && !a.eta_noise_dev && !a.intermediates_dev &&
+                            !a.mask_dev && !a.edit_noise_dev;
+        if (halves && !stream2) {
+            CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
         auto one_step = [&]() -> int {
+            if (halves) {
+                const int mult = a.do_cfg ? 2 : 1;
+                CK(cudaEventRecord(ev_fork, st));
+                CK(cudaStreamWaitEvent(stream2, ev_fork, 0));
+                int rc = 0;
+                for (int hh = 0; hh < 2 && rc == 0; ++hh) {
+                    const int b0 = hh == 0 ? 0 : B / 2, bh = hh == 0 ? B / 2 : B - B / 2;
+                    cudaStream_t sh = hh == 0 ? st : stream2;
+                    hctx = HalfCtx{mult * b0 * (T + 1), mult * b0, b0, hh};
+                    float* eps_h = eps.p + (size_t)mult * b0 * n;
+                    rc = forward_h(sh, lat.p + (size_t)b0 * n, bh, mult * bh, a.do_cfg ? bh : 0, T, emb_tab.p, step_ctr, eps_h, nullptr);
+                    if (rc == 0) {
+                        StepParams sq = sp;
+                        sq.pred = eps_h;
+                        sq.latents = lat.p + (size_t)b0 * n;
+                        sq.init_latents = init_lat.p + (size_t)b0 * n;
+                        sq.result = result_buf.p + (size_t)b0 * n;
+                        sq.B = bh;
+                        cur_tag = TAG_STEP;
+                        cudaError_t le = launch_ex(ddim_step_kernel, dim3(bh, DDIM_SPLIT), dim3(256), 0, sh, pdl, 1, sq);
+                        if (le != cudaSuccess) rc = fail(std::string("step kernel launch failed: ") + cudaGetErrorString(le));
+                        else rc = after_launch(sh);
+                    }
+                }
+                hctx = HalfCtx{0, 0, 0, 0};
+                // (join even after an error: a capture in progress must see its forked stream rejoin)
+                cudaEventRecord(ev_join, stream2);
+                cudaStreamWaitEvent(st, ev_join, 0);
+                if (rc != 0) return rc;
+                CK(launch_ex(add_int_kernel, dim3(1), dim3(1), 0, st, pdl, 1, step_ctr, 1));
+                LAUNCH_CHECK();
+                return 0;
+            }
             if (use_h(Bp * T)) CKI(forward_h(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
             else CKI(forward(st, lat.p, B, Bp, a.do_cfg ? B : 0, T, emb_tab.p, step_ctr, eps.p, nullptr));
             cur_tag = TAG_STEP;
@@ -2088,7 +2149,7 @@ int said_engine::denoise(const said_denoise_args& a, cudaStream_t user) {
             GraphKey key;
             memset(&key, 0, sizeof(key));
             key.B = B; key.T = T; key.Tc = ctx_T; key.do_cfg = a.do_cfg; key.n_steps = sp.n_steps; key.pred_type = a.prediction_type;
-            key.scheduler = a.scheduler; key.precision = precision; key.tc_min_rows = tc_min_rows * 100003 + h_min_rows;
+            key.scheduler = a.scheduler; key.precision = precision; key.tc_min_rows = (tc_min_rows * 100003 + h_min_rows) * 2 + (halves ? 1 : 0);
             key.gscale = a.guidance_scale; key.grescale = a.guidance_rescale; key.latent_scale = a.latent_scale;
             key.eta_noise = a.eta_noise_dev; key.edit_noise = a.edit_noise_dev; key.mask = a.mask_dev;
             key.intermediates = a.intermediates_dev;
