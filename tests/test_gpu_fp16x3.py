@@ -321,3 +321,32 @@ def test_small_batch_default_path_vs_oracle(gpu_model, state_dict, B):
     print(f"small batch {B}: result vs oracle {e:.3e}, pre-clamp {ep:.3e}, vs FFMA kernels {ef:.3e}")
     assert e < 5e-4 and ep < 1e-3
     assert 0.0 < ef < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,seconds", [(3, 5.0), (5, 2.5), (7, 5.0), (9, 5.0), (13, 5.0), (21, 5.0), (27, 5.0), (33, 5.0), (41, 4.0), (2, 7.8)])
+def test_shape_sweep_default_vs_fp32_kernels(gpu_model, B, seconds):
+    """Odd batch sizes and clip lengths through every dispatch regime of the default path (32- / 64- / 96- / 192-column weight
+    tiles, two-GEMM and fused feed-forward with 0..n split leftover tiles, one head / one query tile per attention CTA, PDL, the
+    two-half-batch schedule with unequal halves) against the IEEE fp32 FFMA kernels of the same engine: 3 DDIM steps under CFG."""
+    from said_b200.synth import synthetic_batch
+
+    wave = synthetic_batch(B, seconds)
+    T = int(wave.shape[1] / 16000 * 60)
+    g = torch.Generator().manual_seed(100 + B)
+    noise = torch.randn(B, T, 32, generator=g)
+    m = gpu_model("epsilon")
+    eng = m._engine(torch.device(DEV))
+    eng.set_precision(m.precision, -1, m.encoder_precision)
+    out = _run(m, wave, noise, steps=3)
+    lat = out.latents.cpu()
+    m.tc_min_rows = 1 << 30
+    try:
+        lat_ffma = _run(m, wave, noise, steps=3).latents.cpu()
+    finally:
+        m.tc_min_rows = 0
+        eng.set_precision(m.precision, -1, m.encoder_precision)
+    e = maxdiff(lat, lat_ffma)
+    print(f"shape sweep B={B} T={T}: default vs FFMA kernels {e:.3e}")
+    assert bool(torch.isfinite(lat).all())
+    assert e < 1e-3
