@@ -25,6 +25,12 @@ def main():
     by_id = OrderedDict()
     for r in csv.DictReader(lines):
         m = r.get("Metric Name")
+        if m == "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed":
+            e = by_id.setdefault(r["ID"], [short(r["Kernel Name"]), 0.0, 0.0, False])
+            if len(e) < 5:
+                e.append(0.0)
+            e[4] = float(r["Metric Value"].replace(",", ""))
+            continue
         if m in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"):
             e = by_id.setdefault(r["ID"], [short(r["Kernel Name"]), 0.0, 0.0, False])
             v = float(r["Metric Value"].replace(",", "")) * unit.get(r.get("Metric Unit", "ns"), 1e-6 if m.startswith("gpu") else 1.0)
@@ -33,28 +39,28 @@ def main():
             else:
                 e[2] += v
                 e[3] = True
-    rows = [(e[0], e[1], e[2]) for e in by_id.values()]
+    rows = [(e[0], e[1], e[2], e[4] if len(e) > 4 else None) for e in by_id.values()]
     have_dram = any(e[3] for e in by_id.values())
-    split = max((i for i, (k, _, _) in enumerate(rows) if "prepare_latents_kernel" in k), default=-1)
+    have_tensor = any(len(e) > 4 for e in by_id.values())
+    split = max((i for i, r_ in enumerate(rows) if "prepare_latents_kernel" in r_[0]), default=-1)
     pre, loop = rows[: split + 1], rows[split + 1:]
     print(f"# {title}\n\nCommand: `{cmd}`\n(cold-cache, serialised launches: compare shares, not absolutes.)\n")
     for head, part in (("Loop iterations", loop), ("Once per batch: audio encoder + K/V hoist + tables", pre)):
         agg = OrderedDict()
-        for k, ms, by in part:
-            a = agg.setdefault(k, [0.0, 0, 0.0])
+        for k, ms, by, tp in part:
+            a = agg.setdefault(k, [0.0, 0, 0.0, 0.0])
             a[0] += ms
             a[1] += 1
             a[2] += by
+            a[3] += (tp or 0.0) * ms           # time-weighted tensor-pipe utilisation
         tot = sum(v[0] for v in agg.values())
         totb = sum(v[2] for v in agg.values())
         extra = f", {totb / 1e6:.0f} MB of DRAM traffic (read + write)" if have_dram else ""
         print(f"## {head}\n\n{len(part)} launches, {tot:.2f} ms{extra}.\n")
-        if have_dram:
-            print("| ms | share | launches | us / launch | DRAM MB / launch | kernel |\n|---:|---:|---:|---:|---:|---|")
-        else:
-            print("| ms | share | launches | us / launch | kernel |\n|---:|---:|---:|---:|---|")
-        for k, (ms, n, by) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-            mid = f" {by / n / 1e6:.1f} |" if have_dram else ""
+        hdr = "| ms | share | launches | us / launch |" + (" DRAM MB / launch |" if have_dram else "") + (" tensor pipe % |" if have_tensor else "") + " kernel |"
+        print(hdr + "\n|" + "---:|" * (hdr.count("|") - 2) + "---|")
+        for k, (ms, n, by, tpw) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            mid = (f" {by / n / 1e6:.1f} |" if have_dram else "") + (f" {tpw / ms if ms > 0 else 0.0:.1f} |" if have_tensor else "")
             print(f"| {ms:.3f} | {100 * ms / tot:.1f}% | {n} | {1000 * ms / n:.1f} |{mid} `{k}` |")
         print()
 
