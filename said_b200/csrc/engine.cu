@@ -197,6 +197,7 @@ struct said_engine {
     DevBuf ffn_part, ffn_sync;
     static constexpr int FFN_SPLIT_TILES = 16;
     bool ffn_split = getenv("SAID_FFN_NOSPLIT") == nullptr;
+    bool lean_epi = getenv("SAID_NO_LEAN_EPI") == nullptr;
     int ffn_min_tiles = getenv("SAID_FFN_MIN_TILES") ? atoi(getenv("SAID_FFN_MIN_TILES")) : 75;   // measured at 16 / 24 / 32 / 48 clips: 75 -> 0.95 / 1.06 / 1.43 / 1.78 ms per step, 148 -> 0.95 / 1.12 / 1.44 / 1.77, never -> 0.98 / 1.13 / 1.45 / 1.83
     int ensure_ffn_split(size_t M) {
         (void)M;   // fixed size: room for FFN_SPLIT_TILES leftover tiles per half-batch (two halves may run at once)
@@ -230,9 +231,29 @@ struct said_engine {
         }
         ep.acc_scale = std::ldexp(1.0f, -w2.exp);
         cur_tag = tag;
-        cudaError_t e = hx::launch_ffn_h(st, num_sms, p, w1.img, w2.img, bias1, status_flag, ep, pdl);
+        cudaError_t e;
+        if constexpr (std::is_same<EP, EpiStd>::value) {
+            const int F = lean_epi ? lean_flags(ep, hx::FFN_C) : -1;
+            if (F == 9) e = hx::launch_ffn_h(st, num_sms, p, w1.img, w2.img, bias1, status_flag, make_lean<9>(ep, hx::FFN_C), pdl);
+            else if (F == 1) e = hx::launch_ffn_h(st, num_sms, p, w1.img, w2.img, bias1, status_flag, make_lean<1>(ep, hx::FFN_C), pdl);
+            else e = hx::launch_ffn_h(st, num_sms, p, w1.img, w2.img, bias1, status_flag, ep, pdl);
+        } else {
+            e = hx::launch_ffn_h(st, num_sms, p, w1.img, w2.img, bias1, status_flag, ep, pdl);
+        }
         if (e != cudaSuccess) return fail(std::string("fused feed-forward launch failed: ") + cudaGetErrorString(e));
         return after_launch(st);
+    }
+    // EpiLean feature set of an EpiStd configuration, or -1 if it needs the general epilogue
+    static int lean_flags(const EpiStd& ep, int N) {
+        if (!ep.out || ep.acc_in || ep.out_pair || ep.out_period != 0 || ep.act != 0 || N % 192 != 0) return -1;
+        if (ep.emb && !ep.step_ptr) return -1;            // per-sample embedding rows (said_denoiser_forward): general epilogue
+        if (ep.res_scale && !ep.res) return -1;
+        return (ep.res ? 1 : 0) | (ep.res_scale ? 2 : 0) | (ep.emb ? 4 : 0) | (ep.res && ep.res_mod > 0 ? 8 : 0);
+    }
+    template <int F>
+    static EpiLean<F> make_lean(const EpiStd& ep, int N) {
+        return EpiLean<F>{ep.out, ep.ldo, N, ep.bias, ep.res, ep.ldr, ep.res_scale, ep.res_shift, ep.T > 0 ? ep.T : 1, ep.res_aff_ld,
+                          ep.acc_scale, ep.emb, ep.emb_ld, ep.step_ptr, ep.res_mod > 0 ? ep.res_mod : 1};
     }
     // One contraction on the fp16x3 path.  The K dimension is the concatenation of `segs`: columns [col0, col0 + ncols) of
     // the pair tensor `src` (C columns, `rows` rows), rows shifted by row_shift (Conv1d taps).  Weight = the image of `wkey`.
@@ -290,6 +311,26 @@ struct said_engine {
         ep.acc_scale = std::ldexp(1.0f, -w.exp);
         cur_tag = tag;
         cudaError_t e = cudaErrorInvalidValue;
+        if constexpr (std::is_same<EP, EpiStd>::value) {
+            // the epilogue with its feature set fixed at compile time (EpiLean): EpiStd::store4 tests nine run-time features per
+            // call, and on this kernel the epilogue warps' instruction count is on the critical path of every thin-K layer
+            int F = -1;
+            if (lean_epi && w.bn == 192) F = lean_flags(ep, N);
+            if (F >= 0) {
+                switch (F) {
+                    case 0: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<0>(ep, N), pdl); break;
+                    case 1: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<1>(ep, N), pdl); break;
+                    case 3: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<3>(ep, N), pdl); break;
+                    case 4: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<4>(ep, N), pdl); break;
+                    case 9: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<9>(ep, N), pdl); break;
+                    default: F = -1; break;
+                }
+                if (F >= 0) {
+                    if (e != cudaSuccess) return fail(std::string("fp16x3 gemm launch failed: ") + cudaGetErrorString(e));
+                    return after_launch(st);
+                }
+            }
+        }
         if (w.bn == 192) e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, ep, pdl);
         else if (w.bn == 128) e = hx::launch_gemm_h<128>(st, num_sms, p, w.img, ep, pdl);
         else if (w.bn == 96) e = hx::launch_gemm_h<96>(st, num_sms, p, w.img, ep, pdl);

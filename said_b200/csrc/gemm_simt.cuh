@@ -483,6 +483,60 @@ struct EpiStd {
     }
 };
 
+
+// Lean epilogue of the fp16x3 GEMM for its HBM / epilogue-bound layers (out-projections, q / k / v): what EpiStd does for
+//   out = acc * acc_scale + bias [+ residual [* scale + shift]]      (fp32 output, no remap, no embedding, no split-K)
+// with the feature set fixed at compile time (F bit 0: residual, bit 1: per-(sample, channel) affine on the residual).  EpiStd::store4
+// tests nine run-time features per call; on layers with 36 MMAs per tile the 12 calls per thread and tile are the critical path.
+template <int F>
+struct EpiLean {
+    float* out;
+    long long ldo;
+    int N;
+    const float* bias;
+    const float* res;
+    long long ldr;
+    const float* res_scale;
+    const float* res_shift;
+    int T, res_aff_ld;
+    float acc_scale;
+    const float* emb;        // F & 4: time-embedding projection row of the CURRENT step (the same for every row: a second bias)
+    long long emb_ld;
+    const int* step_ptr;
+    int res_mod;             // F & 8: the residual tensor has res_mod rows, row m reads row m % res_mod (shared CFG prefix)
+    struct RowCtx { const float* res; const float* sc; const float* sh; };
+    SAID_DEVINL bool tc_has_res() const { return (F & 1) != 0; }
+    SAID_DEVINL RowCtx tc_row(int m, int M) const {
+        RowCtx c;
+        const int mm = m < M ? m : M - 1;
+        c.res = (F & 1) ? res + (long long)((F & 8) ? mm % res_mod : mm) * ldr : nullptr;
+        const long long ao = (F & 2) ? (long long)(mm / T) * res_aff_ld : 0;
+        c.sc = (F & 2) ? res_scale + ao : nullptr;
+        c.sh = (F & 2) ? res_shift + ao : nullptr;
+        return c;
+    }
+    SAID_DEVINL float4 tc_prefetch4(const RowCtx& c, int n) const { return ldg4_l2pf(c.res + n); }
+    struct ColCtx { float4 bias; };
+    SAID_DEVINL ColCtx tc_col(int n) const {
+        float4 b = bias ? ldg4(bias + n) : zero4();
+        if (F & 4) {
+            const float4 e = ldg4(emb + (long long)(*step_ptr) * emb_ld + n);
+            b.x += e.x; b.y += e.y; b.z += e.z; b.w += e.w;
+        }
+        return ColCtx{b};
+    }
+    SAID_DEVINL void store4(const RowCtx& c, const ColCtx& cc, int m, int n, float4 a, float4 r) const {
+        a.x = fmaf(a.x, acc_scale, cc.bias.x); a.y = fmaf(a.y, acc_scale, cc.bias.y);
+        a.z = fmaf(a.z, acc_scale, cc.bias.z); a.w = fmaf(a.w, acc_scale, cc.bias.w);
+        if (F & 2) {
+            const float4 sc = ldg4(c.sc + n), sh = ldg4(c.sh + n);
+            r.x = fmaf(r.x, sc.x, sh.x); r.y = fmaf(r.y, sc.y, sh.y); r.z = fmaf(r.z, sc.z, sh.z); r.w = fmaf(r.w, sc.w, sh.w);
+        }
+        if (F & 1) { a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
+        st4(out + (long long)m * ldo + n, a);
+    }
+};
+
 // GEGLU (attention.py:25-32): weight columns are packed interleaved (2j = value_j, 2j+1 = gate_j),
 // out[m, j] = (acc[2j] + bv_j) * gelu(acc[2j+1] + bg_j);  bias is interleaved the same way.
 struct EpiGeglu {
