@@ -255,6 +255,17 @@ struct said_engine {
         return EpiLean<F>{ep.out, ep.ldo, N, ep.bias, ep.res, ep.ldr, ep.res_scale, ep.res_shift, ep.T > 0 ? ep.T : 1, ep.res_aff_ld,
                           ep.acc_scale, ep.emb, ep.emb_ld, ep.step_ptr, ep.res_mod > 0 ? ep.res_mod : 1};
     }
+    template <int BN>
+    bool launch_lean(int F, cudaStream_t st, const hx::HParams& p, const uint8_t* img, const EpiStd& ep, int N, cudaError_t* e) {
+        switch (F) {
+            case 0: *e = hx::launch_gemm_h<BN>(st, num_sms, p, img, make_lean<0>(ep, N), pdl); return true;
+            case 1: *e = hx::launch_gemm_h<BN>(st, num_sms, p, img, make_lean<1>(ep, N), pdl); return true;
+            case 3: *e = hx::launch_gemm_h<BN>(st, num_sms, p, img, make_lean<3>(ep, N), pdl); return true;
+            case 4: *e = hx::launch_gemm_h<BN>(st, num_sms, p, img, make_lean<4>(ep, N), pdl); return true;
+            case 9: *e = hx::launch_gemm_h<BN>(st, num_sms, p, img, make_lean<9>(ep, N), pdl); return true;
+            default: return false;
+        }
+    }
     // One contraction on the fp16x3 path.  The K dimension is the concatenation of `segs`: columns [col0, col0 + ncols) of
     // the pair tensor `src` (C columns, `rows` rows), rows shifted by row_shift (Conv1d taps).  Weight = the image of `wkey`.
     struct HSrc { const __half* base; int C; long long rows; long long pitch_halfs = 0; /* 0: 2 * C */ };
@@ -314,17 +325,15 @@ struct said_engine {
         if constexpr (std::is_same<EP, EpiStd>::value) {
             // the epilogue with its feature set fixed at compile time (EpiLean): EpiStd::store4 tests nine run-time features per
             // call, and on this kernel the epilogue warps' instruction count is on the critical path of every thin-K layer
-            int F = -1;
-            if (lean_epi && w.bn == 192) F = lean_flags(ep, N);
+            int F = lean_epi ? lean_flags(ep, N) : -1;
             if (F >= 0) {
-                switch (F) {
-                    case 0: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<0>(ep, N), pdl); break;
-                    case 1: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<1>(ep, N), pdl); break;
-                    case 3: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<3>(ep, N), pdl); break;
-                    case 4: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<4>(ep, N), pdl); break;
-                    case 9: e = hx::launch_gemm_h<192>(st, num_sms, p, w.img, make_lean<9>(ep, N), pdl); break;
-                    default: F = -1; break;
-                }
+                bool done = true;
+                if (w.bn == 192) done = launch_lean<192>(F, st, p, w.img, ep, N, &e);
+                else if (w.bn == 96) done = launch_lean<96>(F, st, p, w.img, ep, N, &e);
+                else if (w.bn == 64) done = launch_lean<64>(F, st, p, w.img, ep, N, &e);
+                else if (w.bn == 32) done = launch_lean<32>(F, st, p, w.img, ep, N, &e);
+                else done = false;
+                if (!done) F = -1;
                 if (F >= 0) {
                     if (e != cudaSuccess) return fail(std::string("fp16x3 gemm launch failed: ") + cudaGetErrorString(e));
                     return after_launch(st);
