@@ -1760,6 +1760,7 @@ int said_engine::forward(cudaStream_t st, const float* x, int src_batch, int Bp,
         }
         {
             const long long tot = (long long)M * HEADS * 8;   // 8 lanes per (row, head)
+            if (tot >= (1LL << 31)) return fail("cross-attention: batch x frames exceeds the kernel's 32-bit index range");
             cur_tag = TAG_XATTN;
             CK(launch_ex(cross_attention_band_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, pdl, 1, (const float*)q2.p,
                          (const float*)kv.p, 8 * C, i * 2 * C, (const int2*)band_dev, (const float*)(cnull.p + i * C), (const float*)x1, x2,
@@ -2008,6 +2009,7 @@ int said_engine::forward_h(cudaStream_t st, const float* x, int src_batch, int B
         }
         {
             const long long tot = (long long)Bp * T * HEADS * 8;   // 8 lanes per (frame, head)
+            if (tot >= (1LL << 31) || (long long)Bp * (T + 1) >= (1LL << 31)) return fail("cross-attention: batch x frames exceeds the kernel's 32-bit index range");
             cur_tag = TAG_XATTN;
             CK(launch_ex(cross_attention_band_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, pdl, 1, (const float*)q2_p,
                          kv_p, 8 * C, i * 2 * C, (const int2*)band_dev, (const float*)(cnull.p + i * C), (const float*)x1, x2,

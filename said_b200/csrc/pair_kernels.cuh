@@ -376,14 +376,15 @@ cross_attention_band_kernel(const float* __restrict__ q, const float* __restrict
     constexpr int C = 192, HD = 32, H = 6;
     pdl_wait();
     pdl_trigger();
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long idx = gid >> 3;                       // (sample, frame, head) over the VALID frames
+    // (32-bit index arithmetic: the host checks Bp * T * H * 8 < 2^31; the 64-bit divisions this replaces were a third of the kernel)
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned idx = gid >> 3;                        // (sample, frame, head) over the VALID frames
     const int j8 = (int)(gid & 7);
-    const bool live = idx < (long long)Bp * T * H;        // dead lanes still take part in the shuffles
-    const long long ci = live ? idx : 0;
+    const bool live = idx < (unsigned)(Bp * T * H);       // dead lanes still take part in the shuffles
+    const unsigned ci = live ? idx : 0u;
     const int h = (int)(ci % H);
-    const long long vr = ci / H;
-    const int b = (int)(vr / T), t = (int)(vr - (long long)b * T);
+    const unsigned vr = ci / H;
+    const int b = (int)(vr / (unsigned)T), t = (int)(vr - (unsigned)b * (unsigned)T);
     const long long row = (long long)b * Tstr + t;        // row in the (padded) activation buffers
     const int col = h * HD + j8 * 4;
     const bool uncond = b < n_uncond;
@@ -391,7 +392,7 @@ cross_attention_band_kernel(const float* __restrict__ q, const float* __restrict
     float4 qv = zero4();
     const float* kr = kv;
     if (live && uncond) {
-        const float4 a = ldg4(x_res + (row % res_rows) * C + col), c4 = ldg4(c_null + col);   // x_res may hold only the shared samples
+        const float4 a = ldg4(x_res + (long long)((unsigned)row % (unsigned)res_rows) * C + col), c4 = ldg4(c_null + col);   // x_res may hold only the shared samples
         st4(x_out + row * C + col, make_float4(a.x + c4.x, a.y + c4.y, a.z + c4.z, a.w + c4.w));
     } else if (live) {
         const int2 bd = __ldg(band + t);
@@ -419,20 +420,22 @@ cross_attention_band_kernel(const float* __restrict__ q, const float* __restrict
     }
     if (!live || uncond) return;
     float m = -INFINITY;
+    const float sl2 = scale * 1.4426950408889634f;        // softmax in base 2 on the hardware exp2 unit
 #pragma unroll
     for (int j = 0; j < XATT_MAXW; ++j)
-        if (j < cnt) { s[j] *= scale; m = fmaxf(m, s[j]); }
+        if (j < cnt) { s[j] *= sl2; m = fmaxf(m, s[j]); }
     float den = 0.f;
     float4 acc = zero4();
 #pragma unroll
     for (int j = 0; j < XATT_MAXW; ++j)
         if (j < cnt) {
-            const float pj = expf(s[j] - m);
+            float pj;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pj) : "f"(s[j] - m));
             den += pj;
             acc.x = fmaf(pj, vv[j].x, acc.x); acc.y = fmaf(pj, vv[j].y, acc.y);
             acc.z = fmaf(pj, vv[j].z, acc.z); acc.w = fmaf(pj, vv[j].w, acc.w);
         }
-    const float inv = 1.0f / den;
+    const float inv = __fdividef(1.0f, den);
     acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     if (out_pair != nullptr) {
         store_pair4(out_pair, row, C, col, acc);
