@@ -13,7 +13,7 @@ from said_b200.synth import synthetic_batch, synthetic_state_dict  # noqa: E402
 m = SAID_UNet1D()
 m.load_state_dict(synthetic_state_dict(0))
 m.to("cuda:0").eval()
-for B in (1, 8, 12, 16, 32):
+for B in (1, 2, 4, 8, 12):
     wave = synthetic_batch(B, 5.0).to("cuda:0")
     res = {}
     for name, rows in (("tensor-core", 1),):
