@@ -250,9 +250,11 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 qreg[u][1] = ok ? ldg4(src + 4) : zero4();
             }
         };
-        load_q(qt_begin);
-        for (int qt = qt_begin; qt < qt_end; ++qt) {
-            // ---------------- Q tile: 128 rows x [hi | lo], pre-scaled ----------------
+        // Q tile: 128 rows x [hi | lo], pre-scaled, from the prefetched registers; then the tile's first S GEMM.  For every tile but the
+        // first this runs BEFORE the previous tile's output epilogue (the Q buffer is free once the last S GEMM of a tile has
+        // completed, and the tensor pipe executes S(next) after P V(last), which reads the columns S(next) overwrites): the GEMM
+        // and its hand-off latency overlap the epilogue instead of following it.
+        auto stage_q_and_issue = [&]() {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int i = tid + u * AH_SM_THREADS, r = i >> 2, c2 = i & 3;
@@ -264,8 +266,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 sts16(ra + (uint32_t)((c2 ^ (r & 7)) << 4), hi);
                 sts16(ra + (uint32_t)(((4 + c2) ^ (r & 7)) << 4), lo);
             }
-            if (qt + 1 < qt_end) load_q(qt + 1);               // in flight during this tile's MMAs and softmax
-            tc_fence_before();                                 // (TMEM reads of the previous tile's O are complete)
+            tc_fence_before();
             tc::fence_proxy_async();
             mbar_arrive(bar_q);
             if (warp == 0) {
@@ -275,6 +276,11 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 if (tc::elect_one()) issue_s(0);
             }
             __syncwarp();
+        };
+        load_q(qt_begin);
+        stage_q_and_issue();
+        for (int qt = qt_begin; qt < qt_end; ++qt) {
+            if (qt + 1 < qt_end) load_q(qt + 1);               // in flight during this tile's MMAs and softmax
             float m_run = -INFINITY, l_part = 0.f;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int nvalid = min(AH_KB, T - kb * AH_KB);         // valid keys of this block
@@ -367,6 +373,7 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 }
                 __syncwarp();
             }
+            if (qt + 1 < qt_end) stage_q_and_issue();          // next tile's Q and first S GEMM, under this tile's epilogue
             // ---------------- O / rowsum -> global ----------------
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(AH_SM_THREADS + tid) * 4u), "f"(l_part) : "memory");
             stamp();
