@@ -49,6 +49,10 @@ SAID_DEVINL void tmem_st32u(uint32_t taddr, const uint32_t (&v)[32]) {
           "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+SAID_DEVINL void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 SAID_DEVINL uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -325,27 +329,31 @@ self_attention_h_kernel(const float* __restrict__ qkv, int ld, int q_off, int k_
                 const float m_new = fmaxf(m_run, fmaxf(mx, other));
                 const float alpha = ex2f(m_run - m_new);                // 0 on the first block (m_run = -inf)
                 m_run = m_new;
-                // P = 2^(s - m) as packed fp16 hi / lo, written over the score columns
-                uint32_t ph[32], pl[32];
+                // P = 2^(s - m) as packed fp16 hi / lo, written over the score columns 16 scores (8 + 8 packed words) at a time: holding
+                // all 64 packed words next to the 64 scores spilled half of the scores to local memory inside this loop
                 float ls0 = 0.f, ls1 = 0.f;
-                if (have) {
 #pragma unroll
-                    for (int w = 0; w < 32; ++w) {
-                        const float p0 = ex2f(s[w >> 3][(2 * w) & 15] - m_new), p1 = ex2f(s[w >> 3][(2 * w + 1) & 15] - m_new);
-                        ls0 += p0;
-                        ls1 += p1;
-                        const __half2 hh = __floats2half2_rn(p0, p1);
-                        const float2 hf = __half22float2(hh);
-                        ph[w] = *reinterpret_cast<const uint32_t*>(&hh);
-                        pl[w] = pack_h2(p0 - hf.x, p1 - hf.y);
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t ph[8], pl[8];
+                    if (have) {
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) {
+                            const float p0 = ex2f(s[u][2 * w] - m_new), p1 = ex2f(s[u][2 * w + 1] - m_new);
+                            ls0 += p0;
+                            ls1 += p1;
+                            const __half2 hh = __floats2half2_rn(p0, p1);
+                            const float2 hf = __half22float2(hh);
+                            ph[w] = *reinterpret_cast<const uint32_t*>(&hh);
+                            pl[w] = pack_h2(p0 - hf.x, p1 - hf.y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) { ph[w] = 0u; pl[w] = 0u; }
                     }
-                } else {
-#pragma unroll
-                    for (int w = 0; w < 32; ++w) { ph[w] = 0u; pl[w] = 0u; }
+                    tmem_st8u(trow + AH_S_COL + part * 32 + 8 * u, ph);
+                    tmem_st8u(trow + AH_S_COL + 64 + part * 32 + 8 * u, pl);
                 }
                 l_part = l_part * alpha + (ls0 + ls1);
-                tmem_st32u(trow + AH_S_COL + part * 32, ph);
-                tmem_st32u(trow + AH_S_COL + 64 + part * 32, pl);
                 // rescale the running output when the maximum moved (warp-uniform decision: tcgen05.ld/st are warp-wide)
                 if (kb > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
                     float o0[16], o1[16], o[32];
