@@ -324,7 +324,7 @@ def test_small_batch_default_path_vs_oracle(gpu_model, state_dict, B):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,seconds", [(3, 5.0), (5, 2.5), (7, 5.0), (9, 5.0), (13, 5.0), (21, 5.0), (27, 5.0), (33, 5.0), (41, 4.0), (2, 7.8)])
+@pytest.mark.parametrize("B,seconds", [(3, 5.0), (5, 2.5), (7, 5.0), (9, 5.0), (13, 5.0), (21, 5.0), (27, 5.0), (33, 5.0), (41, 4.0), (2, 7.8), (2, 9.0), (20, 9.0)])
 def test_shape_sweep_default_vs_fp32_kernels(gpu_model, B, seconds):
     """Odd batch sizes and clip lengths through every dispatch regime of the default path (32- / 64- / 96- / 192-column weight
     tiles, two-GEMM and fused feed-forward with 0..n split leftover tiles, one head / one query tile per attention CTA, PDL, the
